@@ -1,0 +1,164 @@
+/*
+ * vo_b200.h -- C ABI of libvo_b200.so: the B200 (sm_100a) implementation of the per-frame hot
+ * path of ivario123/r7020e-visual-odometry (a MATLAB stereo visual-odometry script).
+ *
+ * The reference has no FFI of its own: its hot path is six MathWorks toolbox calls.  Each entry
+ * point below replaces one call site; the MEX gateways (csrc/mex/vo_*_mex.cpp) and the Python
+ * mirror (api.py) only marshal arguments onto these functions.
+ *
+ *   vo_sift         <- detectSIFTFeatures + extractFeatures(...,"Method","SIFT")   VO.m:79-84
+ *   vo_match        <- matchFeatures(f1, f2)                      VO.m:87, 283, 293, 311, 323
+ *   vo_triangulate  <- triangulate(p_l, p_r, p1, p2)    VO.m:114-115, CreateLandmarksFromFeatures.m:7
+ *   vo_p3p          <- estworldpose(imagePoints, worldPoints, intrinsics)         VO.m:123-127
+ *   vo_frames       <- one pass of the `for i = 1:n_frames` body over a batch     VO.m:64-232
+ *
+ * Conventions: plain pointers and sizes only.  Host-pointer entry points copy in/out and
+ * synchronise before returning (what a MEX call needs).  `_dev` entry points take device pointers
+ * and a cudaStream_t (as void*) and do not synchronise.  Every function returns 0 on success or
+ * a negative vo_status; vo_last_error() gives the message (thread-local).  There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with VO_ERR_CUDA.
+ */
+#ifndef VO_B200_H
+#define VO_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vo_ctx vo_ctx;
+
+enum vo_status {
+  VO_OK = 0,
+  VO_ERR_ARG = -1,      /* bad argument (null pointer, bad size/class)            */
+  VO_ERR_CUDA = -2,     /* CUDA runtime/driver failure, or no device              */
+  VO_ERR_CAPACITY = -3, /* caller-provided capacity too small                     */
+  VO_ERR_STATE = -4     /* call sequence error                                    */
+};
+
+int vo_version(void);
+const char* vo_last_error(void);
+int vo_ctx_create(int device, vo_ctx** ctx);
+void vo_ctx_destroy(vo_ctx* ctx);
+int vo_ctx_sync(vo_ctx* ctx);
+/* stream used by the host-pointer entry points (cudaStream_t) */
+void* vo_ctx_stream(vo_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------ SIFT */
+typedef struct {
+  float contrast_threshold; /* MATLAB ContrastThreshold (per layer); <= 0 -> 0.04/3          */
+  float edge_threshold;     /* MATLAB EdgeThreshold; <= 0 -> 10                               */
+  int num_layers_in_octave; /* MATLAB NumLayersInOctave; <= 0 -> 3                            */
+  float sigma;              /* MATLAB Sigma; <= 0 -> 1.6                                      */
+  int index_base;           /* 0: OpenCV pt; 1: MATLAB Location (adds 1 to x and y)           */
+} vo_sift_opts;
+
+/* One keypoint record, OpenCV KeyPoint fields (MATLAB SIFTPoints: Scale = size/2,
+ * Orientation = angle*pi/180, Metric = response, Octave/Layer unpacked from `octave`). */
+typedef struct {
+  float x, y;
+  float size;
+  float angle;
+  float response;
+  int32_t octave; /* (octave & 255) | layer << 8 | round((xi+0.5)*255) << 16                  */
+} vo_keypoint;
+
+/* img: rows x cols uint8.  col_major = 0: C layout, element (r,c) at img[r*ld + c];
+ * col_major = 1: MATLAB layout, element (r,c) at img[c*ld + r].
+ * kps[capacity], desc[capacity*128] (row-major, one 128-float descriptor per keypoint, integer
+ * valued 0..255 like OpenCV/MATLAB SIFT).  *n_out = number of keypoints found; if it exceeds
+ * capacity the first `capacity` (in output order: ascending x) are returned with VO_ERR_CAPACITY. */
+int vo_sift(vo_ctx* ctx, const uint8_t* img, int rows, int cols, int ld, int col_major,
+            const vo_sift_opts* opts, int capacity, vo_keypoint* kps, float* desc, int* n_out);
+
+/* n_img images of identical size, contiguous (image stride rows*cols, row-major).
+ * kps[n_img*capacity], desc[n_img*capacity*128], n_out[n_img]. */
+int vo_sift_batch(vo_ctx* ctx, const uint8_t* imgs, int n_img, int rows, int cols,
+                  const vo_sift_opts* opts, int capacity, vo_keypoint* kps, float* desc,
+                  int* n_out);
+
+/* ----------------------------------------------------------------------------------- match */
+typedef struct {
+  float match_threshold; /* MATLAB MatchThreshold in percent; <= 0 -> 1.0 (SSD <= 0.04)      */
+  float max_ratio;       /* MATLAB MaxRatio; <= 0 -> 0.6                                      */
+  int unique;            /* MATLAB Unique (forward-backward consistency); default 0           */
+  int index_base;        /* 0 or 1 (MATLAB)                                                   */
+} vo_match_opts;
+
+/* f1: n1 x dim, f2: n2 x dim float32 (dim <= 256).  col_major = 1: MATLAB layout (element (i,k)
+ * at f[k*n + i]).  idx1/idx2/metric: capacity n1 entries; rows ascending in idx1.
+ * indexPairs(:,1) = idx1, indexPairs(:,2) = idx2, matchMetric = metric (may be NULL). */
+int vo_match(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2, int dim,
+             int col_major, const vo_match_opts* opts, uint32_t* idx1, uint32_t* idx2,
+             float* metric, int* n_pairs);
+
+/* Per-row nearest / second nearest before thresholding (diagnostic + relocalisation shards):
+ * j1[n1] (0-based, UINT32_MAX when n2 == 0), s1[n1], s2[n1] (INF when n2 < 2). */
+int vo_match_top2(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2, int dim,
+                  int col_major, uint32_t* j1, float* s1, float* s2);
+
+/* Device-pointer variant: f1_dev/f2_dev row-major float32 in device memory; outputs device
+ * arrays of n1 entries; n_pairs_dev device int.  Runs on `stream`, no synchronisation. */
+int vo_match_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, int n2, int dim,
+                 const vo_match_opts* opts, uint32_t* idx1_dev, uint32_t* idx2_dev,
+                 float* metric_dev, int* n_pairs_dev, void* stream);
+int vo_match_top2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, int n2,
+                      int dim, uint32_t* j1_dev, float* s1_dev, float* s2_dev, void* stream);
+
+/* counters of the last vo_match / vo_match_top2 call on this ctx (after synchronisation):
+ * stats[0] = 1 if the exact-integer bf16 path ran (0: split-bf16 general path),
+ * stats[1] = rows re-evaluated by the exact FP32 row scan, stats[2] = GEMM kernel launches,
+ * stats[3] = K extent of the GEMM. */
+int vo_match_stats(vo_ctx* ctx, int stats[4]);
+
+/* Debug/unit-test hook: raw tensor-core dot products C = f1 * f2^T (n1 x n2 float32, row-major
+ * host output), computed by the same tcgen05 pipeline as vo_match. */
+int vo_match_debug_gemm(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2, int dim,
+                        float* c_out);
+
+/* ----------------------------------------------------------------------------- triangulate */
+/* pts1/pts2: n x 2 (is_double ? double : float), row-major (col_major = 1: MATLAB n x 2 column
+ * major).  P1, P2: 3x4 row-major double.  xyz: n x 3 in the class of the points, same majorness.
+ * reproj_err (n, same class) and valid (n bytes) may be NULL. */
+int vo_triangulate(vo_ctx* ctx, const void* pts1, const void* pts2, int n, int is_double,
+                   int col_major, const double P1[12], const double P2[12], void* xyz,
+                   void* reproj_err, uint8_t* valid);
+
+/* ------------------------------------------------------------------------------- P3P MSAC */
+typedef struct {
+  int max_num_trials;      /* MATLAB MaxNumTrials; <= 0 -> 1000                              */
+  double confidence;       /* MATLAB Confidence (percent); <= 0 -> 99                         */
+  double max_reproj_error; /* MATLAB MaxReprojectionError (pixels); <= 0 -> 1                 */
+  uint64_t seed;           /* counter-based RNG seed (the reference never seeds MATLAB's RNG) */
+  int adaptive;            /* < 0 -> 1 (MSAC adaptive trial bound); 0: run every trial        */
+} vo_p3p_opts;
+
+/* img: n x 2 double pixels, world: n x 3 double (col_major = 1: MATLAB layout), K = {fx,fy,cx,cy}.
+ * A: 4x4 camera-to-world pose, row-major (col_major = 1: column-major, ready for rigidtform3d).
+ * inliers: n bytes (may be NULL).  *status: 0 ok, 1 fewer than 4 points, 2 not enough inliers.
+ * info (may be NULL): {n_inliers, best_trial, trials_run}. */
+int vo_p3p(vo_ctx* ctx, const double* img, const double* world, int n, int col_major,
+           const double K[4], const vo_p3p_opts* opts, double A[16], uint8_t* inliers,
+           int* status, int info[3]);
+
+/* ------------------------------------------------------------------------- frame pipeline */
+typedef struct {
+  vo_sift_opts sift;
+  vo_match_opts match;
+  vo_p3p_opts p3p;
+  int max_keypoints;   /* per-image capacity; <= 0 -> 8192 */
+} vo_frames_opts;
+
+/* One pass of the VO.m loop body over n_frames consecutive stereo frames held in host memory
+ * (left/right: n_frames x rows x cols uint8).  Frame 0 only seeds the tracker (VO.m:207-210);
+ * for frame i >= 1: SIFT x2, stereo match, find_remaining_points against frame i-1, batched
+ * triangulation, P3P-MSAC.  rel_pose[16*i] = rel_pose.A of frame i (row-major; identity for
+ * i = 0), status[i] = estworldpose status, counts[6*i..] = {N_L, N_R, stereo, K1..K4 -> K4, inl}.
+ * The pose chain pose = pose * rel_pose (VO.m:130) is left to the caller: it is sequential. */
+int vo_frames(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_frames, int rows,
+              int cols, const double P1[12], const double P2[12], const vo_frames_opts* opts,
+              double* rel_pose, int* status, int* counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,94 @@
+// vo_internal.h -- shared internals of libvo_b200.so (context, error handling, scratch buffers).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+#include <map>
+#include <string>
+#include "../../include/vo_b200.h"
+
+namespace vo {
+
+void set_error(const char* fmt, ...);
+
+#define VO_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      vo::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      return VO_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define VO_CHECK_ARG(cond, msg)                      \
+  do {                                               \
+    if (!(cond)) {                                   \
+      vo::set_error("bad argument: %s", msg);        \
+      return VO_ERR_ARG;                             \
+    }                                                \
+  } while (0)
+
+#define VO_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != VO_OK) return _r; \
+  } while (0)
+
+// A named, grow-only device (or pinned-host) scratch buffer owned by the context.
+struct Scratch {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  bool host = false;
+};
+
+struct SiftPlan;   // vo_sift.cu
+struct FramePlan;  // vo_frames.cu
+
+}  // namespace vo
+
+struct vo_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  std::map<std::string, vo::Scratch> scratch;
+  int match_stats[4] = {0, 0, 0, 0};
+  vo::SiftPlan* sift_plan = nullptr;
+  vo::FramePlan* frame_plan = nullptr;
+
+  // returns a device buffer of at least `bytes` (contents undefined), grown geometrically
+  int dev(const char* name, size_t bytes, void** out);
+  int pinned(const char* name, size_t bytes, void** out);
+};
+
+namespace vo {
+template <typename T>
+inline int dev_buf(vo_ctx* c, const char* name, size_t count, T** out) {
+  void* p = nullptr;
+  int r = c->dev(name, count * sizeof(T), &p);
+  *out = static_cast<T*>(p);
+  return r;
+}
+template <typename T>
+inline int pin_buf(vo_ctx* c, const char* name, size_t count, T** out) {
+  void* p = nullptr;
+  int r = c->pinned(name, count * sizeof(T), &p);
+  *out = static_cast<T*>(p);
+  return r;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled();
+
+void sift_plan_destroy(SiftPlan*);
+void frame_plan_destroy(FramePlan*);
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+}  // namespace vo

@@ -1,0 +1,831 @@
+// vo_match.cu -- matchFeatures(f1, f2) on B200 (replaces VO.m:87, 283, 293, 311, 323).
+//
+// Pipeline (all on one stream, no host round trip between kernels):
+//   1. match_prep_kernel (x2)  rows -> 1/||row|| (oracle fmaf order), bf16 hi/lo split operands
+//                              A' = [hi | hi | lo], B' = [hi | lo | hi] (K-major), and a device
+//                              flag "some value is not an integer in 0..255".
+//   2. match_topk_kernel       tcgen05 GEMM C = A' B'^T with fp32 accumulators in TMEM, operands
+//                              staged by TMA (128B swizzle), warp-specialised: 1 TMA warp, 1 MMA
+//                              warp, 8 epilogue warps.  When every value is an integer 0..255 only
+//                              the first K columns are contracted and C is the EXACT dot product;
+//                              otherwise all 3K columns (hi*hi + hi*lo + lo*hi).  The epilogue
+//                              never stores C: it scales by 1/||b_j|| and keeps the per-row top-3
+//                              (key, column) in registers across all column tiles.
+//   3. match_finalize_kernel   merges the per-split candidates, recomputes the oracle's exact FP32
+//                              score for the three candidates, and certifies the row: every
+//                              non-candidate has key <= k3 (+eps on the split path), and the score
+//                              is a monotone function of the key, so if f(k3) > s1 the nearest
+//                              neighbour (lowest index on ties) and s2 are exactly the oracle's.
+//   4. match_rowscan_kernel    rows that could not be certified (3-way ties, near-ties on the
+//                              split path) are re-evaluated by an exact FP32 scan of all columns.
+//   5. select/compact          threshold + ratio (+ Unique) tests, ordered compaction.
+//
+// Score arithmetic is the contract in oracle/match.c (DESIGN.md "match arithmetic").
+#include "vo_internal.h"
+#include <cuda_bf16.h>
+#include <cfloat>
+
+namespace vo {
+
+constexpr int BM = 128;                       // rows per CTA == UMMA M
+constexpr int BN = 256;                       // columns per tile == UMMA N
+constexpr int BK = 64;                        // bf16 per 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_KBLOCK_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;    // 32 KB
+constexpr int MAX_KBLOCKS = 6;                // K' <= 384  (dim <= 128 split, or dim <= 384 exact)
+constexpr int B_STAGES = 4;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
+constexpr int NCAND = 3;
+constexpr int SMEM_BYTES = MAX_KBLOCKS * A_KBLOCK_BYTES + B_STAGES * B_STAGE_BYTES + 1024 + 256;
+constexpr float SPLIT_EPS = 1.0f / 8192.0f;   // |approx key - oracle key| <= 2^-13 * ||a||
+
+// ------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand tile, 128-byte swizzle: 8-row groups are 1024 B apart (SBO), LBO unused (=1).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct Top3 {
+  float k1, k2, k3;
+  uint32_t i1, i2, i3;
+  __device__ __forceinline__ void init() {
+    k1 = k2 = k3 = -INFINITY;
+    i1 = i2 = i3 = 0xFFFFFFFFu;
+  }
+  // strict '>' keeps the lowest column among equal keys when columns arrive in ascending order
+  __device__ __forceinline__ void insert(float v, uint32_t j) {
+    if (v > k1) { k3 = k2; i3 = i2; k2 = k1; i2 = i1; k1 = v; i1 = j; }
+    else if (v > k2) { k3 = k2; i3 = i2; k2 = v; i2 = j; }
+    else { k3 = v; i3 = j; }
+  }
+};
+
+// ------------------------------------------------------------------------- the GEMM kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const float* __restrict__ invb, const int* __restrict__ n1p,
+                  const int* __restrict__ n2p, const int* __restrict__ nonint_flag, int kp_blocks,
+                  int n_splits, uint2* __restrict__ cand, float* __restrict__ dbg_c, int dbg_ld) {
+  extern __shared__ uint8_t smem_raw[];
+  const int n1 = *n1p, n2 = *n2p;
+  const int m0 = blockIdx.x * BM;
+  if (m0 >= n1) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_total = (n2 + BN - 1) / BN;
+  const int split = blockIdx.y;
+  const int t_begin = (int)((long long)split * tiles_total / n_splits);
+  const int t_end = (int)((long long)(split + 1) * tiles_total / n_splits);
+  const int n_slots = n_splits * 2;
+
+  if (t_begin >= t_end) {  // nothing to contract: publish empty candidate slots
+    if (warp >= 2) {
+      const int e = warp - 2, quarter = warp & 3, half = e >> 2;
+      const int row = m0 + quarter * 32 + lane;
+      if (row < n1) {
+        uint2* out = cand + ((size_t)row * n_slots + split * 2 + half) * NCAND;
+        for (int c = 0; c < NCAND; ++c) out[c] = make_uint2(__float_as_uint(-INFINITY), 0xFFFFFFFFu);
+      }
+    }
+    return;
+  }
+  const int kblocks = (*nonint_flag) ? 3 * kp_blocks : kp_blocks;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = sA + MAX_KBLOCKS * A_KBLOCK_BYTES;
+  const uint32_t bars = sB + B_STAGES * B_STAGE_BYTES;
+  const uint32_t bar_a_full = bars;
+  const uint32_t bar_b_full = bars + 8;                    // [B_STAGES]
+  const uint32_t bar_b_empty = bar_b_full + 8 * B_STAGES;  // [B_STAGES]
+  const uint32_t bar_t_full = bar_b_empty + 8 * B_STAGES;  // [2]
+  const uint32_t bar_t_empty = bar_t_full + 16;            // [2]
+  const uint32_t tmem_slot = bar_t_empty + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    mbar_init(bar_a_full, 1);
+    for (int s = 0; s < B_STAGES; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, NUM_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // whole warp: allocate all 512 TMEM columns (2 accumulator stages x 256)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      mbar_expect_tx(bar_a_full, kblocks * A_KBLOCK_BYTES);
+      for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(sA + kb * A_KBLOCK_BYTES, &tmA, bar_a_full, kb * BK, m0);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t)
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+          mbar_expect_tx(bar_b_full + 8 * stage, B_STAGE_BYTES);
+          tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, bar_b_full + 8 * stage, kb * BK, t * BN);
+          if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      mbar_wait(bar_a_full, 0);
+      tc_fence_after();
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(bar_b_full + 8 * stage, phase);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ad = umma_desc_sw128(sA + kb * A_KBLOCK_BYTES + k * UMMA_K * 2);
+            const uint64_t bd = umma_desc_sw128(sB + stage * B_STAGE_BYTES + k * UMMA_K * 2);
+            tc_mma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          tc_commit(bar_b_empty + 8 * stage);
+          if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(bar_t_full + 8 * acc);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue: thread = (row, column half); running top-3 over all tiles of the split =====
+    const int e = warp - 2, quarter = warp & 3, half = e >> 2;
+    const int row = m0 + quarter * 32 + lane;
+    Top3 top; top.init();
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(bar_t_full + 8 * acc, acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        const int col_in_tile = half * 128 + chunk * 32;
+        const int j0 = t * BN + col_in_tile;
+        if (j0 >= n2) break;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_in_tile), r);
+        float ib[32];
+        const float4* ibp = reinterpret_cast<const float4*>(invb + j0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v4 = __ldg(ibp + q);
+          ib[4 * q] = v4.x; ib[4 * q + 1] = v4.y; ib[4 * q + 2] = v4.z; ib[4 * q + 3] = v4.w;
+        }
+        tmem_ld_wait();
+        if (dbg_c != nullptr && row < n1) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (j0 + c < n2) dbg_c[(size_t)row * dbg_ld + j0 + c] = __uint_as_float(r[c]);
+        }
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * ib[c];
+        if (j0 + 32 <= n2) {
+          float m = v[0];
+#pragma unroll
+          for (int c = 1; c < 32; ++c) m = fmaxf(m, v[c]);
+          if (m > top.k3) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (v[c] > top.k3) top.insert(v[c], (uint32_t)(j0 + c));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (j0 + c < n2 && v[c] > top.k3) top.insert(v[c], (uint32_t)(j0 + c));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+    if (row < n1) {
+      uint2* out = cand + ((size_t)row * n_slots + split * 2 + half) * NCAND;
+      out[0] = make_uint2(__float_as_uint(top.k1), top.i1);
+      out[1] = make_uint2(__float_as_uint(top.k2), top.i2);
+      out[2] = make_uint2(__float_as_uint(top.k3), top.i3);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+__global__ void match_set_counts_kernel(int* counts, int n1, int n2) {
+  if (threadIdx.x == 0) { counts[0] = n1; counts[1] = n2; }
+  else if (threadIdx.x >= 2 && threadIdx.x < 8) counts[threadIdx.x] = 0;
+}
+
+// ------------------------------------------------------------------------------ prep kernel
+// 32 rows per block.  Writes out[row][3*kp] bf16 (A: hi|hi|lo, B: hi|lo|hi), inv[row], an optional
+// row-major fp32 copy, and ORs the "not an integer in 0..255" flag.
+constexpr int PREP_ROWS = 32;
+__global__ void __launch_bounds__(256)
+match_prep_kernel(const float* __restrict__ f, const int* __restrict__ np, int n_cap, int dim, int kp,
+                  int col_major, int is_b, __nv_bfloat16* __restrict__ out, float* __restrict__ raw_rm,
+                  float* __restrict__ inv, int* __restrict__ nonint_flag) {
+  extern __shared__ float tile[];  // [PREP_ROWS][dim + 1]
+  const int n = *np;
+  const int row0 = blockIdx.x * PREP_ROWS;
+  const int ldt = dim + 1;
+  const int tid = threadIdx.x;
+  if (row0 >= n) {
+    // rows past n inside the capacity: keep inv finite so padded loads are harmless
+    for (int r = tid; r < PREP_ROWS; r += 256)
+      if (row0 + r < n_cap) inv[row0 + r] = 0.f;
+    return;
+  }
+  if (!col_major) {
+    for (int idx = tid; idx < PREP_ROWS * dim; idx += 256) {
+      const int r = idx / dim, k = idx - r * dim;
+      tile[r * ldt + k] = (row0 + r < n) ? f[(size_t)(row0 + r) * dim + k] : 0.f;
+    }
+  } else {
+    for (int idx = tid; idx < PREP_ROWS * dim; idx += 256) {
+      const int k = idx / PREP_ROWS, r = idx - k * PREP_ROWS;
+      tile[r * ldt + k] = (row0 + r < n) ? f[(size_t)k * n + row0 + r] : 0.f;
+    }
+  }
+  __syncthreads();
+  if (tid < PREP_ROWS) {
+    const float* x = tile + tid * ldt;
+    float acc = 0.f;
+    bool isint = true;
+    for (int k = 0; k < dim; ++k) {
+      const float v = x[k];
+      acc = fmaf(v, v, acc);
+      isint = isint && (v == truncf(v)) && (v >= 0.f) && (v <= 255.f);
+    }
+    if (row0 + tid < n_cap) inv[row0 + tid] = (acc == 0.f || row0 + tid >= n) ? 0.f : __fdiv_rn(1.0f, __fsqrt_rn(acc));
+    if (!isint) atomicOr(nonint_flag, 1);
+  }
+  const int ld_out = 3 * kp;
+  for (int idx = tid; idx < PREP_ROWS * kp; idx += 256) {
+    const int r = idx / kp, k = idx - r * kp;
+    if (row0 + r >= n_cap) continue;
+    const float v = (k < dim) ? tile[r * ldt + k] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* o = out + (size_t)(row0 + r) * ld_out + k;
+    o[0] = hi;
+    o[kp] = is_b ? lo : hi;
+    o[2 * kp] = is_b ? hi : lo;
+    if (raw_rm != nullptr && k < dim && row0 + r < n) raw_rm[(size_t)(row0 + r) * dim + k] = v;
+  }
+}
+
+// ------------------------------------------------------------------------- exact score math
+__device__ __forceinline__ float exact_key(const float* __restrict__ a, const float* __restrict__ b, int dim, float invb) {
+  float acc = 0.f;
+  for (int k = 0; k < dim; ++k) acc = fmaf(a[k], b[k], acc);
+  return __fmul_rn(acc, invb);
+}
+__device__ __forceinline__ float score_from_key(float key, float inva) {
+  const float c = __fmul_rn(key, inva);
+  const float s = fmaf(-2.0f, c, 2.0f);
+  return s < 0.f ? 0.f : s;
+}
+
+// one thread per row: merge candidate slots, exact re-rank, certify or flag for the row scan
+__global__ void __launch_bounds__(128)
+match_finalize_kernel(const uint2* __restrict__ cand, int n_slots, const float* __restrict__ a_raw,
+                      const float* __restrict__ b_raw, int dim, const float* __restrict__ inva,
+                      const float* __restrict__ invb, const int* __restrict__ n1p,
+                      const int* __restrict__ n2p, const int* __restrict__ nonint_flag,
+                      uint32_t* __restrict__ j1_out, float* __restrict__ s1_out, float* __restrict__ s2_out,
+                      int* __restrict__ scan_list, int* __restrict__ scan_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n1 = *n1p, n2 = *n2p;
+  if (i >= n1) return;
+  if (n2 <= 0) { j1_out[i] = 0xFFFFFFFFu; s1_out[i] = INFINITY; s2_out[i] = INFINITY; return; }
+  // top-3 by (key desc, column asc) over all slots
+  float k[3] = {-INFINITY, -INFINITY, -INFINITY};
+  uint32_t j[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  const uint2* c = cand + (size_t)i * n_slots * NCAND;
+  for (int s = 0; s < n_slots * NCAND; ++s) {
+    const uint2 e = c[s];
+    if (e.y >= (uint32_t)n2) continue;
+    const float key = __uint_as_float(e.x);
+    int pos = 3;
+    for (int q = 2; q >= 0; --q)
+      if (key > k[q] || (key == k[q] && e.y < j[q])) pos = q;
+    if (pos < 3) {
+      for (int q = 2; q > pos; --q) { k[q] = k[q - 1]; j[q] = j[q - 1]; }
+      k[pos] = key; j[pos] = e.y;
+    }
+  }
+  const float ia = inva[i];
+  const float* a = a_raw + (size_t)i * dim;
+  float s[3]; int nc = 0;
+  for (int q = 0; q < 3; ++q) {
+    if (j[q] == 0xFFFFFFFFu) { s[q] = INFINITY; continue; }
+    s[q] = score_from_key(exact_key(a, b_raw + (size_t)j[q] * dim, dim, invb[j[q]]), ia);
+    ++nc;
+  }
+  // order candidates by (score asc, column asc)
+  uint32_t jj[3] = {j[0], j[1], j[2]};
+  for (int p = 0; p < 2; ++p)
+    for (int q = 0; q < 2 - p; ++q)
+      if (s[q + 1] < s[q] || (s[q + 1] == s[q] && jj[q + 1] < jj[q])) {
+        const float ts = s[q]; s[q] = s[q + 1]; s[q + 1] = ts;
+        const uint32_t tj = jj[q]; jj[q] = jj[q + 1]; jj[q + 1] = tj;
+      }
+  bool certified;
+  if (n2 <= 3) {
+    certified = (nc == n2);
+  } else if (nc < 3) {
+    certified = false;
+  } else {
+    float kb = k[2];
+    if (*nonint_flag) kb = kb + SPLIT_EPS * ((ia > 0.f) ? __fdiv_rn(1.0f, ia) : 0.f);
+    const float sb = score_from_key(kb, ia);
+    certified = (sb > s[0]) && (sb >= s[1]);
+  }
+  j1_out[i] = jj[0]; s1_out[i] = s[0]; s2_out[i] = (n2 >= 2) ? s[1] : INFINITY;
+  if (!certified) {
+    const int slot = atomicAdd(scan_count, 1);
+    scan_list[slot] = i;
+  }
+}
+
+// exact FP32 scan of every column for the rows in scan_list (block per row, grid-stride)
+__global__ void __launch_bounds__(256)
+match_rowscan_kernel(const int* __restrict__ scan_list, const int* __restrict__ scan_count,
+                     const float* __restrict__ a_raw, const float* __restrict__ b_raw, int dim,
+                     const float* __restrict__ inva, const float* __restrict__ invb,
+                     const int* __restrict__ n2p, uint32_t* __restrict__ j1_out,
+                     float* __restrict__ s1_out, float* __restrict__ s2_out) {
+  __shared__ float sa[256];
+  __shared__ float rs1[256], rs2[256];
+  __shared__ uint32_t rj1[256];
+  const int n2 = *n2p;
+  const int count = *scan_count;
+  for (int f = blockIdx.x; f < count; f += gridDim.x) {
+    const int i = scan_list[f];
+    __syncthreads();
+    for (int k = threadIdx.x; k < dim; k += blockDim.x) sa[k] = a_raw[(size_t)i * dim + k];
+    __syncthreads();
+    const float ia = inva[i];
+    float b1 = INFINITY, b2 = INFINITY; uint32_t bj = 0xFFFFFFFFu;
+    for (int jx = threadIdx.x; jx < n2; jx += blockDim.x) {
+      const float sc = score_from_key(exact_key(sa, b_raw + (size_t)jx * dim, dim, invb[jx]), ia);
+      if (sc < b1) { b2 = b1; b1 = sc; bj = (uint32_t)jx; }
+      else if (sc < b2) b2 = sc;
+    }
+    rs1[threadIdx.x] = b1; rs2[threadIdx.x] = b2; rj1[threadIdx.x] = bj;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      if (threadIdx.x < off) {
+        const float o1 = rs1[threadIdx.x + off], o2 = rs2[threadIdx.x + off];
+        const uint32_t oj = rj1[threadIdx.x + off];
+        float m1 = rs1[threadIdx.x], m2 = rs2[threadIdx.x]; uint32_t mj = rj1[threadIdx.x];
+        // merge two (best, second) pairs; lowest column wins score ties
+        if (o1 < m1 || (o1 == m1 && oj < mj)) { m2 = fminf(m1, o2); m1 = o1; mj = oj; }
+        else { m2 = fminf(m2, o1); }
+        rs1[threadIdx.x] = m1; rs2[threadIdx.x] = m2; rj1[threadIdx.x] = mj;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { j1_out[i] = rj1[0]; s1_out[i] = rs1[0]; s2_out[i] = (n2 >= 2) ? rs2[0] : INFINITY; }
+  }
+}
+
+// ---------------------------------------------------------------------- select + compaction
+__device__ __forceinline__ bool keep_row(float s1, float s2, int n2, float thr, float max_ratio) {
+  if (!(s1 <= thr)) return false;
+  if (n2 >= 2) {
+    const float ratio = (s2 < 1e-6f) ? 1.0f : __fdiv_rn(s1, s2);
+    if (!(ratio <= max_ratio)) return false;
+  }
+  return true;
+}
+
+constexpr int SEL_BLOCK = 1024;
+__global__ void __launch_bounds__(SEL_BLOCK)
+match_count_kernel(const uint32_t* __restrict__ j1, const float* __restrict__ s1, const float* __restrict__ s2,
+                   const uint32_t* __restrict__ back_j1, const int* __restrict__ n1p,
+                   const int* __restrict__ n2p, float thr, float max_ratio, int* __restrict__ block_counts) {
+  const int i = blockIdx.x * SEL_BLOCK + threadIdx.x;
+  const int n1 = *n1p, n2 = *n2p;
+  bool keep = false;
+  if (i < n1 && n2 > 0) {
+    keep = keep_row(s1[i], s2[i], n2, thr, max_ratio);
+    if (keep && back_j1 != nullptr) keep = (back_j1[j1[i]] == (uint32_t)i);
+  }
+  const int cnt = __syncthreads_count(keep);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = cnt;
+}
+
+__global__ void __launch_bounds__(1024)
+match_scan_kernel(int* __restrict__ block_counts, int n_blocks, int* __restrict__ total) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_blocks; base += 1024) {
+    const int idx = base + threadIdx.x;
+    const int v = idx < n_blocks ? block_counts[idx] : 0;
+    int x = v;
+    for (int off = 1; off < 32; off <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, off);
+      if ((threadIdx.x & 31) >= off) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = warp_sums[threadIdx.x];
+      for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, off);
+        if (threadIdx.x >= off) w += y;
+      }
+      warp_sums[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int warp_off = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0;
+    const int incl = x + warp_off + carry;
+    if (idx < n_blocks) block_counts[idx] = incl - v;  // exclusive
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(SEL_BLOCK)
+match_scatter_kernel(const uint32_t* __restrict__ j1, const float* __restrict__ s1, const float* __restrict__ s2,
+                     const uint32_t* __restrict__ back_j1, const int* __restrict__ n1p,
+                     const int* __restrict__ n2p, float thr, float max_ratio, int index_base,
+                     const int* __restrict__ block_offsets, uint32_t* __restrict__ idx1,
+                     uint32_t* __restrict__ idx2, float* __restrict__ metric) {
+  __shared__ int warp_sums[32];
+  const int i = blockIdx.x * SEL_BLOCK + threadIdx.x;
+  const int n1 = *n1p, n2 = *n2p;
+  bool keep = false;
+  if (i < n1 && n2 > 0) {
+    keep = keep_row(s1[i], s2[i], n2, thr, max_ratio);
+    if (keep && back_j1 != nullptr) keep = (back_j1[j1[i]] == (uint32_t)i);
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) warp_sums[w] = __popc(ballot);
+  __syncthreads();
+  if (w == 0) {
+    int x = warp_sums[lane];
+    for (int off = 1; off < 32; off <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += y;
+    }
+    warp_sums[lane] = x;
+  }
+  __syncthreads();
+  if (keep) {
+    const int pos = block_offsets[blockIdx.x] + (w ? warp_sums[w - 1] : 0) + __popc(ballot & ((1u << lane) - 1u));
+    idx1[pos] = (uint32_t)i + (uint32_t)index_base;
+    idx2[pos] = j1[i] + (uint32_t)index_base;
+    if (metric) metric[pos] = s1[i];
+  }
+}
+
+// --------------------------------------------------------------------------- host plumbing
+static int make_operand_map(CUtensorMap* map, const __nv_bfloat16* base, int rows_cap, int kp, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled driver entry point not available"); return VO_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)(3 * kp), (cuuint64_t)rows_cap};
+  cuuint64_t gstride[1] = {(cuuint64_t)(3 * kp) * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return VO_ERR_CUDA; }
+  return VO_OK;
+}
+
+static bool g_attr_set = false;
+
+struct Top2Args {
+  const float* f1; int n1; const float* f2; int n2; int dim;
+  int col_major;      // layout of f1/f2 (device memory)
+  bool tag_b;         // scratch-name suffix so the Unique backward pass does not clobber
+  float* dbg_c;       // optional n1 x n2 raw dot products (device)
+};
+
+// Runs prep + GEMM top-3 + finalize + row scan for device-resident inputs; results stay on device.
+static int run_top2(vo_ctx* ctx, const Top2Args& a, cudaStream_t st, uint32_t** j1, float** s1, float** s2,
+                    const int** n1_dev, const int** n2_dev) {
+  const char* sfx = a.tag_b ? "_b" : "_f";
+  auto nm = [&](const char* base) { return std::string(base) + sfx; };
+  const int n1 = a.n1, n2 = a.n2, dim = a.dim;
+  const int kp = div_up(dim, BK) * BK;
+  if (3 * kp > MAX_KBLOCKS * BK) { set_error("vo_match: dim %d > 128 is not supported by the tensor-core path", dim); return VO_ERR_ARG; }
+  const int n1_pad = div_up(n1 > 0 ? n1 : 1, BM) * BM, n2_pad = div_up(n2 > 0 ? n2 : 1, BN) * BN;
+
+  // counts[0]=n1 counts[1]=n2 counts[2]=nonint flag counts[3]=rowscan count
+  int* counts; VO_TRY(dev_buf(ctx, nm("m_counts").c_str(), 8, &counts));
+  match_set_counts_kernel<<<1, 32, 0, st>>>(counts, n1, n2);
+
+  __nv_bfloat16 *opA, *opB; float *invA, *invB, *rawA = nullptr, *rawB = nullptr;
+  VO_TRY(dev_buf(ctx, nm("m_opA").c_str(), (size_t)n1_pad * 3 * kp, &opA));
+  VO_TRY(dev_buf(ctx, nm("m_opB").c_str(), (size_t)n2_pad * 3 * kp, &opB));
+  VO_TRY(dev_buf(ctx, nm("m_invA").c_str(), (size_t)n1_pad, &invA));
+  VO_TRY(dev_buf(ctx, nm("m_invB").c_str(), (size_t)n2_pad + BN, &invB));
+  const float *a_raw = a.f1, *b_raw = a.f2;
+  if (a.col_major) {
+    VO_TRY(dev_buf(ctx, nm("m_rawA").c_str(), (size_t)n1_pad * dim, &rawA));
+    VO_TRY(dev_buf(ctx, nm("m_rawB").c_str(), (size_t)n2_pad * dim, &rawB));
+    a_raw = rawA; b_raw = rawB;
+  }
+  VO_TRY(dev_buf(ctx, nm("m_j1").c_str(), (size_t)n1_pad, j1));
+  VO_TRY(dev_buf(ctx, nm("m_s1").c_str(), (size_t)n1_pad, s1));
+  VO_TRY(dev_buf(ctx, nm("m_s2").c_str(), (size_t)n1_pad, s2));
+  *n1_dev = counts; *n2_dev = counts + 1;
+  ctx->match_stats[2] = 0; ctx->match_stats[3] = kp;
+  if (n1 == 0) return VO_OK;
+
+  const size_t prep_smem = (size_t)PREP_ROWS * (dim + 1) * sizeof(float);
+  match_prep_kernel<<<n1_pad / PREP_ROWS, 256, prep_smem, st>>>(a.f1, counts, n1_pad, dim, kp, a.col_major, 0, opA, rawA, invA, counts + 2);
+  match_prep_kernel<<<(n2_pad + BN) / PREP_ROWS, 256, prep_smem, st>>>(a.f2, counts + 1, n2_pad + BN, dim, kp, a.col_major, 1, opB, rawB, invB, counts + 2);
+  VO_CUDA(cudaGetLastError());
+
+  // column splits so that (row panels x splits) fills the SMs
+  const int m_blocks = n1_pad / BM, tiles = n2_pad / BN;
+  int n_splits = 1;
+  if (m_blocks < ctx->num_sms) {
+    n_splits = ctx->num_sms / m_blocks;
+    if (n_splits > tiles) n_splits = tiles;
+    if (n_splits < 1) n_splits = 1;
+  }
+  const int n_slots = n_splits * 2;
+  uint2* cand; VO_TRY(dev_buf(ctx, nm("m_cand").c_str(), (size_t)n1_pad * n_slots * NCAND, &cand));
+  int* scan_list; VO_TRY(dev_buf(ctx, nm("m_scanlist").c_str(), (size_t)n1_pad, &scan_list));
+
+  if (n2 > 0) {
+    CUtensorMap tmA, tmB;
+    VO_TRY(make_operand_map(&tmA, opA, n1_pad, kp, BM));
+    VO_TRY(make_operand_map(&tmB, opB, n2_pad, kp, BN));
+    if (!g_attr_set) {
+      VO_CUDA(cudaFuncSetAttribute(match_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      g_attr_set = true;
+    }
+    dim3 grid(m_blocks, n_splits);
+    match_topk_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, invB, counts, counts + 1, counts + 2, kp / BK, n_splits,
+                                                             cand, a.dbg_c, n2);
+    VO_CUDA(cudaGetLastError());
+    ctx->match_stats[2] = 1;
+  }
+  match_finalize_kernel<<<div_up(n1, 128), 128, 0, st>>>(cand, n_slots, a_raw, b_raw, dim, invA, invB, counts, counts + 1,
+                                                         counts + 2, *j1, *s1, *s2, scan_list, counts + 3);
+  if (n2 > 0) {
+    int scan_grid = ctx->num_sms * 2;
+    if (scan_grid > n1) scan_grid = n1;
+    match_rowscan_kernel<<<scan_grid, 256, 0, st>>>(scan_list, counts + 3, a_raw, b_raw, dim, invA, invB, counts + 1, *j1, *s1, *s2);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+static void fill_opts(const vo_match_opts* in, vo_match_opts* o) {
+  o->match_threshold = 1.0f; o->max_ratio = 0.6f; o->unique = 0; o->index_base = 0;
+  if (in) {
+    if (in->match_threshold > 0) o->match_threshold = in->match_threshold;
+    if (in->max_ratio > 0) o->max_ratio = in->max_ratio;
+    o->unique = in->unique != 0;
+    o->index_base = in->index_base;
+  }
+}
+
+// device-resident match: inputs on device (row- or col-major), outputs on device
+static int match_device(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2, int dim, int col_major,
+                        const vo_match_opts* opts, uint32_t* idx1, uint32_t* idx2, float* metric, int* n_pairs_dev,
+                        cudaStream_t st) {
+  vo_match_opts o; fill_opts(opts, &o);
+  uint32_t *j1, *bj1 = nullptr; float *s1, *s2; const int *n1d, *n2d;
+  Top2Args fa{f1, n1, f2, n2, dim, col_major, false, nullptr};
+  VO_TRY(run_top2(ctx, fa, st, &j1, &s1, &s2, &n1d, &n2d));
+  const int fwd_launches = ctx->match_stats[2];
+  if (o.unique && n1 > 0 && n2 > 0) {
+    float *bs1, *bs2; const int *bn1, *bn2;
+    Top2Args ba{f2, n2, f1, n1, dim, col_major, true, nullptr};
+    VO_TRY(run_top2(ctx, ba, st, &bj1, &bs1, &bs2, &bn1, &bn2));
+    ctx->match_stats[2] += fwd_launches;
+  }
+  if (n1 == 0 || n2 == 0) {
+    VO_CUDA(cudaMemsetAsync(n_pairs_dev, 0, sizeof(int), st));
+    return VO_OK;
+  }
+  const int nb = div_up(n1, SEL_BLOCK);
+  int* blk; VO_TRY(dev_buf(ctx, "m_blk", (size_t)nb + 1, &blk));
+  const float thr = o.match_threshold * 0.04f;
+  match_count_kernel<<<nb, SEL_BLOCK, 0, st>>>(j1, s1, s2, bj1, n1d, n2d, thr, o.max_ratio, blk);
+  match_scan_kernel<<<1, 1024, 0, st>>>(blk, nb, n_pairs_dev);
+  match_scatter_kernel<<<nb, SEL_BLOCK, 0, st>>>(j1, s1, s2, bj1, n1d, n2d, thr, o.max_ratio, o.index_base, blk, idx1, idx2, metric);
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+static int upload_features(vo_ctx* ctx, const char* name, const float* f, int n, int dim, float** out, cudaStream_t st) {
+  VO_TRY(dev_buf(ctx, name, (size_t)(n > 0 ? n : 1) * dim, out));
+  if (n > 0) VO_CUDA(cudaMemcpyAsync(*out, f, (size_t)n * dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  return VO_OK;
+}
+
+}  // namespace vo
+
+using namespace vo;
+
+extern "C" {
+
+int vo_match(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2, int dim, int col_major,
+             const vo_match_opts* opts, uint32_t* idx1, uint32_t* idx2, float* metric, int* n_pairs) {
+  VO_CHECK_ARG(ctx && n_pairs, "ctx/n_pairs is null");
+  VO_CHECK_ARG(n1 >= 0 && n2 >= 0 && dim > 0, "negative size");
+  VO_CHECK_ARG((n1 == 0 || f1) && (n2 == 0 || f2), "feature pointer is null");
+  VO_CHECK_ARG(n1 == 0 || (idx1 && idx2), "output pointer is null");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  *n_pairs = 0;
+  if (n1 == 0 || n2 == 0) { ctx->match_stats[0] = 1; ctx->match_stats[1] = 0; ctx->match_stats[2] = 0; return VO_OK; }
+  float *d1, *d2;
+  VO_TRY(upload_features(ctx, "m_in1", f1, n1, dim, &d1, st));
+  VO_TRY(upload_features(ctx, "m_in2", f2, n2, dim, &d2, st));
+  uint32_t *o1, *o2; float* om; int* np;
+  VO_TRY(dev_buf(ctx, "m_out1", (size_t)n1, &o1));
+  VO_TRY(dev_buf(ctx, "m_out2", (size_t)n1, &o2));
+  VO_TRY(dev_buf(ctx, "m_outm", (size_t)n1, &om));
+  VO_TRY(dev_buf(ctx, "m_np", 4, &np));
+  VO_TRY(match_device(ctx, d1, n1, d2, n2, dim, col_major, opts, o1, o2, om, np, st));
+  int* hres; VO_TRY(pin_buf(ctx, "m_res", 8, &hres));
+  int* counts; VO_TRY(dev_buf(ctx, "m_counts_f", 8, &counts));
+  VO_CUDA(cudaMemcpyAsync(hres, np, sizeof(int), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaMemcpyAsync(hres + 1, counts + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaStreamSynchronize(st));
+  const int p = hres[0];
+  ctx->match_stats[0] = hres[1] ? 0 : 1;
+  ctx->match_stats[1] = hres[2];
+  ctx->match_stats[3] = hres[1] ? 3 * ctx->match_stats[3] : ctx->match_stats[3];
+  if (p > 0) {
+    VO_CUDA(cudaMemcpyAsync(idx1, o1, (size_t)p * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    VO_CUDA(cudaMemcpyAsync(idx2, o2, (size_t)p * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (metric) VO_CUDA(cudaMemcpyAsync(metric, om, (size_t)p * sizeof(float), cudaMemcpyDeviceToHost, st));
+    VO_CUDA(cudaStreamSynchronize(st));
+  }
+  *n_pairs = p;
+  return VO_OK;
+}
+
+int vo_match_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, int n2, int dim,
+                 const vo_match_opts* opts, uint32_t* idx1_dev, uint32_t* idx2_dev, float* metric_dev,
+                 int* n_pairs_dev, void* stream) {
+  VO_CHECK_ARG(ctx && n_pairs_dev, "ctx/n_pairs_dev is null");
+  VO_CHECK_ARG(n1 >= 0 && n2 >= 0 && dim > 0, "negative size");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  return match_device(ctx, f1_dev, n1, f2_dev, n2, dim, 0, opts, idx1_dev, idx2_dev, metric_dev, n_pairs_dev,
+                      (cudaStream_t)stream);
+}
+
+int vo_match_top2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, int n2, int dim,
+                      uint32_t* j1_dev, float* s1_dev, float* s2_dev, void* stream) {
+  VO_CHECK_ARG(ctx, "ctx is null");
+  VO_CHECK_ARG(n1 >= 0 && n2 >= 0 && dim > 0, "negative size");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t* j1; float *s1, *s2; const int *n1d, *n2d;
+  Top2Args fa{f1_dev, n1, f2_dev, n2, dim, 0, false, nullptr};
+  VO_TRY(run_top2(ctx, fa, st, &j1, &s1, &s2, &n1d, &n2d));
+  if (n1 > 0) {
+    VO_CUDA(cudaMemcpyAsync(j1_dev, j1, (size_t)n1 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    VO_CUDA(cudaMemcpyAsync(s1_dev, s1, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    VO_CUDA(cudaMemcpyAsync(s2_dev, s2, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return VO_OK;
+}
+
+int vo_match_top2(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2, int dim, int col_major,
+                  uint32_t* j1_out, float* s1_out, float* s2_out) {
+  VO_CHECK_ARG(ctx, "ctx is null");
+  VO_CHECK_ARG(n1 >= 0 && n2 >= 0 && dim > 0, "negative size");
+  VO_CHECK_ARG((n1 == 0 || f1) && (n2 == 0 || f2), "feature pointer is null");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (n1 == 0) return VO_OK;
+  float *d1, *d2;
+  VO_TRY(upload_features(ctx, "m_in1", f1, n1, dim, &d1, st));
+  VO_TRY(upload_features(ctx, "m_in2", f2, n2, dim, &d2, st));
+  uint32_t* j1; float *s1, *s2; const int *n1d, *n2d;
+  Top2Args fa{d1, n1, d2, n2, dim, col_major, false, nullptr};
+  VO_TRY(run_top2(ctx, fa, st, &j1, &s1, &s2, &n1d, &n2d));
+  int* hres; VO_TRY(pin_buf(ctx, "m_res", 8, &hres));
+  VO_CUDA(cudaMemcpyAsync(hres + 1, n1d + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaMemcpyAsync(j1_out, j1, (size_t)n1 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaMemcpyAsync(s1_out, s1, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaMemcpyAsync(s2_out, s2, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaStreamSynchronize(st));
+  ctx->match_stats[0] = hres[1] ? 0 : 1;
+  ctx->match_stats[1] = hres[2];
+  ctx->match_stats[3] = hres[1] ? 3 * ctx->match_stats[3] : ctx->match_stats[3];
+  return VO_OK;
+}
+
+int vo_match_stats(vo_ctx* ctx, int stats[4]) {
+  VO_CHECK_ARG(ctx && stats, "null argument");
+  for (int i = 0; i < 4; ++i) stats[i] = ctx->match_stats[i];
+  return VO_OK;
+}
+
+int vo_match_debug_gemm(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2, int dim, float* c_out) {
+  VO_CHECK_ARG(ctx && f1 && f2 && c_out, "null argument");
+  VO_CHECK_ARG(n1 > 0 && n2 > 0 && dim > 0, "empty input");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  float *d1, *d2, *dc;
+  VO_TRY(upload_features(ctx, "m_in1", f1, n1, dim, &d1, st));
+  VO_TRY(upload_features(ctx, "m_in2", f2, n2, dim, &d2, st));
+  VO_TRY(dev_buf(ctx, "m_dbgc", (size_t)n1 * n2, &dc));
+  VO_CUDA(cudaMemsetAsync(dc, 0xFF, (size_t)n1 * n2 * sizeof(float), st));
+  uint32_t* j1; float *s1, *s2; const int *n1d, *n2d;
+  Top2Args fa{d1, n1, d2, n2, dim, 0, false, dc};
+  VO_TRY(run_top2(ctx, fa, st, &j1, &s1, &s2, &n1d, &n2d));
+  VO_CUDA(cudaMemcpyAsync(c_out, dc, (size_t)n1 * n2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaStreamSynchronize(st));
+  return VO_OK;
+}
+
+}  // extern "C"

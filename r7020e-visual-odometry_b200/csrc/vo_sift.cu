@@ -1,0 +1,888 @@
+// vo_sift.cu -- detectSIFTFeatures + extractFeatures("Method","SIFT") on B200 (VO.m:79-84).
+//
+// Batch-first: every kernel covers one (octave, layer) of ALL images of the batch, so a 1241x376
+// frame (far too small to fill 148 SMs alone) is processed B images at a time.
+//
+// HBM layout (per plan): gauss[o][l][b][h_o][pitch_o] and dog[o][l][b][h_o][pitch_o], fp32, pitch
+// rounded up to 32 floats so rows are 128-byte aligned (vector loads/stores, TMA-legal strides).
+//
+//   sift_base_kernel      u8 -> 2x bilinear upsample (cv::resize convention) -> blur(sig_diff)
+//   sift_blur_dog_kernel  G[l] -> G[l+1] (separable Gaussian through shared memory, reflect-101)
+//                         fused with D[l] = G[l+1] - G[l]; each layer is read once, written once
+//   sift_downsample_kernel  G[o+1][0] = G[o][nl](2y, 2x)
+//   sift_extrema_kernel   3x3x3 DoG extrema, warp-ballot compaction into a candidate list
+//   sift_refine_orient_kernel  warp per candidate: quadratic sub-pixel fit, contrast/edge tests,
+//                         36-bin orientation histogram (shared-memory integer atomics), peaks
+//   sift_rank_kernel / sift_dedupe_kernel  OpenCV keypoint order (x, y, -size, angle, ...) by
+//                         rank sort, duplicate removal, compaction
+//   sift_descriptor_kernel  warp per keypoint: 4x4x8 trilinear histogram (shared-memory integer
+//                         atomics), clip 0.2, scale 512, round to 0..255
+//
+// Arithmetic follows the contract in oracle/sift.c (DESIGN.md "SIFT arithmetic"): explicit fmaf,
+// no implicit contraction (-fmad=false), polynomial exp/atan2, histogram contributions rounded to
+// 1/4096 and summed as integers, so results do not depend on thread scheduling.
+#include "vo_internal.h"
+#include <cfloat>
+#include <cmath>
+
+namespace vo {
+
+constexpr int MAX_OCT = 16;
+constexpr int MAX_R = 16;
+constexpr int SIFT_BORDER = 5;
+constexpr int ORI_BINS = 36;
+constexpr float SIFT_FIX = 4096.0f;
+constexpr float SIFT_INV_FIX = 1.0f / 4096.0f;
+constexpr int TILE_W = 128, TILE_H = 32;
+
+struct Taps { float k[MAX_R + 1]; int r; };
+
+struct SiftPlan {
+  int rows = 0, cols = 0, batch = 0, nl = 0;
+  float sigma = 0, contrast = 0, edge = 0;
+  int n_oct = 0;
+  int h[MAX_OCT], w[MAX_OCT], pitch[MAX_OCT];
+  size_t goff[MAX_OCT], doff[MAX_OCT];   // float offsets of octave o inside gauss/dog
+  float* gauss = nullptr; float* dog = nullptr;
+  uint8_t* img = nullptr;       // [batch][rows][cols]
+  uint8_t* img_t = nullptr;     // staging for column-major input
+  Taps taps[8]; Taps base_taps;
+  int cand_cap = 0, kp_cap = 0;
+  uint32_t* cand = nullptr; int* counters = nullptr;   // counters[b*4 + {0:cand,1:raw kp,2:final}]
+  vo_keypoint* raw = nullptr; vo_keypoint* sorted = nullptr; vo_keypoint* final_kp = nullptr;
+  float* desc = nullptr;
+  size_t layer_elems(int o) const { return (size_t)batch * h[o] * pitch[o]; }
+  float* G(int o, int l) const { return gauss + goff[o] + (size_t)l * layer_elems(o); }
+  float* D(int o, int l) const { return dog + doff[o] + (size_t)l * layer_elems(o); }
+};
+
+void sift_plan_destroy(SiftPlan* p) {
+  if (!p) return;
+  cudaFree(p->gauss); cudaFree(p->dog); cudaFree(p->img); cudaFree(p->img_t); cudaFree(p->cand);
+  cudaFree(p->counters); cudaFree(p->raw); cudaFree(p->sorted); cudaFree(p->final_kp); cudaFree(p->desc);
+  delete p;
+}
+
+// ----------------------------------------------------------------------------- primitives
+__device__ __forceinline__ float vo_expf(float x) {
+  const float t = x * 1.44269504088896341f;
+  float n = rintf(t);
+  if (n < -126.f) return 0.f;
+  if (n > 127.f) n = 127.f;
+  float r = fmaf(n, -0.693145751953125f, x);
+  r = fmaf(n, -1.42860682030941723e-6f, r);
+  float p = 1.0f / 720.0f;
+  p = fmaf(p, r, 1.0f / 120.0f);
+  p = fmaf(p, r, 1.0f / 24.0f);
+  p = fmaf(p, r, 1.0f / 6.0f);
+  p = fmaf(p, r, 0.5f);
+  p = fmaf(p, r, 1.0f);
+  p = fmaf(p, r, 1.0f);
+  return __int_as_float(__float_as_int(p) + (((int)n) << 23));
+}
+
+__device__ __forceinline__ float vo_atan2deg(float y, float x) {
+  const float p1 = 0.9997878412794807f * 57.29577951308232f;
+  const float p3 = -0.3258083974640975f * 57.29577951308232f;
+  const float p5 = 0.1555786518463281f * 57.29577951308232f;
+  const float p7 = -0.04432655554792128f * 57.29577951308232f;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, ax + 2.220446049250313e-16f);
+    c2 = c * c;
+    a = fmaf(fmaf(fmaf(p7, c2, p5), c2, p3), c2, p1) * c;
+  } else {
+    c = __fdiv_rn(ax, ay + 2.220446049250313e-16f);
+    c2 = c * c;
+    a = 90.f - fmaf(fmaf(fmaf(p7, c2, p5), c2, p3), c2, p1) * c;
+  }
+  if (x < 0) a = 180.f - a;
+  if (y < 0) a = 360.f - a;
+  return a;
+}
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) {
+    if (p < 0) p = -p;
+    else p = 2 * (len - 1) - p;
+  }
+  return p;
+}
+
+// value of the 2x-upsampled image (cv::resize INTER_LINEAR convention) at (x, y)
+__device__ __forceinline__ float dbl_at(const uint8_t* __restrict__ img, int rows, int cols, int x, int y) {
+  int ya = (y & 1) ? (y >> 1) : (y >> 1) - 1, yb = ya + 1;
+  const float wyb = (y & 1) ? 0.25f : 0.75f, wya = 1.0f - wyb;
+  if (ya < 0) ya = 0;
+  if (yb > rows - 1) yb = rows - 1;
+  int xa = (x & 1) ? (x >> 1) : (x >> 1) - 1, xb = xa + 1;
+  const float wxb = (x & 1) ? 0.25f : 0.75f, wxa = 1.0f - wxb;
+  if (xa < 0) xa = 0;
+  if (xb > cols - 1) xb = cols - 1;
+  const float a = img[(size_t)ya * cols + xa], b = img[(size_t)ya * cols + xb];
+  const float c = img[(size_t)yb * cols + xa], d = img[(size_t)yb * cols + xb];
+  return wya * (wxa * a + wxb * b) + wyb * (wxa * c + wxb * d);
+}
+
+__global__ void sift_transpose_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int rows, int cols, int ld) {
+  __shared__ uint8_t t[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;   // bx over cols, by over rows
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {    // read src (col-major): element (r,c) at src[c*ld + r]
+    const int c = bx + i, r = by + threadIdx.x;
+    if (c < cols && r < rows) t[i][threadIdx.x] = src[(size_t)c * ld + r];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = by + i, c = bx + threadIdx.x;
+    if (r < rows && c < cols) dst[(size_t)r * cols + c] = t[threadIdx.x][i];
+  }
+}
+
+// ----------------------------------------------------------------- separable blur (+ DoG)
+// One block = TILE_W x TILE_H outputs of one image.  RT > 0: compile-time radius (fully unrolled),
+// RT == 0: runtime radius taps.r (generic options).  FROM_U8: the source is the uint8 input and the
+// tile is filled with the 2x-upsampled values on the fly (base image), no DoG.
+template <int RT, bool FROM_U8>
+__global__ void __launch_bounds__(256)
+sift_blur_dog_kernel(const float* __restrict__ src, const uint8_t* __restrict__ src8, float* __restrict__ dst,
+                     float* __restrict__ dog, int h, int w, int pitch, int rows8, int cols8, const Taps taps) {
+  extern __shared__ float sm[];
+  const int R = RT > 0 ? RT : taps.r;
+  const int in_w = ((TILE_W + 2 * R + 3) & ~3) + 4;   // padded row length of the input tile
+  const int in_h = TILE_H + 2 * R;
+  float* s_in = sm;                       // [in_h][in_w]
+  float* s_tmp = sm + in_h * in_w;        // [in_h][TILE_W]
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+  const size_t img_off = (size_t)b * h * pitch;
+  const int tid = threadIdx.x;
+
+  // ---- load tile + halo (reflect-101 at the image border)
+  const int load_w = TILE_W + 2 * R;
+  for (int idx = tid; idx < in_h * load_w; idx += 256) {
+    const int iy = idx / load_w, ix = idx - iy * load_w;
+    const int gy = reflect101(y0 - R + iy, h), gx = reflect101(x0 - R + ix, w);
+    float v;
+    if (FROM_U8) v = dbl_at(src8 + (size_t)b * rows8 * cols8, rows8, cols8, gx, gy);
+    else v = __ldg(src + img_off + (size_t)gy * pitch + gx);
+    s_in[iy * in_w + ix] = v;
+  }
+  __syncthreads();
+
+  // ---- row pass: warp per row, 4 consecutive outputs per lane
+  {
+    const int lane = tid & 31, wrp = tid >> 5;
+    for (int row = wrp; row < in_h; row += 8) {
+      const float* p = s_in + row * in_w + 4 * lane;
+      float win[4 + 2 * (RT > 0 ? RT : MAX_R)];
+      const int nwin = 4 + 2 * R;
+#pragma unroll
+      for (int q = 0; q < (4 + 2 * (RT > 0 ? RT : MAX_R) + 3) / 4; ++q) {
+        if (4 * q < nwin) {
+          const float4 v4 = *reinterpret_cast<const float4*>(p + 4 * q);
+          win[4 * q] = v4.x;
+          if (4 * q + 1 < 4 + 2 * (RT > 0 ? RT : MAX_R)) win[4 * q + 1] = v4.y;
+          if (4 * q + 2 < 4 + 2 * (RT > 0 ? RT : MAX_R)) win[4 * q + 2] = v4.z;
+          if (4 * q + 3 < 4 + 2 * (RT > 0 ? RT : MAX_R)) win[4 * q + 3] = v4.w;
+        }
+      }
+      float acc[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] = taps.k[0] * win[R + o];
+      if (RT > 0) {
+#pragma unroll
+        for (int i = 1; i <= (RT > 0 ? RT : 1); ++i) {
+#pragma unroll
+          for (int o = 0; o < 4; ++o) acc[o] = fmaf(taps.k[i], win[RT + o - i] + win[RT + o + i], acc[o]);
+        }
+      } else {
+        for (int i = 1; i <= R; ++i)
+          for (int o = 0; o < 4; ++o) acc[o] = fmaf(taps.k[i], p[R + o - i] + p[R + o + i], acc[o]);
+      }
+      *reinterpret_cast<float4*>(s_tmp + row * TILE_W + 4 * lane) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+  }
+  __syncthreads();
+
+  // ---- column pass: thread = (column, 16-row half), 4 outputs at a time
+  {
+    const int x = tid & (TILE_W - 1), half = tid >> 7;
+    const int gx = x0 + x;
+#pragma unroll 1
+    for (int chunk = 0; chunk < 4; ++chunk) {
+      const int ty = half * 16 + chunk * 4;     // first output row of this chunk inside the tile
+      if (y0 + ty >= h) break;
+      const float* p = s_tmp + ty * TILE_W + x;   // window row 0 <-> tile row ty - R  (+R offset in s_tmp)
+      float acc[4];
+      if (RT > 0) {
+        float win[4 + 2 * (RT > 0 ? RT : 1)];
+#pragma unroll
+        for (int q = 0; q < 4 + 2 * (RT > 0 ? RT : 1); ++q) win[q] = p[q * TILE_W];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o] = taps.k[0] * win[RT + o];
+#pragma unroll
+        for (int i = 1; i <= (RT > 0 ? RT : 1); ++i) {
+#pragma unroll
+          for (int o = 0; o < 4; ++o) acc[o] = fmaf(taps.k[i], win[RT + o - i] + win[RT + o + i], acc[o]);
+        }
+      } else {
+        for (int o = 0; o < 4; ++o) acc[o] = taps.k[0] * p[(R + o) * TILE_W];
+        for (int i = 1; i <= R; ++i)
+          for (int o = 0; o < 4; ++o) acc[o] = fmaf(taps.k[i], p[(R + o - i) * TILE_W] + p[(R + o + i) * TILE_W], acc[o]);
+      }
+      if (gx < w) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int gy = y0 + ty + o;
+          if (gy < h) {
+            const size_t g = img_off + (size_t)gy * pitch + gx;
+            dst[g] = acc[o];
+            if (!FROM_U8) dog[g] = acc[o] - s_in[(R + ty + o) * in_w + R + x];
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sift_downsample_kernel(const float* __restrict__ src, float* __restrict__ dst, int sh, int spitch, int dh, int dw, int dpitch) {
+  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+  if (x < dw) dst[(size_t)b * dh * dpitch + (size_t)y * dpitch + x] = __ldg(src + (size_t)b * sh * spitch + (size_t)(2 * y) * spitch + 2 * x);
+}
+
+// ----------------------------------------------------------------------- extrema detection
+// grid (ceil(w/32), ceil(h/8), batch * nl); candidate word = oct<<28 | layer<<25 | y<<13 | x
+__global__ void __launch_bounds__(256)
+sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int nl, int batch, int h, int w, int pitch,
+                    float threshold, uint32_t* __restrict__ cand, int cand_cap, int* __restrict__ counters) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.z / nl, layer = 1 + blockIdx.z % nl;
+  const size_t layer_stride = (size_t)batch * h * pitch;
+  const float* cur = dog_oct + (size_t)layer * layer_stride + (size_t)b * h * pitch;
+  bool ext = false;
+  if (x >= SIFT_BORDER && x < w - SIFT_BORDER && y >= SIFT_BORDER && y < h - SIFT_BORDER) {
+    const size_t q = (size_t)y * pitch + x;
+    const float val = __ldg(cur + q);
+    if (fabsf(val) > threshold) {
+      const float* prv = cur - layer_stride;
+      const float* nxt = cur + layer_stride;
+      ext = true;
+      if (val > 0) {
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const size_t qq = q + dy * pitch + dx;
+            ext = ext && val >= __ldg(cur + qq) && val >= __ldg(prv + qq) && val >= __ldg(nxt + qq);
+          }
+      } else {
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const size_t qq = q + dy * pitch + dx;
+            ext = ext && val <= __ldg(cur + qq) && val <= __ldg(prv + qq) && val <= __ldg(nxt + qq);
+          }
+      }
+    }
+  }
+  const unsigned mask = __ballot_sync(0xffffffffu, ext);
+  if (mask) {
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&counters[b * 4 + 0], __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (ext) {
+      const int slot = base + __popc(mask & ((1u << lane) - 1u));
+      if (slot < cand_cap)
+        cand[(size_t)b * cand_cap + slot] = ((uint32_t)oct << 28) | ((uint32_t)layer << 25) | ((uint32_t)y << 13) | (uint32_t)x;
+    }
+  }
+}
+
+// --------------------------------------------------------- refinement + orientation (warp/cand)
+struct OctInfo { int h[MAX_OCT], w[MAX_OCT], pitch[MAX_OCT]; size_t goff[MAX_OCT], doff[MAX_OCT]; };
+
+__global__ void __launch_bounds__(128)
+sift_refine_orient_kernel(const float* __restrict__ gauss, const float* __restrict__ dog, const OctInfo oi,
+                          int batch, int nl, float contrast_thr, float edge_thr, float sigma,
+                          const uint32_t* __restrict__ cand, int cand_cap, int* __restrict__ counters,
+                          vo_keypoint* __restrict__ raw, int kp_cap) {
+  __shared__ uint32_t s_hist[4][ORI_BINS];
+  __shared__ float s_sm[4][ORI_BINS + 4];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int n_cand = min(counters[b * 4 + 0], cand_cap);
+  const float img_scale = 1.f / 255.f, deriv_scale = img_scale * 0.5f, second_deriv_scale = img_scale,
+              cross_deriv_scale = img_scale * 0.25f;
+  for (int ci = blockIdx.x * 4 + wib; ci < n_cand; ci += gridDim.x * 4) {
+    const uint32_t word = cand[(size_t)b * cand_cap + ci];
+    const int o = word >> 28;
+    int layer = (word >> 25) & 7, r = (word >> 13) & 4095, c = word & 8191;
+    const int rows = oi.h[o], cols = oi.w[o], pitch = oi.pitch[o];
+    const size_t lstride = (size_t)batch * rows * pitch;
+    const float* dbase = dog + oi.doff[o] + (size_t)b * rows * pitch;
+    float xi = 0, xr = 0, xc = 0;
+    bool ok = true;
+    int it = 0;
+    for (; it < 5; ++it) {
+      const float* img = dbase + (size_t)layer * lstride;
+      const float* prv = img - lstride;
+      const float* nxt = img + lstride;
+      const size_t q = (size_t)r * pitch + c;
+      const float dD0 = (img[q + 1] - img[q - 1]) * deriv_scale;
+      const float dD1 = (img[q + pitch] - img[q - pitch]) * deriv_scale;
+      const float dD2 = (nxt[q] - prv[q]) * deriv_scale;
+      const float v2 = img[q] * 2.f;
+      const float dxx = (img[q + 1] + img[q - 1] - v2) * second_deriv_scale;
+      const float dyy = (img[q + pitch] + img[q - pitch] - v2) * second_deriv_scale;
+      const float dss = (nxt[q] + prv[q] - v2) * second_deriv_scale;
+      const float dxy = (img[q + pitch + 1] - img[q + pitch - 1] - img[q - pitch + 1] + img[q - pitch - 1]) * cross_deriv_scale;
+      const float dxs = (nxt[q + 1] - nxt[q - 1] - prv[q + 1] + prv[q - 1]) * cross_deriv_scale;
+      const float dys = (nxt[q + pitch] - nxt[q - pitch] - prv[q + pitch] + prv[q - pitch]) * cross_deriv_scale;
+      const float a00 = dxx, a01 = dxy, a02 = dxs, a11 = dyy, a12 = dys, a22 = dss;
+      const float m0 = a11 * a22 - a12 * a12, m1 = a01 * a22 - a12 * a02, m2 = a01 * a12 - a11 * a02;
+      const float det = a00 * m0 - a01 * m1 + a02 * m2;
+      float X0 = 0, X1 = 0, X2 = 0;
+      if (det != 0.f) {
+        const float d = __fdiv_rn(1.f, det);
+        X0 = d * (dD0 * m0 - a01 * (dD1 * a22 - a12 * dD2) + a02 * (dD1 * a12 - a11 * dD2));
+        X1 = d * (a00 * (dD1 * a22 - a12 * dD2) - dD0 * m1 + a02 * (a01 * dD2 - dD1 * a02));
+        X2 = d * (a00 * (a11 * dD2 - dD1 * a12) - a01 * (a01 * dD2 - dD1 * a02) + dD0 * m2);
+      }
+      xi = -X2; xr = -X1; xc = -X0;
+      if (fabsf(xi) < 0.5f && fabsf(xr) < 0.5f && fabsf(xc) < 0.5f) break;
+      const float big = (float)(INT32_MAX / 3);
+      if (fabsf(xi) > big || fabsf(xr) > big || fabsf(xc) > big) { ok = false; break; }
+      c += __float2int_rn(xc); r += __float2int_rn(xr); layer += __float2int_rn(xi);
+      if (layer < 1 || layer > nl || c < SIFT_BORDER || c >= cols - SIFT_BORDER || r < SIFT_BORDER || r >= rows - SIFT_BORDER) {
+        ok = false; break;
+      }
+    }
+    if (it >= 5) ok = false;
+    float kx = 0, ky = 0, ksize = 0, kresp = 0; int koct = 0;
+    if (ok) {
+      const float* img = dbase + (size_t)layer * lstride;
+      const float* prv = img - lstride;
+      const float* nxt = img + lstride;
+      const size_t q = (size_t)r * pitch + c;
+      const float dD0 = (img[q + 1] - img[q - 1]) * deriv_scale;
+      const float dD1 = (img[q + pitch] - img[q - pitch]) * deriv_scale;
+      const float dD2 = (nxt[q] - prv[q]) * deriv_scale;
+      const float t = dD0 * xc + dD1 * xr + dD2 * xi;
+      const float contr = img[q] * img_scale + t * 0.5f;
+      if (fabsf(contr) * nl < contrast_thr) ok = false;
+      const float v2 = img[q] * 2.f;
+      const float dxx = (img[q + 1] + img[q - 1] - v2) * second_deriv_scale;
+      const float dyy = (img[q + pitch] + img[q - pitch] - v2) * second_deriv_scale;
+      const float dxy = (img[q + pitch + 1] - img[q + pitch - 1] - img[q - pitch + 1] + img[q - pitch - 1]) * cross_deriv_scale;
+      const float tr = dxx + dyy, det = dxx * dyy - dxy * dxy;
+      if (det <= 0 || tr * tr * edge_thr >= (edge_thr + 1) * (edge_thr + 1) * det) ok = false;
+      kx = (c + xc) * (float)(1 << o);
+      ky = (r + xr) * (float)(1 << o);
+      koct = o + (layer << 8) + (__float2int_rn((xi + 0.5f) * 255.f) << 16);
+      ksize = sigma * vo_expf(__fdiv_rn((float)layer + xi, (float)nl) * 0.693147180559945f) * (float)(1 << o) * 2.f;
+      kresp = fabsf(contr);
+    }
+    if (!ok) continue;   // warp-uniform: every lane computed the same values
+
+    // ---- orientation histogram over the (2*radius+1)^2 window of gauss[o][layer]
+    const float scl_octv = ksize * 0.5f / (float)(1 << o);
+    const int radius = __float2int_rn(4.5f * scl_octv);
+    const float osig = 1.5f * scl_octv;
+    const float expf_scale = __fdiv_rn(-1.f, 2.f * osig * osig);
+    const float* gimg = gauss + oi.goff[o] + (size_t)layer * lstride + (size_t)b * rows * pitch;
+    for (int k = lane; k < ORI_BINS; k += 32) s_hist[wib][k] = 0;
+    __syncwarp();
+    const int side = 2 * radius + 1;
+    for (int idx = lane; idx < side * side; idx += 32) {
+      const int i = idx / side - radius, j = idx % side - radius;
+      const int y = r + i, x = c + j;
+      if (y <= 0 || y >= rows - 1 || x <= 0 || x >= cols - 1) continue;
+      const float dx = gimg[(size_t)y * pitch + x + 1] - gimg[(size_t)y * pitch + x - 1];
+      const float dy = gimg[(size_t)(y - 1) * pitch + x] - gimg[(size_t)(y + 1) * pitch + x];
+      const float wgt = vo_expf((float)(i * i + j * j) * expf_scale);
+      const float ang = vo_atan2deg(dy, dx);
+      const float mag = __fsqrt_rn(fmaf(dx, dx, dy * dy));
+      int bin = __float2int_rn((ORI_BINS / 360.f) * ang);
+      if (bin >= ORI_BINS) bin -= ORI_BINS;
+      if (bin < 0) bin += ORI_BINS;
+      atomicAdd(&s_hist[wib][bin], (uint32_t)__float2int_rn(wgt * mag * SIFT_FIX));
+    }
+    __syncwarp();
+    float* th = s_sm[wib];   // th[i + 2] = raw bin i, with 2 wrapped entries on each side
+    for (int k = lane; k < ORI_BINS; k += 32) th[k + 2] = (float)s_hist[wib][k] * SIFT_INV_FIX;
+    __syncwarp();
+    if (lane == 0) { th[1] = th[ORI_BINS + 1]; th[0] = th[ORI_BINS]; th[ORI_BINS + 2] = th[2]; th[ORI_BINS + 3] = th[3]; }
+    __syncwarp();
+    float hv[2];
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+      const int k = lane + 32 * rep;
+      hv[rep] = -1.f;
+      if (k < ORI_BINS)
+        hv[rep] = (th[k] + th[k + 4]) * (1.f / 16.f) + (th[k + 1] + th[k + 3]) * (4.f / 16.f) + th[k + 2] * (6.f / 16.f);
+    }
+    float mx = fmaxf(hv[0], hv[1]);
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    __syncwarp();
+    // smoothed histogram back to shared memory for neighbour access
+    float* hs = s_sm[wib];
+    __syncwarp();
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) { const int k = lane + 32 * rep; if (k < ORI_BINS) hs[k] = hv[rep]; }
+    __syncwarp();
+    const float mag_thr = mx * 0.8f;
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+      const int j = lane + 32 * rep;
+      bool peak = false; float angle = 0.f;
+      if (j < ORI_BINS) {
+        const int l = j > 0 ? j - 1 : ORI_BINS - 1, r2 = j < ORI_BINS - 1 ? j + 1 : 0;
+        const float hj = hs[j], hl = hs[l], hr = hs[r2];
+        if (hj > hl && hj > hr && hj >= mag_thr) {
+          float bin = j + __fdiv_rn(0.5f * (hl - hr), hl - 2 * hj + hr);
+          bin = bin < 0 ? ORI_BINS + bin : bin >= ORI_BINS ? bin - ORI_BINS : bin;
+          angle = 360.f - (360.f / ORI_BINS) * bin;
+          if (fabsf(angle - 360.f) < FLT_EPSILON) angle = 0.f;
+          peak = true;
+        }
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, peak);
+      if (mask) {
+        const int leader = __ffs(mask) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&counters[b * 4 + 1], __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (peak) {
+          const int slot = base + __popc(mask & ((1u << lane) - 1u));
+          if (slot < kp_cap) {
+            vo_keypoint kp; kp.x = kx; kp.y = ky; kp.size = ksize; kp.angle = angle; kp.response = kresp; kp.octave = koct;
+            raw[(size_t)b * kp_cap + slot] = kp;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ ordering + duplicates
+__device__ __forceinline__ bool kp_before(const vo_keypoint& a, int ia, const vo_keypoint& b, int ib) {
+  if (a.x != b.x) return a.x < b.x;
+  if (a.y != b.y) return a.y < b.y;
+  if (a.size != b.size) return a.size > b.size;
+  if (a.angle != b.angle) return a.angle < b.angle;
+  if (a.response != b.response) return a.response > b.response;
+  if (a.octave != b.octave) return a.octave > b.octave;
+  return ia < ib;
+}
+
+// rank sort: grid (kp_cap/256, batch)
+__global__ void __launch_bounds__(256)
+sift_rank_kernel(const vo_keypoint* __restrict__ raw, int kp_cap, const int* __restrict__ counters,
+                 vo_keypoint* __restrict__ sorted) {
+  __shared__ vo_keypoint tile[256];
+  const int b = blockIdx.y;
+  const int n = min(counters[b * 4 + 1], kp_cap);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (blockIdx.x * 256 >= n) return;
+  const vo_keypoint* src = raw + (size_t)b * kp_cap;
+  vo_keypoint me;
+  if (i < n) me = src[i];
+  int rank = 0;
+  for (int base = 0; base < n; base += 256) {
+    __syncthreads();
+    if (base + threadIdx.x < n) tile[threadIdx.x] = src[base + threadIdx.x];
+    __syncthreads();
+    const int m = min(256, n - base);
+    if (i < n)
+      for (int j = 0; j < m; ++j) rank += kp_before(tile[j], base + j, me, i) ? 1 : 0;
+  }
+  if (i < n) sorted[(size_t)b * kp_cap + rank] = me;
+}
+
+// one block per image: drop exact duplicates (x, y, size, angle), compact, apply the first-octave
+// (-1) adjustment: pt *= 0.5, size *= 0.5, octave word - 1
+__global__ void __launch_bounds__(1024)
+sift_dedupe_kernel(const vo_keypoint* __restrict__ sorted, int kp_cap, int* __restrict__ counters,
+                   vo_keypoint* __restrict__ out, float loc_offset) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int b = blockIdx.x;
+  const int n = min(counters[b * 4 + 1], kp_cap);
+  const vo_keypoint* src = sorted + (size_t)b * kp_cap;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    bool keep = false; vo_keypoint me;
+    if (i < n) {
+      me = src[i];
+      keep = true;
+      if (i > 0) {
+        const vo_keypoint p = src[i - 1];
+        keep = (p.x != me.x || p.y != me.y || p.size != me.size || p.angle != me.angle);
+      }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warp_sums[w] = __popc(ballot);
+    __syncthreads();
+    if (w == 0) {
+      int x = warp_sums[lane];
+      for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
+      }
+      warp_sums[lane] = x;
+    }
+    __syncthreads();
+    if (keep) {
+      const int pos = carry + (w ? warp_sums[w - 1] : 0) + __popc(ballot & ((1u << lane) - 1u));
+      me.octave = (me.octave & ~255) | ((me.octave - 1) & 255);
+      me.x = me.x * 0.5f + loc_offset; me.y = me.y * 0.5f + loc_offset; me.size *= 0.5f;
+      out[(size_t)b * kp_cap + pos] = me;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += warp_sums[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counters[b * 4 + 2] = carry;
+}
+
+// ------------------------------------------------------------------------------ descriptors
+__global__ void __launch_bounds__(128)
+sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int batch, int nl,
+                       const vo_keypoint* __restrict__ kps, int kp_cap, const int* __restrict__ counters,
+                       float loc_offset, float* __restrict__ desc) {
+  constexpr int D = 4, N = 8, HLEN = (D + 2) * (D + 2) * (N + 2);
+  __shared__ uint32_t s_hist[4][HLEN];
+  __shared__ float s_vec[4][128];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int n = min(counters[b * 4 + 2], kp_cap);
+  for (int ki = blockIdx.x * 4 + wib; ki < n; ki += gridDim.x * 4) {
+    const vo_keypoint kp = kps[(size_t)b * kp_cap + ki];
+    int oc = kp.octave & 255; const int layer = (kp.octave >> 8) & 255;
+    oc = oc < 128 ? oc : (-128 | oc);
+    const float scale = oc >= 0 ? __fdiv_rn(1.f, (float)(1 << oc)) : (float)(1 << -oc);
+    const float size = kp.size * scale;
+    float ori = 360.f - kp.angle;
+    if (fabsf(ori - 360.f) < FLT_EPSILON) ori = 0.f;
+    const int po = oc + 1;
+    const int rows = oi.h[po], cols = oi.w[po], pitch = oi.pitch[po];
+    const float* img = gauss + oi.goff[po] + (size_t)layer * batch * rows * pitch + (size_t)b * rows * pitch;
+    const float ptx = (kp.x - loc_offset) * scale, pty = (kp.y - loc_offset) * scale;
+    const float scl = size * 0.5f;
+    const int px = __float2int_rn(ptx), py = __float2int_rn(pty);
+    const double ang = (double)ori * (3.14159265358979323846 / 180.0);
+    float cos_t = (float)cos(ang), sin_t = (float)sin(ang);
+    const float bins_per_rad = N / 360.f, exp_scale = -1.f / (D * D * 0.5f);
+    const float hist_width = 3.0f * scl;
+    int radius = __float2int_rn(hist_width * 1.4142135623730951f * (D + 1) * 0.5f);
+    const int diag = (int)sqrt((double)cols * cols + (double)rows * rows);
+    if (radius > diag) radius = diag;
+    cos_t = __fdiv_rn(cos_t, hist_width); sin_t = __fdiv_rn(sin_t, hist_width);
+    for (int k = lane; k < HLEN; k += 32) s_hist[wib][k] = 0;
+    __syncwarp();
+    const int side = 2 * radius + 1;
+    for (int idx = lane; idx < side * side; idx += 32) {
+      const int i = idx / side - radius, j = idx % side - radius;
+      const float c_rot = j * cos_t - i * sin_t;
+      const float r_rot = j * sin_t + i * cos_t;
+      float rbin = r_rot + D / 2 - 0.5f, cbin = c_rot + D / 2 - 0.5f;
+      const int r = py + i, c = px + j;
+      if (!(rbin > -1 && rbin < D && cbin > -1 && cbin < D && r > 0 && r < rows - 1 && c > 0 && c < cols - 1)) continue;
+      const float dx = img[(size_t)r * pitch + c + 1] - img[(size_t)r * pitch + c - 1];
+      const float dy = img[(size_t)(r - 1) * pitch + c] - img[(size_t)(r + 1) * pitch + c];
+      const float wgt = vo_expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
+      const float a = vo_atan2deg(dy, dx);
+      const float mag = __fsqrt_rn(fmaf(dx, dx, dy * dy)) * wgt;
+      float obin = (a - ori) * bins_per_rad;
+      const int r0 = (int)floorf(rbin), c0 = (int)floorf(cbin);
+      int o0 = (int)floorf(obin);
+      rbin -= r0; cbin -= c0; obin -= o0;
+      if (o0 < 0) o0 += N;
+      if (o0 >= N) o0 -= N;
+      const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
+      const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11;
+      const float v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
+      const float v111 = v_rc11 * obin, v110 = v_rc11 - v111;
+      const float v101 = v_rc10 * obin, v100 = v_rc10 - v101;
+      const float v011 = v_rc01 * obin, v010 = v_rc01 - v011;
+      const float v001 = v_rc00 * obin, v000 = v_rc00 - v001;
+      uint32_t* hp = &s_hist[wib][((r0 + 1) * (D + 2) + c0 + 1) * (N + 2) + o0];
+      atomicAdd(hp, (uint32_t)__float2int_rn(v000 * SIFT_FIX));
+      atomicAdd(hp + 1, (uint32_t)__float2int_rn(v001 * SIFT_FIX));
+      atomicAdd(hp + (N + 2), (uint32_t)__float2int_rn(v010 * SIFT_FIX));
+      atomicAdd(hp + (N + 3), (uint32_t)__float2int_rn(v011 * SIFT_FIX));
+      atomicAdd(hp + (D + 2) * (N + 2), (uint32_t)__float2int_rn(v100 * SIFT_FIX));
+      atomicAdd(hp + (D + 2) * (N + 2) + 1, (uint32_t)__float2int_rn(v101 * SIFT_FIX));
+      atomicAdd(hp + (D + 3) * (N + 2), (uint32_t)__float2int_rn(v110 * SIFT_FIX));
+      atomicAdd(hp + (D + 3) * (N + 2) + 1, (uint32_t)__float2int_rn(v111 * SIFT_FIX));
+    }
+    __syncwarp();
+    // fold the circular orientation bins and flatten to 128 floats
+    for (int e = lane; e < 128; e += 32) {
+      const int k = e & 7, cell = e >> 3, i = cell >> 2, j = cell & 3;
+      const int idx = ((i + 1) * (D + 2) + (j + 1)) * (N + 2);
+      uint32_t v = s_hist[wib][idx + k];
+      if (k < 2) v += s_hist[wib][idx + N + k];
+      s_vec[wib][e] = (float)v * SIFT_INV_FIX;
+    }
+    __syncwarp();
+    float nrm2 = 0.f;
+    for (int k = 0; k < 128; ++k) nrm2 = fmaf(s_vec[wib][k], s_vec[wib][k], nrm2);   // oracle order
+    const float thr = __fsqrt_rn(nrm2) * 0.2f;
+    nrm2 = 0.f;
+    for (int k = 0; k < 128; ++k) {
+      const float v = fminf(s_vec[wib][k], thr);
+      nrm2 = fmaf(v, v, nrm2);
+    }
+    const float s = __fsqrt_rn(nrm2);
+    const float sc = __fdiv_rn(512.f, fmaxf(s, FLT_EPSILON));
+    float4 o4;
+    float* ov = reinterpret_cast<float*>(&o4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float v = rintf(fminf(s_vec[wib][4 * lane + q], thr) * sc);
+      ov[q] = v > 255.f ? 255.f : (v < 0.f ? 0.f : v);
+    }
+    reinterpret_cast<float4*>(desc + ((size_t)b * kp_cap + ki) * 128)[lane] = o4;
+    __syncwarp();
+  }
+}
+
+// --------------------------------------------------------------------------- host plumbing
+static void gauss_taps(float sigma, Taps* t) {
+  const int ksize = ((int)lrint((double)sigma * 8.0 + 1.0)) | 1;
+  const int r = ksize / 2;
+  double sum = 0, v[64];
+  const double s2 = -0.5 / ((double)sigma * (double)sigma);
+  for (int i = 0; i < ksize; ++i) {
+    const double x = i - (ksize - 1) * 0.5;
+    v[i] = std::exp(s2 * x * x);
+    sum += v[i];
+  }
+  sum = 1.0 / sum;
+  memset(t, 0, sizeof(*t));
+  t->r = r;
+  for (int i = 0; i <= r && i <= MAX_R; ++i) t->k[i] = (float)(v[r + i] * sum);
+}
+
+static size_t blur_smem(int R) {
+  const int in_w = ((TILE_W + 2 * R + 3) & ~3) + 4, in_h = TILE_H + 2 * R;
+  return (size_t)(in_h * in_w + in_h * TILE_W) * sizeof(float);
+}
+
+template <int RT, bool U8>
+static int launch_blur_t(const float* src, const uint8_t* src8, float* dst, float* dog, int h, int w, int pitch,
+                         int rows8, int cols8, int batch, const Taps& t, cudaStream_t st) {
+  static bool attr = false;
+  const size_t smem = blur_smem(t.r);
+  if (!attr) {
+    VO_CUDA(cudaFuncSetAttribute(sift_blur_dog_kernel<RT, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)blur_smem(RT > 0 ? RT : MAX_R)));
+    attr = true;
+  }
+  dim3 grid(div_up(w, TILE_W), div_up(h, TILE_H), batch);
+  sift_blur_dog_kernel<RT, U8><<<grid, 256, smem, st>>>(src, src8, dst, dog, h, w, pitch, rows8, cols8, t);
+  return VO_OK;
+}
+
+static int launch_blur(const float* src, float* dst, float* dog, int h, int w, int pitch, int batch, const Taps& t,
+                       cudaStream_t st) {
+  switch (t.r) {
+    case 5: return launch_blur_t<5, false>(src, nullptr, dst, dog, h, w, pitch, 0, 0, batch, t, st);
+    case 6: return launch_blur_t<6, false>(src, nullptr, dst, dog, h, w, pitch, 0, 0, batch, t, st);
+    case 8: return launch_blur_t<8, false>(src, nullptr, dst, dog, h, w, pitch, 0, 0, batch, t, st);
+    case 10: return launch_blur_t<10, false>(src, nullptr, dst, dog, h, w, pitch, 0, 0, batch, t, st);
+    case 13: return launch_blur_t<13, false>(src, nullptr, dst, dog, h, w, pitch, 0, 0, batch, t, st);
+    default: return launch_blur_t<0, false>(src, nullptr, dst, dog, h, w, pitch, 0, 0, batch, t, st);
+  }
+}
+
+static void fill_sift_opts(const vo_sift_opts* in, vo_sift_opts* o) {
+  o->contrast_threshold = 0.04f / 3.0f; o->edge_threshold = 10.f; o->num_layers_in_octave = 3; o->sigma = 1.6f; o->index_base = 0;
+  if (in) {
+    if (in->contrast_threshold > 0) o->contrast_threshold = in->contrast_threshold;
+    if (in->edge_threshold > 0) o->edge_threshold = in->edge_threshold;
+    if (in->num_layers_in_octave > 0) o->num_layers_in_octave = in->num_layers_in_octave;
+    if (in->sigma > 0) o->sigma = in->sigma;
+    o->index_base = in->index_base;
+  }
+}
+
+static int get_plan(vo_ctx* ctx, int rows, int cols, int batch, const vo_sift_opts& o, int capacity, SiftPlan** out) {
+  SiftPlan* p = ctx->sift_plan;
+  const int nl = o.num_layers_in_octave;
+  int kp_cap = ((capacity > 4096 ? capacity : 4096) + 1023) / 1024 * 1024;
+  if (p && p->rows == rows && p->cols == cols && p->batch >= batch && p->nl == nl && p->sigma == o.sigma && p->kp_cap >= kp_cap) {
+    *out = p; return VO_OK;
+  }
+  if (p) { VO_CUDA(cudaStreamSynchronize(ctx->stream)); sift_plan_destroy(p); ctx->sift_plan = nullptr; }
+  if (nl > 5) { set_error("vo_sift: NumLayersInOctave > 5 is not supported"); return VO_ERR_ARG; }
+  p = new SiftPlan();
+  p->rows = rows; p->cols = cols; p->batch = batch; p->nl = nl; p->sigma = o.sigma;
+  const int R2 = rows * 2, C2 = cols * 2;
+  int n_oct = (int)lrint(std::log((double)(R2 < C2 ? R2 : C2)) / std::log(2.0) - 2.0) + 1;
+  if (n_oct < 1) n_oct = 1;
+  if (n_oct > MAX_OCT) n_oct = MAX_OCT;
+  size_t gtot = 0, dtot = 0;
+  int used = 0;
+  for (int oc = 0; oc < n_oct; ++oc) {
+    p->h[oc] = oc == 0 ? R2 : p->h[oc - 1] / 2;
+    p->w[oc] = oc == 0 ? C2 : p->w[oc - 1] / 2;
+    if (p->h[oc] < 1 || p->w[oc] < 1) break;
+    p->pitch[oc] = (p->w[oc] + 31) / 32 * 32;
+    p->goff[oc] = gtot; p->doff[oc] = dtot;
+    gtot += (size_t)(nl + 3) * p->layer_elems(oc);
+    dtot += (size_t)(nl + 2) * p->layer_elems(oc);
+    used = oc + 1;
+  }
+  p->n_oct = used;
+  const double k = std::pow(2.0, 1.0 / nl);
+  for (int i = 1; i < nl + 3; ++i) {
+    const double sp = std::pow(k, (double)(i - 1)) * o.sigma, stt = sp * k;
+    gauss_taps((float)std::sqrt(stt * stt - sp * sp), &p->taps[i]);
+    if (p->taps[i].r > MAX_R) { set_error("vo_sift: Sigma too large for the blur kernels"); sift_plan_destroy(p); return VO_ERR_ARG; }
+  }
+  const float sd2 = o.sigma * o.sigma - 0.5f * 0.5f * 4.0f;
+  gauss_taps(sqrtf(sd2 > 0.01f ? sd2 : 0.01f), &p->base_taps);
+  if (p->base_taps.r > MAX_R) { set_error("vo_sift: Sigma too large"); sift_plan_destroy(p); return VO_ERR_ARG; }
+  p->kp_cap = kp_cap; p->cand_cap = kp_cap * 8;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes); };
+  A((void**)&p->gauss, gtot * sizeof(float)); A((void**)&p->dog, dtot * sizeof(float));
+  A((void**)&p->img, (size_t)batch * rows * cols); A((void**)&p->img_t, (size_t)batch * rows * cols);
+  A((void**)&p->cand, (size_t)batch * p->cand_cap * sizeof(uint32_t)); A((void**)&p->counters, (size_t)batch * 4 * sizeof(int));
+  A((void**)&p->raw, (size_t)batch * kp_cap * sizeof(vo_keypoint)); A((void**)&p->sorted, (size_t)batch * kp_cap * sizeof(vo_keypoint));
+  A((void**)&p->final_kp, (size_t)batch * kp_cap * sizeof(vo_keypoint)); A((void**)&p->desc, (size_t)batch * kp_cap * 128 * sizeof(float));
+  if (e != cudaSuccess) { set_error("vo_sift: device allocation failed: %s", cudaGetErrorString(e)); sift_plan_destroy(p); return VO_ERR_CUDA; }
+  ctx->sift_plan = p; *out = p;
+  return VO_OK;
+}
+
+// Runs the whole detector+descriptor on p->img (device, batch images) -> p->final_kp / p->desc / counters.
+int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, cudaStream_t st) {
+  const int nl = p->nl;
+  VO_CUDA(cudaMemsetAsync(p->counters, 0, (size_t)batch * 4 * sizeof(int), st));
+  // pyramid
+  if (p->base_taps.r == 5)
+    VO_TRY((launch_blur_t<5, true>(nullptr, p->img, p->G(0, 0), nullptr, p->h[0], p->w[0], p->pitch[0], p->rows, p->cols, batch, p->base_taps, st)));
+  else
+    VO_TRY((launch_blur_t<0, true>(nullptr, p->img, p->G(0, 0), nullptr, p->h[0], p->w[0], p->pitch[0], p->rows, p->cols, batch, p->base_taps, st)));
+  // note: layer_elems uses p->batch; kernels index images with the plan's batch stride
+  for (int oc = 0; oc < p->n_oct; ++oc) {
+    if (oc > 0) {
+      dim3 g(div_up(p->w[oc], 256), p->h[oc], batch);
+      sift_downsample_kernel<<<g, 256, 0, st>>>(p->G(oc - 1, nl), p->G(oc, 0), p->h[oc - 1], p->pitch[oc - 1], p->h[oc], p->w[oc], p->pitch[oc]);
+    }
+    for (int i = 1; i < nl + 3; ++i)
+      VO_TRY(launch_blur(p->G(oc, i - 1), p->G(oc, i), p->D(oc, i - 1), p->h[oc], p->w[oc], p->pitch[oc], batch, p->taps[i], st));
+  }
+  VO_CUDA(cudaGetLastError());
+  // extrema
+  const float contrast_cv = o.contrast_threshold * nl;   // OpenCV-style threshold (0.04)
+  const float threshold = (float)(int)std::floor(0.5 * contrast_cv / nl * 255.0);
+  for (int oc = 0; oc < p->n_oct; ++oc) {
+    if (p->h[oc] <= 2 * SIFT_BORDER || p->w[oc] <= 2 * SIFT_BORDER) continue;
+    dim3 g(div_up(p->w[oc], 32), div_up(p->h[oc], 8), batch * nl);
+    sift_extrema_kernel<<<g, 256, 0, st>>>(p->D(oc, 0), oc, nl, p->batch, p->h[oc], p->w[oc], p->pitch[oc], threshold, p->cand, p->cand_cap, p->counters);
+  }
+  OctInfo oi;
+  memset(&oi, 0, sizeof(oi));
+  for (int oc = 0; oc < p->n_oct; ++oc) { oi.h[oc] = p->h[oc]; oi.w[oc] = p->w[oc]; oi.pitch[oc] = p->pitch[oc]; oi.goff[oc] = p->goff[oc]; oi.doff[oc] = p->doff[oc]; }
+  {
+    dim3 g(ctx->num_sms * 4 / (batch > 4 ? 4 : 1), batch);
+    sift_refine_orient_kernel<<<g, 128, 0, st>>>(p->gauss, p->dog, oi, p->batch, nl, contrast_cv, o.edge_threshold, o.sigma, p->cand, p->cand_cap, p->counters, p->raw, p->kp_cap);
+  }
+  {
+    dim3 g(p->kp_cap / 256, batch);
+    sift_rank_kernel<<<g, 256, 0, st>>>(p->raw, p->kp_cap, p->counters, p->sorted);
+    sift_dedupe_kernel<<<batch, 1024, 0, st>>>(p->sorted, p->kp_cap, p->counters, p->final_kp, (float)o.index_base);
+  }
+  {
+    dim3 g(ctx->num_sms * 4 / (batch > 4 ? 4 : 1), batch);
+    sift_descriptor_kernel<<<g, 128, 0, st>>>(p->gauss, oi, p->batch, nl, p->final_kp, p->kp_cap, p->counters, (float)o.index_base, p->desc);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+// accessors used by the frame pipeline
+int sift_prepare(vo_ctx* ctx, int rows, int cols, int batch, const vo_sift_opts* opts, int capacity, SiftPlan** plan, vo_sift_opts* filled) {
+  fill_sift_opts(opts, filled);
+  return get_plan(ctx, rows, cols, batch, *filled, capacity, plan);
+}
+uint8_t* sift_plan_images(SiftPlan* p) { return p->img; }
+vo_keypoint* sift_plan_keypoints(SiftPlan* p) { return p->final_kp; }
+float* sift_plan_desc(SiftPlan* p) { return p->desc; }
+int* sift_plan_counters(SiftPlan* p) { return p->counters; }
+int sift_plan_kp_cap(SiftPlan* p) { return p->kp_cap; }
+
+}  // namespace vo
+
+using namespace vo;
+
+static int sift_host(vo_ctx* ctx, const uint8_t* imgs, int n_img, int rows, int cols, int ld, int col_major,
+                     const vo_sift_opts* opts, int capacity, vo_keypoint* kps, float* desc, int* n_out) {
+  VO_CHECK_ARG(ctx && imgs && n_out, "null argument");
+  VO_CHECK_ARG(n_img > 0 && rows > 0 && cols > 0 && capacity >= 0, "bad size");
+  VO_CHECK_ARG(rows <= 4095 / 2 && cols <= 8191 / 2, "image too large (max 2047 x 4095)");
+  VO_CHECK_ARG(capacity == 0 || (kps && desc), "null output");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  vo_sift_opts o; SiftPlan* p;
+  VO_TRY(sift_prepare(ctx, rows, cols, n_img, opts, capacity, &p, &o));
+  if (col_major) {
+    for (int b = 0; b < n_img; ++b)
+      VO_CUDA(cudaMemcpy2DAsync(p->img_t + (size_t)b * rows * cols, rows, imgs + (size_t)b * ld * cols, ld, rows, cols, cudaMemcpyHostToDevice, st));
+    dim3 g(div_up(cols, 32), div_up(rows, 32));
+    for (int b = 0; b < n_img; ++b)
+      sift_transpose_u8_kernel<<<g, dim3(32, 8), 0, st>>>(p->img_t + (size_t)b * rows * cols, p->img + (size_t)b * rows * cols, rows, cols, rows);
+  } else if (ld == cols) {
+    VO_CUDA(cudaMemcpyAsync(p->img, imgs, (size_t)n_img * rows * cols, cudaMemcpyHostToDevice, st));
+  } else {
+    for (int b = 0; b < n_img; ++b)
+      VO_CUDA(cudaMemcpy2DAsync(p->img + (size_t)b * rows * cols, cols, imgs + (size_t)b * ld * rows, ld, cols, rows, cudaMemcpyHostToDevice, st));
+  }
+  VO_TRY(sift_run_device(ctx, p, n_img, o, st));
+  int* hc; VO_TRY(pin_buf(ctx, "sift_counts", (size_t)n_img * 4, &hc));
+  VO_CUDA(cudaMemcpyAsync(hc, p->counters, (size_t)n_img * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaStreamSynchronize(st));
+  int rc = VO_OK;
+  for (int b = 0; b < n_img; ++b) {
+    int n = hc[b * 4 + 2];
+    if (hc[b * 4 + 0] > p->cand_cap || hc[b * 4 + 1] > p->kp_cap) {
+      set_error("vo_sift: internal capacity exceeded (candidates %d/%d, keypoints %d/%d); raise `capacity`", hc[b * 4 + 0], p->cand_cap, hc[b * 4 + 1], p->kp_cap);
+      rc = VO_ERR_CAPACITY;
+    }
+    n_out[b] = n;
+    if (n > capacity) { if (rc == VO_OK) set_error("vo_sift: %d keypoints exceed capacity %d", n, capacity); rc = VO_ERR_CAPACITY; n = capacity; }
+    if (n > 0) {
+      VO_CUDA(cudaMemcpyAsync(kps + (size_t)b * capacity, p->final_kp + (size_t)b * p->kp_cap, (size_t)n * sizeof(vo_keypoint), cudaMemcpyDeviceToHost, st));
+      VO_CUDA(cudaMemcpyAsync(desc + (size_t)b * capacity * 128, p->desc + (size_t)b * p->kp_cap * 128, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+  }
+  VO_CUDA(cudaStreamSynchronize(st));
+  return rc;
+}
+
+extern "C" {
+
+int vo_sift(vo_ctx* ctx, const uint8_t* img, int rows, int cols, int ld, int col_major, const vo_sift_opts* opts,
+            int capacity, vo_keypoint* kps, float* desc, int* n_out) {
+  return sift_host(ctx, img, 1, rows, cols, ld, col_major, opts, capacity, kps, desc, n_out);
+}
+
+int vo_sift_batch(vo_ctx* ctx, const uint8_t* imgs, int n_img, int rows, int cols, const vo_sift_opts* opts,
+                  int capacity, vo_keypoint* kps, float* desc, int* n_out) {
+  return sift_host(ctx, imgs, n_img, rows, cols, cols, 0, opts, capacity, kps, desc, n_out);
+}
+
+}  // extern "C"

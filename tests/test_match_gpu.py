@@ -1,0 +1,134 @@
+"""GPU parity of vo_match (tcgen05 GEMM + exact re-rank) against the CPU oracle: indices and
+metrics must be BIT-EXACT on identical descriptor inputs (north_star)."""
+import numpy as np
+import pytest
+
+from conftest import correlated_pair, sift_like_descriptors
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, f1, f2, **kw):
+    import vo_b200
+    pairs, metric = vo_b200.matchFeatures(f1, f2, return_metric=True, ctx=ctx, **kw)
+    okw = dict(match_threshold=kw.get("MatchThreshold", 1.0), max_ratio=kw.get("MaxRatio", 0.6),
+               unique=kw.get("Unique", False), index_base=kw.get("index_base", 0))
+    opairs, ometric = oracle.match(f1, f2, **okw)
+    assert pairs.shape == opairs.shape, (pairs.shape, opairs.shape)
+    assert np.array_equal(pairs, opairs)
+    assert np.array_equal(metric.view(np.uint32), ometric.view(np.uint32))
+    return pairs
+
+
+def test_debug_gemm_is_exact_integer_dot(ctx):
+    import vo_b200.api as api
+    f1 = sift_like_descriptors(300, 11)
+    f2 = sift_like_descriptors(700, 12)
+    c = api.match_debug_gemm(f1, f2, ctx=ctx)
+    ref = f1.astype(np.float64) @ f2.astype(np.float64).T
+    assert np.array_equal(c.astype(np.float64), ref)
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (1, 2), (2, 1), (3, 3), (5, 300), (127, 129), (128, 256),
+                                   (129, 257), (1000, 777), (2048, 2048), (3000, 3100)])
+def test_top2_bit_exact(ctx, n1, n2):
+    import vo_b200.api as api
+    f1, f2 = correlated_pair(n1, n2, seed=100 + n1 + n2)
+    j1, s1, s2 = api.match_top2(f1, f2, ctx=ctx)
+    oj1, os1, os2 = oracle.match_top2(f1, f2)
+    assert np.array_equal(j1, oj1)
+    assert np.array_equal(s1.view(np.uint32), os1.view(np.uint32))
+    assert np.array_equal(s2.view(np.uint32), os2.view(np.uint32))
+    assert ctx.match_stats()["exact_integer_path"]
+
+
+@pytest.mark.parametrize("n1,n2", [(64, 64), (500, 900), (3000, 2500)])
+def test_match_default_bit_exact(ctx, n1, n2):
+    pairs = _check(ctx, *correlated_pair(n1, n2, seed=7 + n1))
+    if n1 >= 500:
+        assert len(pairs) > 50            # the synthetic pairs really do match
+
+
+def test_match_options(ctx):
+    f1, f2 = correlated_pair(800, 800, seed=3)
+    _check(ctx, f1, f2, MatchThreshold=10.0, MaxRatio=0.8)
+    _check(ctx, f1, f2, index_base=1)
+    _check(ctx, f1, f2, Unique=True)
+
+
+def test_empty_and_tiny(ctx):
+    import vo_b200
+    e = np.zeros((0, 128), dtype=np.float32)
+    f = sift_like_descriptors(10, 1)
+    assert vo_b200.matchFeatures(e, f, ctx=ctx).shape == (0, 2)
+    assert vo_b200.matchFeatures(f, e, ctx=ctx).shape == (0, 2)
+    _check(ctx, f[:1], f[:1])          # n2 == 1: no ratio test
+    _check(ctx, f, f[:2])
+
+
+def test_adversarial_ties(ctx):
+    """5 % duplicated rows and rows differing by +-1 in one bin (SURVEY.md 8d config 4 ii): ties must
+    resolve to the lowest index, exactly like the oracle; triple duplicates go through the row scan."""
+    rng = np.random.default_rng(5)
+    f2 = sift_like_descriptors(1500, 21)
+    dup = rng.permutation(1500)[:150]
+    f2[dup[:75]] = f2[dup[75:150]]                       # exact duplicates
+    f2[dup[:10]] = f2[dup[10]]                           # a 10-fold duplicate
+    near = rng.permutation(1500)[:75]
+    f2[near, rng.integers(0, 128, 75)] += 1.0
+    f1 = f2[rng.permutation(1500)[:900]].copy()
+    f1[::3, 5] = np.clip(f1[::3, 5] + 1, 0, 255)
+    import vo_b200.api as api
+    j1, s1, s2 = api.match_top2(f1, f2, ctx=ctx)
+    oj1, os1, os2 = oracle.match_top2(f1, f2)
+    assert np.array_equal(j1, oj1)
+    assert np.array_equal(s1.view(np.uint32), os1.view(np.uint32))
+    assert np.array_equal(s2.view(np.uint32), os2.view(np.uint32))
+    _check(ctx, f1, f2, MaxRatio=1.0)
+
+
+def test_general_float_path(ctx):
+    """Non-integer descriptors (unit-norm floats, as MATLAB might hand over): split-bf16 GEMM +
+    exact FP32 re-rank must still reproduce the oracle bit for bit."""
+    rng = np.random.default_rng(9)
+    f2 = np.abs(rng.standard_normal((1200, 128))).astype(np.float32)
+    f2 /= np.linalg.norm(f2, axis=1, keepdims=True)
+    f1 = f2[rng.permutation(1200)[:700]] + rng.normal(0, 0.01, (700, 128)).astype(np.float32)
+    f1 = f1.astype(np.float32)
+    import vo_b200.api as api
+    j1, s1, s2 = api.match_top2(f1, f2, ctx=ctx)
+    st = ctx.match_stats()
+    assert not st["exact_integer_path"]
+    oj1, os1, os2 = oracle.match_top2(f1, f2)
+    assert np.array_equal(j1, oj1)
+    assert np.array_equal(s1.view(np.uint32), os1.view(np.uint32))
+    assert np.array_equal(s2.view(np.uint32), os2.view(np.uint32))
+    assert st["rowscan_rows"] < 0.2 * len(f1)
+    _check(ctx, f1, f2)
+    # signed, non-normalised general floats
+    g1 = rng.standard_normal((333, 128)).astype(np.float32) * 3.0
+    g2 = rng.standard_normal((555, 128)).astype(np.float32) * 0.5
+    _check(ctx, g1, g2, MatchThreshold=100.0, MaxRatio=1.0)
+
+
+def test_col_major_inputs(ctx):
+    f1, f2 = correlated_pair(400, 500, seed=77)
+    import vo_b200
+    a = vo_b200.matchFeatures(np.asfortranarray(f1), np.asfortranarray(f2), ctx=ctx)
+    b, _ = oracle.match(f1, f2)
+    assert np.array_equal(a, b)
+
+
+def test_large_linearity_property(ctx):
+    """Full-size property (no oracle run): matching f2 against a row-permuted copy of itself returns
+    the permutation with metric 0 for every row that has a unique nearest neighbour."""
+    n = 16384
+    f2 = sift_like_descriptors(n, 1234)
+    perm = np.random.default_rng(1).permutation(n)
+    f1 = f2[perm]
+    import vo_b200.api as api
+    j1, s1, s2 = api.match_top2(f1, f2, ctx=ctx)
+    assert np.array_equal(j1, perm.astype(np.uint32))
+    assert float(s1.max()) <= 1e-6          # 2 - 2c with c one or two ulps below 1
+    assert float(s2.min()) > 0.1
