@@ -146,14 +146,19 @@ typedef struct {
   vo_match_opts match;
   vo_p3p_opts p3p;
   int max_keypoints;   /* per-image capacity; <= 0 -> 8192 */
+  int first_frame;     /* absolute index of frame 0 of this batch: keys the MSAC random stream so a
+                          frame gets the same samples however the sequence is cut into batches */
 } vo_frames_opts;
 
 /* One pass of the VO.m loop body over n_frames consecutive stereo frames held in host memory
- * (left/right: n_frames x rows x cols uint8).  Frame 0 only seeds the tracker (VO.m:207-210);
- * for frame i >= 1: SIFT x2, stereo match, find_remaining_points against frame i-1, batched
- * triangulation, P3P-MSAC.  rel_pose[16*i] = rel_pose.A of frame i (row-major; identity for
- * i = 0), status[i] = estworldpose status, counts[6*i..] = {N_L, N_R, stereo, K1..K4 -> K4, inl}.
- * The pose chain pose = pose * rel_pose (VO.m:130) is left to the caller: it is sequential. */
+ * (left/right: n_frames x rows x cols uint8, row-major).  Frame 0 only seeds the tracker
+ * (VO.m:207-210); for frame i >= 1: SIFT x2, stereo match, find_remaining_points against frame
+ * i-1 (VO.m:280-334), batched triangulation of the previous pair, P3P-MSAC.
+ * rel_pose[16*i] = rel_pose.A of frame i (row-major; identity for i = 0), status[i] = estworldpose
+ * status (0 ok, 1 too few points, 2 too few inliers),
+ * counts[8*i..] = {N_L, N_R, K0 (stereo), K1, K2, K3, K4 (tracked), inliers}  (may be NULL).
+ * The pose chain pose = pose * rel_pose (VO.m:130) is left to the caller: it is sequential.
+ * To stream a long sequence call with overlapping batches [i0-1, i0+B). */
 int vo_frames(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_frames, int rows,
               int cols, const double P1[12], const double P2[12], const vo_frames_opts* opts,
               double* rel_pose, int* status, int* counts);

@@ -38,7 +38,7 @@ class P3POpts(C.Structure):
 
 class FramesOpts(C.Structure):
     _fields_ = [("sift", SiftOpts), ("match", MatchOpts), ("p3p", P3POpts),
-                ("max_keypoints", C.c_int)]
+                ("max_keypoints", C.c_int), ("first_frame", C.c_int)]
 
 
 # every symbol include/vo_b200.h declares (tests check that the .so exports each one)

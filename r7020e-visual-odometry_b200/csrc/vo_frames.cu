@@ -1,7 +1,191 @@
-// placeholder until the frame pipeline lands
+// vo_frames.cu -- one pass of the VO.m loop body (VO.m:64-232) over a batch of stereo frames,
+// entirely on the device: no host round trip between SIFT, the five matchFeatures calls,
+// find_remaining_points' index chain (VO.m:280-334), triangulation and P3P-MSAC.
+//
+// Frame i of the batch uses images 2i (left) and 2i+1 (right) of the SIFT plan.  Problem p of the
+// tracking stage is the frame pair (p, p+1).  Every data-dependent size (keypoints per image,
+// K0..K4) lives in device memory; launch shapes depend on capacities only.
 #include "vo_internal.h"
-namespace vo { void frame_plan_destroy(FramePlan*) {} }
-extern "C" {
-int vo_frames(vo_ctx*, const uint8_t*, const uint8_t*, int, int, int, const double*, const double*, const vo_frames_opts*, double*, int*, int*) {
-  vo::set_error("vo_frames: not built yet"); return VO_ERR_STATE; }
+#include "vo_match.h"
+#include "vo_stages.h"
+
+namespace vo {
+
+void frame_plan_destroy(FramePlan*) {}
+
+// out_k[p][k] = src_k[p][idx[p][k]] for k < cnt[p]   (up to two arrays share one index list)
+__global__ void __launch_bounds__(256)
+compose_kernel(uint32_t* __restrict__ out1, const uint32_t* __restrict__ src1, uint32_t* __restrict__ out2,
+               const uint32_t* __restrict__ src2, const uint32_t* __restrict__ idx, const int* __restrict__ cnt,
+               int stride) {
+  const int p = blockIdx.y;
+  const int n = min(cnt[p], stride);
+  for (int k = blockIdx.x * 256 + threadIdx.x; k < n; k += gridDim.x * 256) {
+    const uint32_t j = idx[(size_t)p * stride + k];
+    if (out1) out1[(size_t)p * stride + k] = src1[(size_t)p * stride + j];
+    if (out2) out2[(size_t)p * stride + k] = src2[(size_t)p * stride + j];
+  }
+}
+
+// final gather of find_remaining_points + the Location reads of VO.m:114,124:
+//   old L/R pixel positions (previous frame, for triangulation), current L positions (for P3P)
+__global__ void __launch_bounds__(256)
+gather_points_kernel(const vo_keypoint* __restrict__ kps, int kp_cap, const uint32_t* __restrict__ oL2,
+                     const uint32_t* __restrict__ oR2, const uint32_t* __restrict__ cL3,
+                     const uint32_t* __restrict__ a4, const uint32_t* __restrict__ b4, const int* __restrict__ k4,
+                     double* __restrict__ old_l, double* __restrict__ old_r, double* __restrict__ cur_l) {
+  const int p = blockIdx.y;
+  const int n = min(k4[p], kp_cap);
+  const vo_keypoint* kl0 = kps + (size_t)(2 * p) * kp_cap;       // previous left
+  const vo_keypoint* kr0 = kps + (size_t)(2 * p + 1) * kp_cap;   // previous right
+  const vo_keypoint* kl1 = kps + (size_t)(2 * p + 2) * kp_cap;   // current left
+  for (int k = blockIdx.x * 256 + threadIdx.x; k < n; k += gridDim.x * 256) {
+    const size_t o = (size_t)p * kp_cap + k;
+    const uint32_t ia = a4[o], ib = b4[o];
+    const vo_keypoint ol = kl0[oL2[(size_t)p * kp_cap + ib]];
+    const vo_keypoint orr = kr0[oR2[(size_t)p * kp_cap + ib]];
+    const vo_keypoint cl = kl1[cL3[(size_t)p * kp_cap + ia]];
+    old_l[2 * o] = (double)ol.x; old_l[2 * o + 1] = (double)ol.y;
+    old_r[2 * o] = (double)orr.x; old_r[2 * o + 1] = (double)orr.y;
+    cur_l[2 * o] = (double)cl.x; cur_l[2 * o + 1] = (double)cl.y;
+  }
+}
+
+}  // namespace vo
+
+using namespace vo;
+
+extern "C" int vo_frames(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n, int rows, int cols,
+                         const double P1[12], const double P2[12], const vo_frames_opts* opts, double* rel_pose,
+                         int* status, int* counts) {
+  VO_CHECK_ARG(ctx && left && right && P1 && P2 && rel_pose && status, "null argument");
+  VO_CHECK_ARG(n >= 1 && rows > 0 && cols > 0, "bad size");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  vo_match_opts mo; fill_match_opts(opts ? &opts->match : nullptr, &mo);
+  mo.index_base = 0; mo.unique = 0;
+  vo_p3p_opts po; fill_p3p_opts(opts ? &opts->p3p : nullptr, &po);
+  const int want_cap = (opts && opts->max_keypoints > 0) ? opts->max_keypoints : 8192;
+  const int first_frame = opts ? opts->first_frame : 0;
+  SiftPlan* plan; vo_sift_opts so;
+  VO_TRY(sift_prepare(ctx, rows, cols, 2 * n, opts ? &opts->sift : nullptr, want_cap, &plan, &so));
+  const int kc = sift_plan_kp_cap(plan);
+  const size_t img_bytes = (size_t)rows * cols;
+  uint8_t* dimg = sift_plan_images(plan);
+  VO_CUDA(cudaMemcpy2DAsync(dimg, 2 * img_bytes, left, img_bytes, img_bytes, n, cudaMemcpyHostToDevice, st));
+  VO_CUDA(cudaMemcpy2DAsync(dimg + img_bytes, 2 * img_bytes, right, img_bytes, img_bytes, n, cudaMemcpyHostToDevice, st));
+  VO_TRY(sift_run_device(ctx, plan, 2 * n, so, st));
+  const float* desc = sift_plan_desc(plan);
+  const vo_keypoint* kps = sift_plan_keypoints(plan);
+  const int* cnt = sift_plan_counters(plan);
+  const size_t img_stride = (size_t)kc * 128;   // floats per image's descriptor block
+
+  // index / count arrays, [n][kc] each
+  uint32_t *l0, *r0, *a1, *b1, *oL1, *oR1, *a2, *b2, *oL2, *oR2, *a3, *b3, *cL3, *cR3, *a4, *b4;
+  uint32_t** arrs[] = {&l0, &r0, &a1, &b1, &oL1, &oR1, &a2, &b2, &oL2, &oR2, &a3, &b3, &cL3, &cR3, &a4, &b4};
+  uint32_t* pool; VO_TRY(dev_buf(ctx, "fr_idx", (size_t)16 * n * kc, &pool));
+  for (int i = 0; i < 16; ++i) *arrs[i] = pool + (size_t)i * n * kc;
+  int* K; VO_TRY(dev_buf(ctx, "fr_K", (size_t)5 * n + 8, &K));   // K[s*n + p], s = 0..4
+  VO_CUDA(cudaMemsetAsync(K, 0, ((size_t)5 * n + 8) * sizeof(int), st));
+
+  auto raw_op = [&](int first_img) {   // raw descriptor set of image (first_img + 2p)
+    MatchOperand o; o.base = desc + (size_t)first_img * img_stride; o.prob_stride = 2 * img_stride;
+    o.count = cnt + first_img * 4 + 2; o.count_stride = 8; o.cap = kc; return o;
+  };
+  auto gath_op = [&](int first_img, const uint32_t* g, const int* c) {
+    MatchOperand o = raw_op(first_img); o.gather = g; o.gather_stride = kc; o.count = c; o.count_stride = 1; return o;
+  };
+  MatchTop2 t;
+  // matched = matchFeatures(l_desc, r_desc)                                      VO.m:87
+  {
+    MatchOperand A = raw_op(0), B = raw_op(1);
+    VO_TRY(match_batch_top2(ctx, A, B, n, 128, "fr", nullptr, st, &t));
+    VO_TRY(match_batch_select(ctx, t, A, B, n, mo, l0, r0, nullptr, kc, K, 1, st));
+  }
+  const int np = n - 1;
+  const dim3 cg(8, np > 0 ? np : 1);
+  if (np > 0) {
+    // M1 = matchFeatures(cur.l_desc, old.l_desc)                                 VO.m:283
+    {
+      MatchOperand A = raw_op(2), B = gath_op(0, l0, K);
+      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t));
+      VO_TRY(match_batch_select(ctx, t, A, B, np, mo, a1, b1, nullptr, kc, K + n, 1, st));
+      compose_kernel<<<cg, 256, 0, st>>>(oL1, l0, oR1, r0, b1, K + n, kc);            // VO.m:287-290
+    }
+    // M2 = matchFeatures(cur.r_desc, old.r_desc)                                 VO.m:293
+    {
+      MatchOperand A = raw_op(3), B = gath_op(1, oR1, K + n);
+      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t));
+      VO_TRY(match_batch_select(ctx, t, A, B, np, mo, a2, b2, nullptr, kc, K + 2 * n, 1, st));
+      compose_kernel<<<cg, 256, 0, st>>>(oL2, oL1, oR2, oR1, b2, K + 2 * n, kc);      // VO.m:297-300
+    }
+    // M3 = matchFeatures(cur.l_desc(M1(:,1)), cur.r_desc(M2(:,1)))               VO.m:305-311
+    {
+      MatchOperand A = gath_op(2, a1, K + n), B = gath_op(3, a2, K + 2 * n);
+      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t));
+      VO_TRY(match_batch_select(ctx, t, A, B, np, mo, a3, b3, nullptr, kc, K + 3 * n, 1, st));
+      compose_kernel<<<cg, 256, 0, st>>>(cL3, a1, nullptr, nullptr, a3, K + 3 * n, kc);  // VO.m:314-315
+      compose_kernel<<<cg, 256, 0, st>>>(cR3, a2, nullptr, nullptr, b3, K + 3 * n, kc);  // VO.m:316-317
+    }
+    // M4 = matchFeatures(cur.l_desc, old.l_desc)                                 VO.m:323
+    {
+      MatchOperand A = gath_op(2, cL3, K + 3 * n), B = gath_op(0, oL2, K + 2 * n);
+      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t));
+      VO_TRY(match_batch_select(ctx, t, A, B, np, mo, a4, b4, nullptr, kc, K + 4 * n, 1, st));
+    }
+  }
+  // triangulate the old pair (VO.m:114) and estimate the pose (VO.m:123-127)
+  double *old_l, *old_r, *cur_l, *world, *dA, *dP;
+  VO_TRY(dev_buf(ctx, "fr_oldl", (size_t)n * kc * 2, &old_l));
+  VO_TRY(dev_buf(ctx, "fr_oldr", (size_t)n * kc * 2, &old_r));
+  VO_TRY(dev_buf(ctx, "fr_curl", (size_t)n * kc * 2, &cur_l));
+  VO_TRY(dev_buf(ctx, "fr_world", (size_t)n * kc * 3, &world));
+  VO_TRY(dev_buf(ctx, "fr_A", (size_t)n * 16, &dA));
+  VO_TRY(dev_buf(ctx, "fr_P", 32, &dP));
+  int* dstat; VO_TRY(dev_buf(ctx, "fr_stat", (size_t)n * 4, &dstat));
+  double hP[28];
+  for (int k = 0; k < 12; ++k) { hP[k] = P1[k]; hP[12 + k] = P2[k]; }
+  hP[24] = P1[0]; hP[25] = P1[5]; hP[26] = P1[2]; hP[27] = P1[6];   // fx fy cx cy (VO.m:35-38)
+  VO_CUDA(cudaMemcpyAsync(dP, hP, sizeof(hP), cudaMemcpyHostToDevice, st));
+  if (np > 0) {
+    gather_points_kernel<<<cg, 256, 0, st>>>(kps, kc, oL2, oR2, cL3, a4, b4, K + 4 * n, old_l, old_r, cur_l);
+    VO_TRY(triangulate_batch_device(old_l, old_r, K + 4 * n, 1, kc, np, dP, world, st));
+    vo_p3p_opts pp = po;
+    pp.seed = po.seed + (uint64_t)(first_frame + 1) * 0x9E3779B97F4A7C15ull;
+    VO_TRY(p3p_batch_device(ctx, cur_l, world, K + 4 * n, kc, np, dP + 24, pp, dA, nullptr, dstat, dstat + n, st));
+  }
+  // results
+  double* hA; VO_TRY(pin_buf(ctx, "fr_hA", (size_t)n * 16, &hA));
+  int* hI; VO_TRY(pin_buf(ctx, "fr_hI", (size_t)n * 4 + (size_t)5 * n + (size_t)2 * n * 4 + 16, &hI));
+  int* hK = hI + (size_t)n * 4;
+  int* hC = hK + (size_t)5 * n;
+  if (np > 0) {
+    VO_CUDA(cudaMemcpyAsync(hA, dA, (size_t)np * 16 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    VO_CUDA(cudaMemcpyAsync(hI, dstat, (size_t)n * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  VO_CUDA(cudaMemcpyAsync(hK, K, (size_t)5 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaMemcpyAsync(hC, cnt, (size_t)2 * n * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < 16; ++k) rel_pose[k] = (k % 5 == 0) ? 1.0 : 0.0;
+  status[0] = 0;
+  int rc = VO_OK;
+  for (int i = 0; i < n; ++i) {
+    if (i >= 1) {
+      memcpy(rel_pose + 16 * i, hA + 16 * (i - 1), 16 * sizeof(double));
+      status[i] = hI[i - 1];
+    }
+    const int nl = hC[(2 * i) * 4 + 2], nr = hC[(2 * i + 1) * 4 + 2];
+    if (nl > kc || nr > kc || hC[(2 * i) * 4 + 1] > kc || hC[(2 * i + 1) * 4 + 1] > kc) {
+      set_error("vo_frames: frame %d has more keypoints (%d / %d) than max_keypoints capacity %d", i, nl, nr, kc);
+      rc = VO_ERR_CAPACITY;
+    }
+    if (counts) {
+      int* c = counts + 8 * i;
+      c[0] = nl; c[1] = nr; c[2] = hK[i];
+      c[3] = i >= 1 ? hK[n + i - 1] : 0; c[4] = i >= 1 ? hK[2 * n + i - 1] : 0;
+      c[5] = i >= 1 ? hK[3 * n + i - 1] : 0; c[6] = i >= 1 ? hK[4 * n + i - 1] : 0;
+      c[7] = i >= 1 ? hI[n + 3 * (i - 1)] : 0;
+    }
+  }
+  return rc;
 }

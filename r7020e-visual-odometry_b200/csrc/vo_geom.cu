@@ -104,15 +104,19 @@ __device__ void dlt_point(const double p1[2], const double p2[2], const double* 
 }
 
 // P: [2][12] projection matrices in global memory.  pts as n x 2 (row-major: ld=2,stride 1;
-// col-major: element (i,c) at [c*n + i]).
+// col-major: element (i,c) at [c*n + i]).  grid (ceil(cap/128), problems); problem p uses the
+// slices [p*cap, (p+1)*cap) of every array and count np[p*np_stride] (np == null: cap).
 template <typename T>
 __global__ void __launch_bounds__(128)
 triangulate_kernel(const T* __restrict__ pts1, const T* __restrict__ pts2, const int* __restrict__ np,
-                   int n_cap, int col_major, const double* __restrict__ P, T* __restrict__ xyz,
+                   int np_stride, int n_cap, int col_major, const double* __restrict__ P, T* __restrict__ xyz,
                    T* __restrict__ err, uint8_t* __restrict__ valid) {
-  const int n = np ? *np : n_cap;
+  const int prob = blockIdx.y;
+  int n = np ? np[prob * np_stride] : n_cap;
+  if (n > n_cap) n = n_cap;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  pts1 += (size_t)prob * n_cap * 2; pts2 += (size_t)prob * n_cap * 2; xyz += (size_t)prob * n_cap * 3;
   const int ld = col_major ? n : 1, st = col_major ? 1 : 2;
   const double p1[2] = {(double)pts1[(size_t)i * st], (double)pts1[(size_t)i * st + ld]};
   const double p2[2] = {(double)pts2[(size_t)i * st], (double)pts2[(size_t)i * st + ld]};
@@ -136,8 +140,8 @@ triangulate_kernel(const T* __restrict__ pts1, const T* __restrict__ pts2, const
     esum += sqrt(du * du + dv * dv);
     if (!(d > 0)) ok = 0;
   }
-  if (err) err[i] = (T)(0.5 * esum);
-  if (valid) valid[i] = (uint8_t)ok;
+  if (err) err[(size_t)prob * n_cap + i] = (T)(0.5 * esum);
+  if (valid) valid[(size_t)prob * n_cap + i] = (uint8_t)ok;
 }
 
 // ------------------------------------------------------------------------------------- P3P
@@ -445,10 +449,10 @@ int p3p_batch_device(vo_ctx* ctx, const double* img, const double* world, const 
   return VO_OK;
 }
 
-int triangulate_device(const double* pts1, const double* pts2, const int* n_dev, int n_cap, const double* P_dev,
-                       double* xyz, double* err, uint8_t* valid, cudaStream_t st) {
-  if (n_cap <= 0) return VO_OK;
-  triangulate_kernel<double><<<div_up(n_cap, 128), 128, 0, st>>>(pts1, pts2, n_dev, n_cap, 0, P_dev, xyz, err, valid);
+int triangulate_batch_device(const double* pts1, const double* pts2, const int* n_dev, int n_stride, int cap, int n_prob,
+                             const double* P_dev, double* xyz, cudaStream_t st) {
+  if (cap <= 0 || n_prob <= 0) return VO_OK;
+  triangulate_kernel<double><<<dim3(div_up(cap, 128), n_prob), 128, 0, st>>>(pts1, pts2, n_dev, n_stride, cap, 0, P_dev, xyz, nullptr, nullptr);
   VO_CUDA(cudaGetLastError());
   return VO_OK;
 }
@@ -480,10 +484,10 @@ int vo_triangulate(vo_ctx* ctx, const void* pts1, const void* pts2, int n, int i
   VO_CUDA(cudaMemcpyAsync(dP, P1, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
   VO_CUDA(cudaMemcpyAsync(dP + 12, P2, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
   if (is_double)
-    triangulate_kernel<double><<<div_up(n, 128), 128, 0, st>>>((const double*)d1, (const double*)d2, nullptr, n, col_major, dP,
+    triangulate_kernel<double><<<div_up(n, 128), 128, 0, st>>>((const double*)d1, (const double*)d2, nullptr, 0, n, col_major, dP,
                                                                (double*)dx, (double*)de, dv);
   else
-    triangulate_kernel<float><<<div_up(n, 128), 128, 0, st>>>((const float*)d1, (const float*)d2, nullptr, n, col_major, dP,
+    triangulate_kernel<float><<<div_up(n, 128), 128, 0, st>>>((const float*)d1, (const float*)d2, nullptr, 0, n, col_major, dP,
                                                               (float*)dx, (float*)de, dv);
   VO_CUDA(cudaGetLastError());
   VO_CUDA(cudaMemcpyAsync(xyz, dx, (size_t)n * 3 * es, cudaMemcpyDeviceToHost, st));

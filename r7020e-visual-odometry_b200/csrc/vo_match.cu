@@ -22,6 +22,7 @@
 //
 // Score arithmetic is the contract in oracle/match.c (DESIGN.md "match arithmetic").
 #include "vo_internal.h"
+#include "vo_match.h"
 #include <cuda_bf16.h>
 #include <cfloat>
 
@@ -66,10 +67,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -124,13 +125,17 @@ struct Top3 {
 };
 
 // ------------------------------------------------------------------------- the GEMM kernel
+// grid (row panels, column splits, problems).  Counts are read from device memory, so the launch
+// shape depends only on capacities; CTAs outside the live problem exit (or publish empty slots).
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const float* __restrict__ invb, const int* __restrict__ n1p,
-                  const int* __restrict__ n2p, const int* __restrict__ nonint_flag, int kp_blocks,
-                  int n_splits, uint2* __restrict__ cand, float* __restrict__ dbg_c, int dbg_ld) {
+                  const float* __restrict__ invb_base, int invb_stride, const int* __restrict__ n1p,
+                  int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
+                  const int* __restrict__ nonint_flag, int kp_blocks, int n_splits,
+                  uint2* __restrict__ cand_base, size_t cand_stride, float* __restrict__ dbg_c, int dbg_ld) {
   extern __shared__ uint8_t smem_raw[];
-  const int n1 = *n1p, n2 = *n2p;
+  const int prob = blockIdx.z;
+  const int n1 = min(n1p[prob * n1_stride], cap1), n2 = min(n2p[prob * n2_stride], cap2);
   const int m0 = blockIdx.x * BM;
   if (m0 >= n1) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -139,6 +144,8 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int t_begin = (int)((long long)split * tiles_total / n_splits);
   const int t_end = (int)((long long)(split + 1) * tiles_total / n_splits);
   const int n_slots = n_splits * 2;
+  uint2* cand = cand_base + (size_t)prob * cand_stride;
+  const float* invb = invb_base + (size_t)prob * invb_stride;
 
   if (t_begin >= t_end) {  // nothing to contract: publish empty candidate slots
     if (warp >= 2) {
@@ -185,13 +192,13 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
       mbar_expect_tx(bar_a_full, kblocks * A_KBLOCK_BYTES);
-      for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(sA + kb * A_KBLOCK_BYTES, &tmA, bar_a_full, kb * BK, m0);
+      for (int kb = 0; kb < kblocks; ++kb) tma_load_3d(sA + kb * A_KBLOCK_BYTES, &tmA, bar_a_full, kb * BK, m0, prob);
       int stage = 0; uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t)
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
           mbar_expect_tx(bar_b_full + 8 * stage, B_STAGE_BYTES);
-          tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, bar_b_full + 8 * stage, kb * BK, t * BN);
+          tma_load_3d(sB + stage * B_STAGE_BYTES, &tmB, bar_b_full + 8 * stage, kb * BK, t * BN, prob);
           if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
         }
     }
@@ -291,37 +298,45 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 __global__ void match_set_counts_kernel(int* counts, int n1, int n2) {
   if (threadIdx.x == 0) { counts[0] = n1; counts[1] = n2; }
-  else if (threadIdx.x >= 2 && threadIdx.x < 8) counts[threadIdx.x] = 0;
 }
 
 // ------------------------------------------------------------------------------ prep kernel
-// 32 rows per block.  Writes out[row][3*kp] bf16 (A: hi|hi|lo, B: hi|lo|hi), inv[row], an optional
-// row-major fp32 copy, and ORs the "not an integer in 0..255" flag.
+// grid (cap_pad / 32, problems).  Writes out[p][row][3*kp] bf16 (A: hi|hi|lo, B: hi|lo|hi),
+// inv[p][row] (0 for rows >= n), an optional compact row-major fp32 copy (needed when rows are
+// gathered or column-major), and ORs the "not an integer in 0..255" flag.
 constexpr int PREP_ROWS = 32;
 __global__ void __launch_bounds__(256)
-match_prep_kernel(const float* __restrict__ f, const int* __restrict__ np, int n_cap, int dim, int kp,
-                  int col_major, int is_b, __nv_bfloat16* __restrict__ out, float* __restrict__ raw_rm,
-                  float* __restrict__ inv, int* __restrict__ nonint_flag) {
+match_prep_kernel(const MatchOperand op, int rows_alloc, int dim, int kp, int is_b,
+                  __nv_bfloat16* __restrict__ out, float* __restrict__ raw_copy, float* __restrict__ inv,
+                  int* __restrict__ nonint_flag) {
   extern __shared__ float tile[];  // [PREP_ROWS][dim + 1]
-  const int n = *np;
+  const int prob = blockIdx.y;
+  const int n = min(op.count[prob * op.count_stride], op.cap);
   const int row0 = blockIdx.x * PREP_ROWS;
   const int ldt = dim + 1;
   const int tid = threadIdx.x;
+  float* inv_p = inv + (size_t)prob * rows_alloc;
   if (row0 >= n) {
-    // rows past n inside the capacity: keep inv finite so padded loads are harmless
     for (int r = tid; r < PREP_ROWS; r += 256)
-      if (row0 + r < n_cap) inv[row0 + r] = 0.f;
+      if (row0 + r < rows_alloc) inv_p[row0 + r] = 0.f;
     return;
   }
-  if (!col_major) {
+  const float* f = op.base + (size_t)prob * op.prob_stride;
+  const uint32_t* g = op.gather ? op.gather + (size_t)prob * op.gather_stride : nullptr;
+  if (!op.col_major) {
     for (int idx = tid; idx < PREP_ROWS * dim; idx += 256) {
       const int r = idx / dim, k = idx - r * dim;
-      tile[r * ldt + k] = (row0 + r < n) ? f[(size_t)(row0 + r) * dim + k] : 0.f;
+      float v = 0.f;
+      if (row0 + r < n) {
+        const size_t src_row = g ? (size_t)g[row0 + r] : (size_t)(row0 + r);
+        v = f[src_row * dim + k];
+      }
+      tile[r * ldt + k] = v;
     }
   } else {
     for (int idx = tid; idx < PREP_ROWS * dim; idx += 256) {
       const int k = idx / PREP_ROWS, r = idx - k * PREP_ROWS;
-      tile[r * ldt + k] = (row0 + r < n) ? f[(size_t)k * n + row0 + r] : 0.f;
+      tile[r * ldt + k] = (row0 + r < n) ? f[(size_t)k * op.ld + row0 + r] : 0.f;
     }
   }
   __syncthreads();
@@ -334,21 +349,24 @@ match_prep_kernel(const float* __restrict__ f, const int* __restrict__ np, int n
       acc = fmaf(v, v, acc);
       isint = isint && (v == truncf(v)) && (v >= 0.f) && (v <= 255.f);
     }
-    if (row0 + tid < n_cap) inv[row0 + tid] = (acc == 0.f || row0 + tid >= n) ? 0.f : __fdiv_rn(1.0f, __fsqrt_rn(acc));
+    if (row0 + tid < rows_alloc)
+      inv_p[row0 + tid] = (acc == 0.f || row0 + tid >= n) ? 0.f : __fdiv_rn(1.0f, __fsqrt_rn(acc));
     if (!isint) atomicOr(nonint_flag, 1);
   }
   const int ld_out = 3 * kp;
+  __nv_bfloat16* out_p = out + (size_t)prob * rows_alloc * ld_out;
+  float* raw_p = raw_copy ? raw_copy + (size_t)prob * rows_alloc * dim : nullptr;
   for (int idx = tid; idx < PREP_ROWS * kp; idx += 256) {
     const int r = idx / kp, k = idx - r * kp;
-    if (row0 + r >= n_cap) continue;
+    if (row0 + r >= rows_alloc) continue;
     const float v = (k < dim) ? tile[r * ldt + k] : 0.f;
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    __nv_bfloat16* o = out + (size_t)(row0 + r) * ld_out + k;
+    __nv_bfloat16* o = out_p + (size_t)(row0 + r) * ld_out + k;
     o[0] = hi;
     o[kp] = is_b ? lo : hi;
     o[2 * kp] = is_b ? hi : lo;
-    if (raw_rm != nullptr && k < dim && row0 + r < n) raw_rm[(size_t)(row0 + r) * dim + k] = v;
+    if (raw_p != nullptr && k < dim && row0 + r < n) raw_p[(size_t)(row0 + r) * dim + k] = v;
   }
 }
 
@@ -364,22 +382,26 @@ __device__ __forceinline__ float score_from_key(float key, float inva) {
   return s < 0.f ? 0.f : s;
 }
 
-// one thread per row: merge candidate slots, exact re-rank, certify or flag for the row scan
+struct RawRows { const float* base; size_t prob_stride; };   // compact row-major fp32 rows per problem
+
+// thread per row: merge candidate slots, exact re-rank, certify or flag for the row scan
 __global__ void __launch_bounds__(128)
-match_finalize_kernel(const uint2* __restrict__ cand, int n_slots, const float* __restrict__ a_raw,
-                      const float* __restrict__ b_raw, int dim, const float* __restrict__ inva,
-                      const float* __restrict__ invb, const int* __restrict__ n1p,
-                      const int* __restrict__ n2p, const int* __restrict__ nonint_flag,
-                      uint32_t* __restrict__ j1_out, float* __restrict__ s1_out, float* __restrict__ s2_out,
+match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, int n_slots, RawRows ra, RawRows rb,
+                      int dim, const float* __restrict__ inva_base, int inva_stride,
+                      const float* __restrict__ invb_base, int invb_stride, const int* __restrict__ n1p,
+                      int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
+                      const int* __restrict__ nonint_flag, uint32_t* __restrict__ j1_out,
+                      float* __restrict__ s1_out, float* __restrict__ s2_out, int row_stride,
                       int* __restrict__ scan_list, int* __restrict__ scan_count) {
+  const int prob = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n1 = *n1p, n2 = *n2p;
+  const int n1 = min(n1p[prob * n1_stride], cap1), n2 = min(n2p[prob * n2_stride], cap2);
   if (i >= n1) return;
-  if (n2 <= 0) { j1_out[i] = 0xFFFFFFFFu; s1_out[i] = INFINITY; s2_out[i] = INFINITY; return; }
-  // top-3 by (key desc, column asc) over all slots
+  const size_t orow = (size_t)prob * row_stride + i;
+  if (n2 <= 0) { j1_out[orow] = 0xFFFFFFFFu; s1_out[orow] = INFINITY; s2_out[orow] = INFINITY; return; }
   float k[3] = {-INFINITY, -INFINITY, -INFINITY};
   uint32_t j[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-  const uint2* c = cand + (size_t)i * n_slots * NCAND;
+  const uint2* c = cand_base + (size_t)prob * cand_stride + (size_t)i * n_slots * NCAND;
   for (int s = 0; s < n_slots * NCAND; ++s) {
     const uint2 e = c[s];
     if (e.y >= (uint32_t)n2) continue;
@@ -392,15 +414,16 @@ match_finalize_kernel(const uint2* __restrict__ cand, int n_slots, const float* 
       k[pos] = key; j[pos] = e.y;
     }
   }
-  const float ia = inva[i];
-  const float* a = a_raw + (size_t)i * dim;
+  const float ia = inva_base[(size_t)prob * inva_stride + i];
+  const float* invb = invb_base + (size_t)prob * invb_stride;
+  const float* a = ra.base + (size_t)prob * ra.prob_stride + (size_t)i * dim;
+  const float* b_rows = rb.base + (size_t)prob * rb.prob_stride;
   float s[3]; int nc = 0;
   for (int q = 0; q < 3; ++q) {
     if (j[q] == 0xFFFFFFFFu) { s[q] = INFINITY; continue; }
-    s[q] = score_from_key(exact_key(a, b_raw + (size_t)j[q] * dim, dim, invb[j[q]]), ia);
+    s[q] = score_from_key(exact_key(a, b_rows + (size_t)j[q] * dim, dim, invb[j[q]]), ia);
     ++nc;
   }
-  // order candidates by (score asc, column asc)
   uint32_t jj[3] = {j[0], j[1], j[2]};
   for (int p = 0; p < 2; ++p)
     for (int q = 0; q < 2 - p; ++q)
@@ -419,34 +442,37 @@ match_finalize_kernel(const uint2* __restrict__ cand, int n_slots, const float* 
     const float sb = score_from_key(kb, ia);
     certified = (sb > s[0]) && (sb >= s[1]);
   }
-  j1_out[i] = jj[0]; s1_out[i] = s[0]; s2_out[i] = (n2 >= 2) ? s[1] : INFINITY;
+  j1_out[orow] = jj[0]; s1_out[orow] = s[0]; s2_out[orow] = (n2 >= 2) ? s[1] : INFINITY;
   if (!certified) {
     const int slot = atomicAdd(scan_count, 1);
-    scan_list[slot] = i;
+    scan_list[slot] = prob * row_stride + i;
   }
 }
 
 // exact FP32 scan of every column for the rows in scan_list (block per row, grid-stride)
 __global__ void __launch_bounds__(256)
-match_rowscan_kernel(const int* __restrict__ scan_list, const int* __restrict__ scan_count,
-                     const float* __restrict__ a_raw, const float* __restrict__ b_raw, int dim,
-                     const float* __restrict__ inva, const float* __restrict__ invb,
-                     const int* __restrict__ n2p, uint32_t* __restrict__ j1_out,
-                     float* __restrict__ s1_out, float* __restrict__ s2_out) {
+match_rowscan_kernel(const int* __restrict__ scan_list, const int* __restrict__ scan_count, RawRows ra, RawRows rb,
+                     int dim, const float* __restrict__ inva_base, int inva_stride,
+                     const float* __restrict__ invb_base, int invb_stride, const int* __restrict__ n2p,
+                     int n2_stride, int cap2, uint32_t* __restrict__ j1_out, float* __restrict__ s1_out,
+                     float* __restrict__ s2_out, int row_stride) {
   __shared__ float sa[256];
   __shared__ float rs1[256], rs2[256];
   __shared__ uint32_t rj1[256];
-  const int n2 = *n2p;
   const int count = *scan_count;
   for (int f = blockIdx.x; f < count; f += gridDim.x) {
-    const int i = scan_list[f];
+    const int code = scan_list[f];
+    const int prob = code / row_stride, i = code - prob * row_stride;
+    const int n2 = min(n2p[prob * n2_stride], cap2);
+    const float* invb = invb_base + (size_t)prob * invb_stride;
+    const float* b_rows = rb.base + (size_t)prob * rb.prob_stride;
     __syncthreads();
-    for (int k = threadIdx.x; k < dim; k += blockDim.x) sa[k] = a_raw[(size_t)i * dim + k];
+    for (int k = threadIdx.x; k < dim; k += blockDim.x) sa[k] = ra.base[(size_t)prob * ra.prob_stride + (size_t)i * dim + k];
     __syncthreads();
-    const float ia = inva[i];
+    const float ia = inva_base[(size_t)prob * inva_stride + i];
     float b1 = INFINITY, b2 = INFINITY; uint32_t bj = 0xFFFFFFFFu;
     for (int jx = threadIdx.x; jx < n2; jx += blockDim.x) {
-      const float sc = score_from_key(exact_key(sa, b_raw + (size_t)jx * dim, dim, invb[jx]), ia);
+      const float sc = score_from_key(exact_key(sa, b_rows + (size_t)jx * dim, dim, invb[jx]), ia);
       if (sc < b1) { b2 = b1; b1 = sc; bj = (uint32_t)jx; }
       else if (sc < b2) b2 = sc;
     }
@@ -457,14 +483,16 @@ match_rowscan_kernel(const int* __restrict__ scan_list, const int* __restrict__ 
         const float o1 = rs1[threadIdx.x + off], o2 = rs2[threadIdx.x + off];
         const uint32_t oj = rj1[threadIdx.x + off];
         float m1 = rs1[threadIdx.x], m2 = rs2[threadIdx.x]; uint32_t mj = rj1[threadIdx.x];
-        // merge two (best, second) pairs; lowest column wins score ties
         if (o1 < m1 || (o1 == m1 && oj < mj)) { m2 = fminf(m1, o2); m1 = o1; mj = oj; }
         else { m2 = fminf(m2, o1); }
         rs1[threadIdx.x] = m1; rs2[threadIdx.x] = m2; rj1[threadIdx.x] = mj;
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) { j1_out[i] = rj1[0]; s1_out[i] = rs1[0]; s2_out[i] = (n2 >= 2) ? rs2[0] : INFINITY; }
+    if (threadIdx.x == 0) {
+      const size_t orow = (size_t)prob * row_stride + i;
+      j1_out[orow] = rj1[0]; s1_out[orow] = rs1[0]; s2_out[orow] = (n2 >= 2) ? rs2[0] : INFINITY;
+    }
   }
 }
 
@@ -478,6 +506,51 @@ __device__ __forceinline__ bool keep_row(float s1, float s2, int n2, float thr, 
   return true;
 }
 
+// one block per problem: ordered compaction of the surviving rows (batched path, n1 <= ~16k)
+__global__ void __launch_bounds__(1024)
+match_select_block_kernel(const uint32_t* __restrict__ j1, const float* __restrict__ s1, const float* __restrict__ s2,
+                          int row_stride, const int* __restrict__ n1p, int n1_stride, int cap1,
+                          const int* __restrict__ n2p, int n2_stride, int cap2, float thr, float max_ratio,
+                          int index_base, uint32_t* __restrict__ idx1, uint32_t* __restrict__ idx2,
+                          float* __restrict__ metric, int out_stride, int* __restrict__ n_pairs, int np_stride) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int prob = blockIdx.x;
+  const int n1 = min(n1p[prob * n1_stride], cap1), n2 = min(n2p[prob * n2_stride], cap2);
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < n1 && n2 > 0; base += 1024) {
+    const int i = base + threadIdx.x;
+    const size_t row = (size_t)prob * row_stride + i;
+    const bool keep = (i < n1) && keep_row(s1[row], s2[row], n2, thr, max_ratio);
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_sums[w] = __popc(ballot);
+    __syncthreads();
+    if (w == 0) {
+      int x = warp_sums[lane];
+      for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
+      }
+      warp_sums[lane] = x;
+    }
+    __syncthreads();
+    if (keep) {
+      const int pos = carry + (w ? warp_sums[w - 1] : 0) + __popc(ballot & ((1u << lane) - 1u));
+      const size_t o = (size_t)prob * out_stride + pos;
+      idx1[o] = (uint32_t)i + (uint32_t)index_base;
+      idx2[o] = j1[row] + (uint32_t)index_base;
+      if (metric) metric[o] = s1[row];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += warp_sums[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) n_pairs[prob * np_stride] = carry;
+}
+
+// large single problem: count / scan / scatter over 1024-row blocks
 constexpr int SEL_BLOCK = 1024;
 __global__ void __launch_bounds__(SEL_BLOCK)
 match_count_kernel(const uint32_t* __restrict__ j1, const float* __restrict__ s1, const float* __restrict__ s2,
@@ -565,14 +638,15 @@ match_scatter_kernel(const uint32_t* __restrict__ j1, const float* __restrict__ 
 }
 
 // --------------------------------------------------------------------------- host plumbing
-static int make_operand_map(CUtensorMap* map, const __nv_bfloat16* base, int rows_cap, int kp, int box_rows) {
+static int make_operand_map(CUtensorMap* map, const __nv_bfloat16* base, int rows_alloc, int kp, int n_prob, int box_rows) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) { set_error("cuTensorMapEncodeTiled driver entry point not available"); return VO_ERR_CUDA; }
-  cuuint64_t gdim[2] = {(cuuint64_t)(3 * kp), (cuuint64_t)rows_cap};
-  cuuint64_t gstride[1] = {(cuuint64_t)(3 * kp) * sizeof(__nv_bfloat16)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim, gstride, box, estr,
+  cuuint64_t gdim[3] = {(cuuint64_t)(3 * kp), (cuuint64_t)rows_alloc, (cuuint64_t)n_prob};
+  cuuint64_t gstride[2] = {(cuuint64_t)(3 * kp) * sizeof(__nv_bfloat16),
+                           (cuuint64_t)rows_alloc * (3 * kp) * sizeof(__nv_bfloat16)};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return VO_ERR_CUDA; }
@@ -581,88 +655,83 @@ static int make_operand_map(CUtensorMap* map, const __nv_bfloat16* base, int row
 
 static bool g_attr_set = false;
 
-struct Top2Args {
-  const float* f1; int n1; const float* f2; int n2; int dim;
-  int col_major;      // layout of f1/f2 (device memory)
-  bool tag_b;         // scratch-name suffix so the Unique backward pass does not clobber
-  float* dbg_c;       // optional n1 x n2 raw dot products (device)
-};
-
-// Runs prep + GEMM top-3 + finalize + row scan for device-resident inputs; results stay on device.
-static int run_top2(vo_ctx* ctx, const Top2Args& a, cudaStream_t st, uint32_t** j1, float** s1, float** s2,
-                    const int** n1_dev, const int** n2_dev) {
-  const char* sfx = a.tag_b ? "_b" : "_f";
-  auto nm = [&](const char* base) { return std::string(base) + sfx; };
-  const int n1 = a.n1, n2 = a.n2, dim = a.dim;
+int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, int n_prob, int dim,
+                     const char* tag, float* dbg_c, cudaStream_t st, MatchTop2* out) {
+  auto nm = [&](const char* base) { return std::string(base) + "_" + tag; };
   const int kp = div_up(dim, BK) * BK;
   if (3 * kp > MAX_KBLOCKS * BK) { set_error("vo_match: dim %d > 128 is not supported by the tensor-core path", dim); return VO_ERR_ARG; }
-  const int n1_pad = div_up(n1 > 0 ? n1 : 1, BM) * BM, n2_pad = div_up(n2 > 0 ? n2 : 1, BN) * BN;
+  const int a_alloc = div_up(A.cap > 0 ? A.cap : 1, BM) * BM;
+  const int b_tiles = div_up(B.cap > 0 ? B.cap : 1, BN);
+  const int b_alloc = b_tiles * BN;   // multiple of 256, so the epilogue's 32-wide invb loads stay in bounds
 
-  // counts[0]=n1 counts[1]=n2 counts[2]=nonint flag counts[3]=rowscan count
-  int* counts; VO_TRY(dev_buf(ctx, nm("m_counts").c_str(), 8, &counts));
-  match_set_counts_kernel<<<1, 32, 0, st>>>(counts, n1, n2);
-
+  int* ctl; VO_TRY(dev_buf(ctx, nm("m_ctl").c_str(), 8, &ctl));
+  VO_CUDA(cudaMemsetAsync(ctl, 0, 8 * sizeof(int), st));
   __nv_bfloat16 *opA, *opB; float *invA, *invB, *rawA = nullptr, *rawB = nullptr;
-  VO_TRY(dev_buf(ctx, nm("m_opA").c_str(), (size_t)n1_pad * 3 * kp, &opA));
-  VO_TRY(dev_buf(ctx, nm("m_opB").c_str(), (size_t)n2_pad * 3 * kp, &opB));
-  VO_TRY(dev_buf(ctx, nm("m_invA").c_str(), (size_t)n1_pad, &invA));
-  VO_TRY(dev_buf(ctx, nm("m_invB").c_str(), (size_t)n2_pad + BN, &invB));
-  const float *a_raw = a.f1, *b_raw = a.f2;
-  if (a.col_major) {
-    VO_TRY(dev_buf(ctx, nm("m_rawA").c_str(), (size_t)n1_pad * dim, &rawA));
-    VO_TRY(dev_buf(ctx, nm("m_rawB").c_str(), (size_t)n2_pad * dim, &rawB));
-    a_raw = rawA; b_raw = rawB;
+  VO_TRY(dev_buf(ctx, nm("m_opA").c_str(), (size_t)n_prob * a_alloc * 3 * kp, &opA));
+  VO_TRY(dev_buf(ctx, nm("m_opB").c_str(), (size_t)n_prob * b_alloc * 3 * kp, &opB));
+  VO_TRY(dev_buf(ctx, nm("m_invA").c_str(), (size_t)n_prob * a_alloc, &invA));
+  VO_TRY(dev_buf(ctx, nm("m_invB").c_str(), (size_t)n_prob * b_alloc, &invB));
+  RawRows ra{A.base, A.prob_stride}, rb{B.base, B.prob_stride};
+  if (A.gather || A.col_major) {
+    VO_TRY(dev_buf(ctx, nm("m_rawA").c_str(), (size_t)n_prob * a_alloc * dim, &rawA));
+    ra = RawRows{rawA, (size_t)a_alloc * dim};
   }
-  VO_TRY(dev_buf(ctx, nm("m_j1").c_str(), (size_t)n1_pad, j1));
-  VO_TRY(dev_buf(ctx, nm("m_s1").c_str(), (size_t)n1_pad, s1));
-  VO_TRY(dev_buf(ctx, nm("m_s2").c_str(), (size_t)n1_pad, s2));
-  *n1_dev = counts; *n2_dev = counts + 1;
+  if (B.gather || B.col_major) {
+    VO_TRY(dev_buf(ctx, nm("m_rawB").c_str(), (size_t)n_prob * b_alloc * dim, &rawB));
+    rb = RawRows{rawB, (size_t)b_alloc * dim};
+  }
+  VO_TRY(dev_buf(ctx, nm("m_j1").c_str(), (size_t)n_prob * a_alloc, &out->j1));
+  VO_TRY(dev_buf(ctx, nm("m_s1").c_str(), (size_t)n_prob * a_alloc, &out->s1));
+  VO_TRY(dev_buf(ctx, nm("m_s2").c_str(), (size_t)n_prob * a_alloc, &out->s2));
+  out->row_stride = a_alloc; out->ctl = ctl;
   ctx->match_stats[2] = 0; ctx->match_stats[3] = kp;
-  if (n1 == 0) return VO_OK;
+  if (A.cap <= 0 || n_prob <= 0) return VO_OK;
 
   const size_t prep_smem = (size_t)PREP_ROWS * (dim + 1) * sizeof(float);
-  match_prep_kernel<<<n1_pad / PREP_ROWS, 256, prep_smem, st>>>(a.f1, counts, n1_pad, dim, kp, a.col_major, 0, opA, rawA, invA, counts + 2);
-  match_prep_kernel<<<(n2_pad + BN) / PREP_ROWS, 256, prep_smem, st>>>(a.f2, counts + 1, n2_pad + BN, dim, kp, a.col_major, 1, opB, rawB, invB, counts + 2);
+  match_prep_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, kp, 0, opA, rawA, invA, ctl);
+  match_prep_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, kp, 1, opB, rawB, invB, ctl);
   VO_CUDA(cudaGetLastError());
 
-  // column splits so that (row panels x splits) fills the SMs
-  const int m_blocks = n1_pad / BM, tiles = n2_pad / BN;
+  const int m_blocks = a_alloc / BM;
   int n_splits = 1;
-  if (m_blocks < ctx->num_sms) {
-    n_splits = ctx->num_sms / m_blocks;
-    if (n_splits > tiles) n_splits = tiles;
+  if (m_blocks * n_prob < ctx->num_sms) {
+    n_splits = ctx->num_sms / (m_blocks * n_prob);
+    if (n_splits > b_tiles) n_splits = b_tiles;
     if (n_splits < 1) n_splits = 1;
   }
   const int n_slots = n_splits * 2;
-  uint2* cand; VO_TRY(dev_buf(ctx, nm("m_cand").c_str(), (size_t)n1_pad * n_slots * NCAND, &cand));
-  int* scan_list; VO_TRY(dev_buf(ctx, nm("m_scanlist").c_str(), (size_t)n1_pad, &scan_list));
+  const size_t cand_stride = (size_t)a_alloc * n_slots * NCAND;
+  uint2* cand; VO_TRY(dev_buf(ctx, nm("m_cand").c_str(), (size_t)n_prob * cand_stride, &cand));
+  int* scan_list; VO_TRY(dev_buf(ctx, nm("m_scanlist").c_str(), (size_t)n_prob * a_alloc, &scan_list));
 
-  if (n2 > 0) {
+  if (B.cap > 0) {
     CUtensorMap tmA, tmB;
-    VO_TRY(make_operand_map(&tmA, opA, n1_pad, kp, BM));
-    VO_TRY(make_operand_map(&tmB, opB, n2_pad, kp, BN));
+    VO_TRY(make_operand_map(&tmA, opA, a_alloc, kp, n_prob, BM));
+    VO_TRY(make_operand_map(&tmB, opB, b_alloc, kp, n_prob, BN));
     if (!g_attr_set) {
       VO_CUDA(cudaFuncSetAttribute(match_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       g_attr_set = true;
     }
-    dim3 grid(m_blocks, n_splits);
-    match_topk_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, invB, counts, counts + 1, counts + 2, kp / BK, n_splits,
-                                                             cand, a.dbg_c, n2);
+    dim3 grid(m_blocks, n_splits, n_prob);
+    match_topk_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, invB, b_alloc, A.count, A.count_stride, A.cap, B.count,
+                                                             B.count_stride, B.cap, ctl, kp / BK, n_splits, cand, cand_stride,
+                                                             dbg_c, B.cap);
     VO_CUDA(cudaGetLastError());
     ctx->match_stats[2] = 1;
   }
-  match_finalize_kernel<<<div_up(n1, 128), 128, 0, st>>>(cand, n_slots, a_raw, b_raw, dim, invA, invB, counts, counts + 1,
-                                                         counts + 2, *j1, *s1, *s2, scan_list, counts + 3);
-  if (n2 > 0) {
+  match_finalize_kernel<<<dim3(div_up(A.cap, 128), n_prob), 128, 0, st>>>(
+      cand, cand_stride, n_slots, ra, rb, dim, invA, a_alloc, invB, b_alloc, A.count, A.count_stride, A.cap, B.count,
+      B.count_stride, B.cap, ctl, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
+  if (B.cap > 0) {
     int scan_grid = ctx->num_sms * 2;
-    if (scan_grid > n1) scan_grid = n1;
-    match_rowscan_kernel<<<scan_grid, 256, 0, st>>>(scan_list, counts + 3, a_raw, b_raw, dim, invA, invB, counts + 1, *j1, *s1, *s2);
+    match_rowscan_kernel<<<scan_grid, 256, 0, st>>>(scan_list, ctl + 1, ra, rb, dim, invA, a_alloc, invB, b_alloc, B.count,
+                                                    B.count_stride, B.cap, out->j1, out->s1, out->s2, a_alloc);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
 }
 
-static void fill_opts(const vo_match_opts* in, vo_match_opts* o) {
+void fill_match_opts(const vo_match_opts* in, vo_match_opts* o) {
   o->match_threshold = 1.0f; o->max_ratio = 0.6f; o->unique = 0; o->index_base = 0;
   if (in) {
     if (in->match_threshold > 0) o->match_threshold = in->match_threshold;
@@ -672,31 +741,64 @@ static void fill_opts(const vo_match_opts* in, vo_match_opts* o) {
   }
 }
 
-// device-resident match: inputs on device (row- or col-major), outputs on device
+int match_batch_select(vo_ctx* ctx, const MatchTop2& t, const MatchOperand& A, const MatchOperand& B, int n_prob,
+                       const vo_match_opts& o, uint32_t* idx1, uint32_t* idx2, float* metric, int out_stride,
+                       int* n_pairs, int np_stride, cudaStream_t st) {
+  (void)ctx;
+  if (n_prob <= 0) return VO_OK;
+  const float thr = o.match_threshold * 0.04f;
+  match_select_block_kernel<<<n_prob, 1024, 0, st>>>(t.j1, t.s1, t.s2, t.row_stride, A.count, A.count_stride, A.cap, B.count,
+                                                     B.count_stride, B.cap, thr, o.max_ratio, o.index_base, idx1, idx2, metric,
+                                                     out_stride, n_pairs, np_stride);
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+// ------------------------------------------------------------- single-problem entry points
+struct Single {
+  MatchOperand A, B;
+  int* counts;   // device {n1, n2}
+};
+
+static int single_operands(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2, int col_major, const char* tag,
+                           cudaStream_t st, Single* s) {
+  VO_TRY(dev_buf(ctx, (std::string("m_counts_") + tag).c_str(), 8, &s->counts));
+  match_set_counts_kernel<<<1, 32, 0, st>>>(s->counts, n1, n2);
+  s->A = MatchOperand(); s->B = MatchOperand();
+  s->A.base = f1; s->A.count = s->counts; s->A.cap = n1; s->A.col_major = col_major; s->A.ld = n1;
+  s->B.base = f2; s->B.count = s->counts + 1; s->B.cap = n2; s->B.col_major = col_major; s->B.ld = n2;
+  return VO_OK;
+}
+
+// device-resident single match (inputs on device, row- or col-major; outputs on device)
 static int match_device(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2, int dim, int col_major,
                         const vo_match_opts* opts, uint32_t* idx1, uint32_t* idx2, float* metric, int* n_pairs_dev,
                         cudaStream_t st) {
-  vo_match_opts o; fill_opts(opts, &o);
-  uint32_t *j1, *bj1 = nullptr; float *s1, *s2; const int *n1d, *n2d;
-  Top2Args fa{f1, n1, f2, n2, dim, col_major, false, nullptr};
-  VO_TRY(run_top2(ctx, fa, st, &j1, &s1, &s2, &n1d, &n2d));
-  const int fwd_launches = ctx->match_stats[2];
-  if (o.unique && n1 > 0 && n2 > 0) {
-    float *bs1, *bs2; const int *bn1, *bn2;
-    Top2Args ba{f2, n2, f1, n1, dim, col_major, true, nullptr};
-    VO_TRY(run_top2(ctx, ba, st, &bj1, &bs1, &bs2, &bn1, &bn2));
-    ctx->match_stats[2] += fwd_launches;
-  }
+  vo_match_opts o; fill_match_opts(opts, &o);
   if (n1 == 0 || n2 == 0) {
     VO_CUDA(cudaMemsetAsync(n_pairs_dev, 0, sizeof(int), st));
     return VO_OK;
   }
+  Single s; VO_TRY(single_operands(ctx, f1, n1, f2, n2, col_major, "f", st, &s));
+  MatchTop2 t;
+  VO_TRY(match_batch_top2(ctx, s.A, s.B, 1, dim, "f", nullptr, st, &t));
+  const uint32_t* bj1 = nullptr;
+  if (o.unique) {
+    Single sb; VO_TRY(single_operands(ctx, f2, n2, f1, n1, col_major, "b", st, &sb));
+    MatchTop2 tb;
+    VO_TRY(match_batch_top2(ctx, sb.A, sb.B, 1, dim, "b", nullptr, st, &tb));
+    bj1 = tb.j1;
+    ctx->match_stats[2] = 2;
+  }
+  if (!o.unique && n1 <= 16384)
+    return match_batch_select(ctx, t, s.A, s.B, 1, o, idx1, idx2, metric, n1, n_pairs_dev, 1, st);
   const int nb = div_up(n1, SEL_BLOCK);
   int* blk; VO_TRY(dev_buf(ctx, "m_blk", (size_t)nb + 1, &blk));
   const float thr = o.match_threshold * 0.04f;
-  match_count_kernel<<<nb, SEL_BLOCK, 0, st>>>(j1, s1, s2, bj1, n1d, n2d, thr, o.max_ratio, blk);
+  match_count_kernel<<<nb, SEL_BLOCK, 0, st>>>(t.j1, t.s1, t.s2, bj1, s.counts, s.counts + 1, thr, o.max_ratio, blk);
   match_scan_kernel<<<1, 1024, 0, st>>>(blk, nb, n_pairs_dev);
-  match_scatter_kernel<<<nb, SEL_BLOCK, 0, st>>>(j1, s1, s2, bj1, n1d, n2d, thr, o.max_ratio, o.index_base, blk, idx1, idx2, metric);
+  match_scatter_kernel<<<nb, SEL_BLOCK, 0, st>>>(t.j1, t.s1, t.s2, bj1, s.counts, s.counts + 1, thr, o.max_ratio, o.index_base, blk,
+                                                 idx1, idx2, metric);
   VO_CUDA(cudaGetLastError());
   return VO_OK;
 }
@@ -704,6 +806,17 @@ static int match_device(vo_ctx* ctx, const float* f1, int n1, const float* f2, i
 static int upload_features(vo_ctx* ctx, const char* name, const float* f, int n, int dim, float** out, cudaStream_t st) {
   VO_TRY(dev_buf(ctx, name, (size_t)(n > 0 ? n : 1) * dim, out));
   if (n > 0) VO_CUDA(cudaMemcpyAsync(*out, f, (size_t)n * dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  return VO_OK;
+}
+
+static int read_stats(vo_ctx* ctx, cudaStream_t st) {
+  int* ctl; VO_TRY(dev_buf(ctx, "m_ctl_f", 8, &ctl));
+  int* h; VO_TRY(pin_buf(ctx, "m_ctl", 8, &h));
+  VO_CUDA(cudaMemcpyAsync(h, ctl, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaStreamSynchronize(st));
+  ctx->match_stats[0] = h[0] ? 0 : 1;
+  ctx->match_stats[1] = h[1];
+  if (h[0]) ctx->match_stats[3] *= 3;
   return VO_OK;
 }
 
@@ -733,14 +846,9 @@ int vo_match(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2, int 
   VO_TRY(dev_buf(ctx, "m_np", 4, &np));
   VO_TRY(match_device(ctx, d1, n1, d2, n2, dim, col_major, opts, o1, o2, om, np, st));
   int* hres; VO_TRY(pin_buf(ctx, "m_res", 8, &hres));
-  int* counts; VO_TRY(dev_buf(ctx, "m_counts_f", 8, &counts));
   VO_CUDA(cudaMemcpyAsync(hres, np, sizeof(int), cudaMemcpyDeviceToHost, st));
-  VO_CUDA(cudaMemcpyAsync(hres + 1, counts + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  VO_CUDA(cudaStreamSynchronize(st));
+  VO_TRY(read_stats(ctx, st));
   const int p = hres[0];
-  ctx->match_stats[0] = hres[1] ? 0 : 1;
-  ctx->match_stats[1] = hres[2];
-  ctx->match_stats[3] = hres[1] ? 3 * ctx->match_stats[3] : ctx->match_stats[3];
   if (p > 0) {
     VO_CUDA(cudaMemcpyAsync(idx1, o1, (size_t)p * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     VO_CUDA(cudaMemcpyAsync(idx2, o2, (size_t)p * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -767,14 +875,13 @@ int vo_match_top2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_
   VO_CHECK_ARG(n1 >= 0 && n2 >= 0 && dim > 0, "negative size");
   VO_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
-  uint32_t* j1; float *s1, *s2; const int *n1d, *n2d;
-  Top2Args fa{f1_dev, n1, f2_dev, n2, dim, 0, false, nullptr};
-  VO_TRY(run_top2(ctx, fa, st, &j1, &s1, &s2, &n1d, &n2d));
-  if (n1 > 0) {
-    VO_CUDA(cudaMemcpyAsync(j1_dev, j1, (size_t)n1 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-    VO_CUDA(cudaMemcpyAsync(s1_dev, s1, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    VO_CUDA(cudaMemcpyAsync(s2_dev, s2, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  }
+  if (n1 == 0) return VO_OK;
+  Single s; VO_TRY(single_operands(ctx, f1_dev, n1, f2_dev, n2, 0, "f", st, &s));
+  MatchTop2 t;
+  VO_TRY(match_batch_top2(ctx, s.A, s.B, 1, dim, "f", nullptr, st, &t));
+  VO_CUDA(cudaMemcpyAsync(j1_dev, t.j1, (size_t)n1 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  VO_CUDA(cudaMemcpyAsync(s1_dev, t.s1, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  VO_CUDA(cudaMemcpyAsync(s2_dev, t.s2, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return VO_OK;
 }
 
@@ -789,18 +896,13 @@ int vo_match_top2(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2,
   float *d1, *d2;
   VO_TRY(upload_features(ctx, "m_in1", f1, n1, dim, &d1, st));
   VO_TRY(upload_features(ctx, "m_in2", f2, n2, dim, &d2, st));
-  uint32_t* j1; float *s1, *s2; const int *n1d, *n2d;
-  Top2Args fa{d1, n1, d2, n2, dim, col_major, false, nullptr};
-  VO_TRY(run_top2(ctx, fa, st, &j1, &s1, &s2, &n1d, &n2d));
-  int* hres; VO_TRY(pin_buf(ctx, "m_res", 8, &hres));
-  VO_CUDA(cudaMemcpyAsync(hres + 1, n1d + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  VO_CUDA(cudaMemcpyAsync(j1_out, j1, (size_t)n1 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  VO_CUDA(cudaMemcpyAsync(s1_out, s1, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  VO_CUDA(cudaMemcpyAsync(s2_out, s2, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  VO_CUDA(cudaStreamSynchronize(st));
-  ctx->match_stats[0] = hres[1] ? 0 : 1;
-  ctx->match_stats[1] = hres[2];
-  ctx->match_stats[3] = hres[1] ? 3 * ctx->match_stats[3] : ctx->match_stats[3];
+  Single s; VO_TRY(single_operands(ctx, d1, n1, d2, n2, col_major, "f", st, &s));
+  MatchTop2 t;
+  VO_TRY(match_batch_top2(ctx, s.A, s.B, 1, dim, "f", nullptr, st, &t));
+  VO_CUDA(cudaMemcpyAsync(j1_out, t.j1, (size_t)n1 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaMemcpyAsync(s1_out, t.s1, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaMemcpyAsync(s2_out, t.s2, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  VO_TRY(read_stats(ctx, st));
   return VO_OK;
 }
 
@@ -820,9 +922,9 @@ int vo_match_debug_gemm(vo_ctx* ctx, const float* f1, int n1, const float* f2, i
   VO_TRY(upload_features(ctx, "m_in2", f2, n2, dim, &d2, st));
   VO_TRY(dev_buf(ctx, "m_dbgc", (size_t)n1 * n2, &dc));
   VO_CUDA(cudaMemsetAsync(dc, 0xFF, (size_t)n1 * n2 * sizeof(float), st));
-  uint32_t* j1; float *s1, *s2; const int *n1d, *n2d;
-  Top2Args fa{d1, n1, d2, n2, dim, 0, false, dc};
-  VO_TRY(run_top2(ctx, fa, st, &j1, &s1, &s2, &n1d, &n2d));
+  Single s; VO_TRY(single_operands(ctx, d1, n1, d2, n2, 0, "f", st, &s));
+  MatchTop2 t;
+  VO_TRY(match_batch_top2(ctx, s.A, s.B, 1, dim, "f", dc, st, &t));
   VO_CUDA(cudaMemcpyAsync(c_out, dc, (size_t)n1 * n2 * sizeof(float), cudaMemcpyDeviceToHost, st));
   VO_CUDA(cudaStreamSynchronize(st));
   return VO_OK;

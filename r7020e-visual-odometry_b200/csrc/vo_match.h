@@ -1,0 +1,39 @@
+// vo_match.h -- internal interface of the batched, device-count-driven match core (vo_match.cu),
+// shared with the on-device frame loop (vo_frames.cu).
+#pragma once
+#include "vo_internal.h"
+
+namespace vo {
+
+// One side of a batch of match problems.  Problem p uses feature rows
+//   row(i) = base + p*prob_stride + (gather ? gather[p*gather_stride + i] : i) * dim
+// for i < min(count[p*count_stride], cap).
+struct MatchOperand {
+  const float* base = nullptr;
+  size_t prob_stride = 0;
+  const uint32_t* gather = nullptr;
+  size_t gather_stride = 0;
+  const int* count = nullptr;
+  int count_stride = 0;
+  int cap = 0;
+  int col_major = 0;   // single problem only: element (i,k) at base[k*ld + i]
+  int ld = 0;
+};
+
+struct MatchTop2 {       // device results, [n_prob][cap_a_pad]
+  uint32_t* j1; float* s1; float* s2; int row_stride;
+  int* ctl;              // ctl[0] = non-integer flag, ctl[1] = rows sent to the exact scan
+};
+
+// prep + tcgen05 GEMM top-3 + finalize + exact row scan.  No host synchronisation.
+int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, int n_prob, int dim,
+                     const char* tag, float* dbg_c, cudaStream_t st, MatchTop2* out);
+
+// threshold / ratio tests + ordered compaction, one block per problem.
+// idx1/idx2/metric: [n_prob][out_stride]; n_pairs[p*np_stride].
+int match_batch_select(vo_ctx* ctx, const MatchTop2& t, const MatchOperand& A, const MatchOperand& B, int n_prob,
+                       const vo_match_opts& o, uint32_t* idx1, uint32_t* idx2, float* metric, int out_stride,
+                       int* n_pairs, int np_stride, cudaStream_t st);
+
+void fill_match_opts(const vo_match_opts* in, vo_match_opts* o);
+}  // namespace vo

@@ -52,16 +52,17 @@ def texture(h, w, seed=0, n_rect=150):
 def shift_stream(n_frames, seed=20260, h=KITTI_H, w=KITTI_W, disparity=12, shift=3):
     """Returns (left, right) uint8 arrays of shape (n_frames, h, w).
 
-    left_i(x) = T(x + i*shift + disparity), right_i(x) = T(x + i*shift): a plane at depth
-    Z = fx*b/disparity (32.2 m for KITTI calibration) and a rig moving +x by shift*Z/fx per frame.
+    left_i(x) = T(x + i*shift), right_i(x) = T(x + i*shift + disparity), i.e. x_left - x_right =
+    +disparity: a plane at depth Z = fx*b/disparity (32.2 m for KITTI calibration) seen by a rig
+    moving +x by shift*Z/fx per frame.
     """
     big = texture(h, w + disparity + shift * n_frames + 8, seed)
     left = np.empty((n_frames, h, w), dtype=np.uint8)
     right = np.empty((n_frames, h, w), dtype=np.uint8)
     for i in range(n_frames):
         o = i * shift
-        right[i] = big[:, o:o + w]
-        left[i] = big[:, o + disparity:o + disparity + w]
+        left[i] = big[:, o:o + w]
+        right[i] = big[:, o + disparity:o + disparity + w]
     return left, right
 
 
