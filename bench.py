@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- KITTI-shaped stereo frames/s of the VO hot path on B200, with roofline evidence.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): the per-frame body of VO.m (SIFT x2 -> stereo match ->
+find_remaining_points (4 matches) -> triangulate -> P3P-MSAC) over 1241x376 stereo frames.  KITTI
+images are not shipped with the reference and there is no network, so the frames are the seeded
+synthetic stream of synth.shift_stream (data: "synthetic").  A *step* = one vo_frames call over
+B+1 consecutive frames (one halo frame + B new frames -> B relative poses).
+
+One JSON line on stdout (rank 0):
+  value    frames/s with the images already resident in HBM (vo_frames_dev), CUDA-event timed
+  e2e      frames/s through the C ABI with HOST (pinned) images: H2D of every frame and D2H of
+           the poses inside the timed region (vo_frames)
+  roofline the dominant kernel stage of the step (live CUDA-event timers inside the library)
+  match_gemm  the tcgen05 match GEMM alone at 32768 x 32768 x 128 (second headline of BASELINE.json)
+  cpu_baseline  the single-threaded C oracle on a bounded sample of the same frames (rank 0, N=1)
+
+--impl reference times the reference's CPU implementation of the path.  MATLAB is not available
+offline, so this is the oracle port run with one process per host core.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+H, W = 376, 1241
+METRIC = "kitti_stereo_frames_per_s_end_to_end"
+UNIT = "frames/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nme in enumerate(names):
+                    if r[2 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def make_frames(n_batches, batch, seed):
+    """n_batches x (batch+1) consecutive synthetic stereo frames, as one pinned uint8 tensor pair."""
+    import torch
+    from vo_b200 import synth
+    n = batch + 1
+    left = torch.empty((n_batches, n, H, W), dtype=torch.uint8).pin_memory()
+    right = torch.empty((n_batches, n, H, W), dtype=torch.uint8).pin_memory()
+    for b in range(n_batches):
+        l, r = synth.shift_stream(n, seed=seed + 1000 * b, h=H, w=W)
+        left[b] = torch.from_numpy(l); right[b] = torch.from_numpy(r)
+    return left, right
+
+
+# ------------------------------------------------------------------------------------ CPU legs
+def _oracle_frame(args):
+    """SIFT x2 + stereo match of one frame with the oracle (worker process)."""
+    from oracle_ops import OracleOps
+    l, r = args
+    ops = OracleOps()
+    ld, lp = ops.detect_and_extract(l)
+    rd, rp = ops.detect_and_extract(r)
+    m = ops.matchFeatures(ld, rd)
+    return ld, lp, rd, rp, m
+
+
+def _oracle_pair(args):
+    """find_remaining_points + triangulate + P3P for one frame pair with the oracle."""
+    from oracle_ops import OracleOps
+    from vo_b200 import vo, synth
+    prev, cur, idx = args
+    ops = OracleOps(seed=1)
+    ld, lp, rd, rp, m = prev
+    old = dict(l_desc=ld[m[:, 0]], r_desc=rd[m[:, 1]], l_pos=lp[m[:, 0]], r_pos=rp[m[:, 1]])
+    c = dict(l_desc=cur[0], l_pos=cur[1], r_desc=cur[2], r_pos=cur[3])
+    c, o, _, _, _ = vo.find_remaining_points(ops, old, c)
+    xyz = ops.triangulate(o["l_pos"], o["r_pos"], synth.KITTI_P0, synth.KITTI_P1)
+    r = ops.estworldpose(c["l_pos"].astype(np.float64), xyz, synth.KITTI_K4, idx)
+    return r["status"]
+
+
+def cpu_oracle_sample(n_frames=3, seed=77):
+    """Single-threaded oracle on n_frames consecutive frames (n_frames SIFT pairs + n_frames-1 poses)."""
+    from vo_b200 import synth
+    left, right = synth.shift_stream(n_frames, seed=seed, h=H, w=W)
+    t0 = time.perf_counter()
+    fr = [_oracle_frame((left[i], right[i])) for i in range(n_frames)]
+    for i in range(1, n_frames):
+        _oracle_pair((fr[i - 1], fr[i], i))
+    dt = time.perf_counter() - t0
+    return dict(value=n_frames / dt, unit=UNIT, cores=1, kind="port",
+                sample=f"{n_frames} consecutive 1241x376 stereo frames ({2 * n_frames} SIFT, {n_frames} stereo "
+                       f"matches, {n_frames - 1} tracked pairs + P3P) in {dt:.1f} s, single thread, C oracle "
+                       "(MATLAB + Computer Vision Toolbox not installed: BASELINE.md)")
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the oracle port on all host cores (one process per core), rank 0 only."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from vo_b200 import synth
+    cores = os.cpu_count() or 1
+    n = cores                      # frames per step: one per core (+1 halo frame)
+    left, right = synth.shift_stream(n + 1, seed=99, h=H, w=W)
+    ctxm = mp.get_context("fork")
+    with ctxm.Pool(cores) as pool:
+        def step():
+            fr = pool.map(_oracle_frame, [(left[i], right[i]) for i in range(n + 1)])
+            pool.map(_oracle_pair, [(fr[i - 1], fr[i], i) for i in range(1, n + 1)])
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+    v = args.steps * n / dt
+    line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="VO.m loop body on synthetic 1241x376 stereo frames (BASELINE.json configs[1])",
+                            frames_per_step=n, note="reference = CPU oracle port; MATLAB not installed (BASELINE.md)"),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
+                                  sample=f"{n} frames (+1 halo) per step, one process per core"),
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU legs
+def match_gemm_leg(ctx, torch, pk, n=32768):
+    """tcgen05 match GEMM alone: top-2 of n x n x 128 SIFT-like descriptors resident in HBM."""
+    import ctypes as C
+    from vo_b200 import _lib
+    from conftest import sift_like_descriptors
+    f1 = torch.from_numpy(sift_like_descriptors(n, 1234)).cuda()
+    f2 = torch.from_numpy(sift_like_descriptors(n, 5678)).cuda()
+    j1 = torch.empty(n, dtype=torch.int32, device="cuda"); s1 = torch.empty(n, device="cuda"); s2 = torch.empty(n, device="cuda")
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    L = _lib.lib()
+
+    def call():
+        _lib.check(L.vo_match_top2_dev(ctx.handle, C.c_void_p(f1.data_ptr()), n, C.c_void_p(f2.data_ptr()), n, 128,
+                                       C.c_void_p(j1.data_ptr()), C.c_void_p(s1.data_ptr()), C.c_void_p(s2.data_ptr()),
+                                       C.c_void_p(ctx.stream)))
+    torch.cuda.synchronize()
+    for _ in range(3):
+        call()
+    ctx.sync()
+    ctx.profile_enable(True)
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        call()
+    e1.record(stream)
+    ctx.sync()
+    prof = ctx.profile()
+    ctx.profile_enable(False)
+    g = prof["match_gemm_topk"]
+    flops = 2.0 * n * n * 128
+    t_kernel = g["ms"] / g["launches"] * 1e-3
+    tf = flops / t_kernel / 1e12
+    return dict(n1=n, n2=n, dim=128, kernel_ms=1e3 * t_kernel, call_ms=e0.elapsed_time(e1) / reps, tflops=tf,
+                frac_of_burst_peak=tf / pk["tf_burst"], frac_of_sustained_peak=tf / pk["tf_sust"],
+                peak_tflops_burst=pk["tf_burst"], peak_source=pk["src"])
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import vo_b200
+    from vo_b200 import synth, vo
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libvo_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = vo_b200.Context(local_rank)
+    pk = peaks()
+    B = args.batch
+    n_batches = min(args.steps + args.warmup, 4)
+    left, right = make_frames(n_batches, B, seed=20260 + 7919 * rank)
+    dleft, dright = left.cuda(), right.cuda()
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    P0, P1 = synth.KITTI_P0, synth.KITTI_P1
+
+    def step_dev(i):
+        b = i % n_batches
+        return vo.run_frames(None, None, P0, P1, seed=1, first_frame=i * B, ctx=ctx,
+                             device_ptrs=(dleft[b].data_ptr(), dright[b].data_ptr(), B + 1, H, W))
+
+    def step_host(i):
+        b = i % n_batches
+        return vo.run_frames(left[b].numpy(), right[b].numpy(), P0, P1, seed=1, first_frame=i * B, ctx=ctx)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, profile):
+        for i in range(args.warmup):
+            step_fn(i)
+        barrier()
+        if profile:
+            ctx.profile_enable(True)
+        launches0 = ctx.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        counts = []
+        for i in range(args.steps):
+            rel, status, cnt = step_fn(args.warmup + i)
+            counts.append(cnt)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof = ctx.profile() if profile else None
+        if profile:
+            ctx.profile_enable(False)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, prof, ctx.kernel_launches() - launches0, counts, (rel, status)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev, prof, launches, counts, last = timed(step_dev, profile=True)
+    clocks = sampler.stop()
+    ms_host, _, _, _, _ = timed(step_host, profile=False)
+    frames = args.steps * B * world
+    value = frames / (ms_dev * 1e-3)
+    e2e = frames / (ms_host * 1e-3)
+    if rank != 0:
+        return
+    # dominant kernel stage of the step and its roofline
+    total_ms = sum(v["ms"] for v in prof.values())
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    cnt = np.concatenate(counts, axis=0).astype(np.float64)
+    shares = {k: round(v["ms"] / total_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    if d["bytes"] > 0:
+        ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        roof = dict(kernel=dom, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
+                    traffic=None, launches=d["launches"], avg_launch_ms=d["ms"] / d["launches"],
+                    algorithmic_bytes_per_launch=d["bytes"] / d["launches"], peak_source=pk["src"],
+                    share_of_step=shares[dom])
+    else:
+        roof = dict(kernel=dom, bound="latency", achieved=None, peak=None, unit=None, frac=None, traffic=None,
+                    launches=d["launches"], avg_launch_ms=d["ms"] / d["launches"], share_of_step=shares[dom])
+    # algorithmic flops of the five matches of the step from the observed sizes (2*N1*N2*128)
+    mm = (cnt[:, 0] * cnt[:, 1]).sum()
+    gemm_ms = prof.get("match_gemm_topk", dict(ms=0))["ms"]
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32 (SIFT) / bf16->f32 exact-integer tensor-core GEMM (match) / f64 (triangulate, P3P)",
+                data="synthetic",
+                config=dict(workload="VO.m loop body on synthetic 1241x376 stereo frames (BASELINE.json configs[1]: "
+                                     "kitti/00-shaped stream; KITTI images absent offline)",
+                            frames_per_step_per_gpu=B, halo_frames=1, rows=H, cols=W,
+                            l2="per-step working set ~%.1f GB of pyramids >> 126 MB L2; %d distinct input batches"
+                               % ((B + 1) * 2 * 110e6 / 1e9, n_batches),
+                            parallelism=f"frame-sharded x{world}, no data-path collective"),
+                e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=int((B + 1) * 2 * H * W),
+                         d2h_bytes_per_step=int((B + 1) * (16 * 8 + 4 + 4 * 4 + 5 * 4 + 2 * 16)), ms_per_step=ms_host / args.steps),
+                gpu_launches=int(launches), clocks=clocks, roofline=roof, stage_share=shares,
+                keypoints_per_image=float(cnt[:, :2].mean()), tracked_per_frame=float(cnt[:, 6].mean()),
+                stereo_match_gflop_per_step=2.0 * mm * 128 / 1e9 / args.steps, match_gemm_ms_per_step=gemm_ms / args.steps)
+    if world == 1:
+        try:
+            line["match_gemm"] = match_gemm_leg(ctx, torch, pk)
+        except Exception as e:  # keep the headline line even if the side leg fails
+            line["match_gemm"] = dict(error=str(e))
+        if not args.no_cpu:
+            line["cpu_baseline"] = cpu_oracle_sample()
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="new frames per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -43,6 +43,17 @@ int vo_ctx_sync(vo_ctx* ctx);
 /* stream used by the host-pointer entry points (cudaStream_t) */
 void* vo_ctx_stream(vo_ctx* ctx);
 
+/* Stage profiler (used by bench.py for the roofline line): when enabled, every kernel stage is
+ * bracketed by CUDA events on its launching stream.  vo_profile_get returns, per stage name, the
+ * summed device time, the number of launches and the ALGORITHMIC bytes / flops those launches
+ * were asked to process (DESIGN.md "roofline accounting"). */
+int vo_profile_enable(vo_ctx* ctx, int on);
+/* number of CUDA kernels this context has launched since creation */
+long long vo_kernel_launches(vo_ctx* ctx);
+int vo_profile_count(vo_ctx* ctx);
+int vo_profile_get(vo_ctx* ctx, int i, char* name, int name_cap, double* ms, long long* launches,
+                   double* bytes, double* flops);
+
 /* ------------------------------------------------------------------------------------ SIFT */
 typedef struct {
   float contrast_threshold; /* MATLAB ContrastThreshold (per layer); <= 0 -> 0.04/3          */
@@ -162,6 +173,10 @@ typedef struct {
 int vo_frames(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_frames, int rows,
               int cols, const double P1[12], const double P2[12], const vo_frames_opts* opts,
               double* rel_pose, int* status, int* counts);
+/* Same, with the images already resident in device memory (left_dev/right_dev: device pointers). */
+int vo_frames_dev(vo_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev, int n_frames,
+                  int rows, int cols, const double P1[12], const double P2[12],
+                  const vo_frames_opts* opts, double* rel_pose, int* status, int* counts);
 
 #ifdef __cplusplus
 }

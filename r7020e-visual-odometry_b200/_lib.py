@@ -44,7 +44,7 @@ class FramesOpts(C.Structure):
 # every symbol include/vo_b200.h declares (tests check that the .so exports each one)
 EXPORTS = [
     "vo_version", "vo_last_error", "vo_ctx_create", "vo_ctx_destroy", "vo_ctx_sync",
-    "vo_ctx_stream", "vo_sift", "vo_sift_batch", "vo_match", "vo_match_top2", "vo_match_dev",
+    "vo_ctx_stream", "vo_profile_enable", "vo_kernel_launches", "vo_profile_count", "vo_profile_get", "vo_frames_dev", "vo_sift", "vo_sift_batch", "vo_match", "vo_match_top2", "vo_match_dev",
     "vo_match_top2_dev", "vo_match_stats", "vo_match_debug_gemm", "vo_triangulate", "vo_p3p",
     "vo_frames",
 ]
@@ -64,6 +64,8 @@ def lib():
         L.vo_ctx_destroy.argtypes = [C.c_void_p]
         L.vo_ctx_destroy.restype = None
         L.vo_ctx_sync.argtypes = [C.c_void_p]
+        L.vo_kernel_launches.restype = C.c_longlong
+        L.vo_kernel_launches.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 

@@ -54,6 +54,30 @@ class Context:
     def sync(self):
         check(_lib.lib().vo_ctx_sync(self._h))
 
+    def profile_enable(self, on=True):
+        """Bracket every kernel stage with CUDA events (see vo_profile_enable); resets the totals."""
+        check(_lib.lib().vo_profile_enable(self._h, 1 if on else 0))
+
+    def profile(self):
+        """{stage: dict(ms, launches, bytes, flops)} accumulated since profile_enable()."""
+        L = _lib.lib()
+        out = {}
+        for i in range(L.vo_profile_count(self._h)):
+            name = C.create_string_buffer(64)
+            ms, by, fl = C.c_double(), C.c_double(), C.c_double()
+            ln = C.c_longlong()
+            check(L.vo_profile_get(self._h, i, name, 64, C.byref(ms), C.byref(ln), C.byref(by), C.byref(fl)))
+            out[name.value.decode()] = dict(ms=ms.value, launches=ln.value, bytes=by.value, flops=fl.value)
+        return out
+
+    def kernel_launches(self):
+        return int(_lib.lib().vo_kernel_launches(self._h))
+
+    @property
+    def stream(self):
+        """cudaStream_t (int) the host-pointer entry points launch on."""
+        return _lib.lib().vo_ctx_stream(self._h)
+
     def match_stats(self):
         s = (C.c_int * 4)()
         check(_lib.lib().vo_match_stats(self._h, s))

@@ -24,7 +24,42 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
+ProfScope::ProfScope(vo_ctx* ctx, cudaStream_t s, const char* name, double bytes, double flops, int kernels) : c(ctx), st(s), on(false) {
+  if (ctx) ctx->kernel_launches += kernels;
+  if (!ctx || !ctx->prof_enabled) return;
+  rec.stage = ctx->prof_stage_id(name);
+  ProfStage& ps = ctx->prof_stages[rec.stage];
+  ps.bytes += bytes; ps.flops += flops; ps.launches += 1;
+  auto get = [&]() { cudaEvent_t e; if (!ctx->prof_pool.empty()) { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+  rec.e0 = get(); rec.e1 = get();
+  cudaEventRecord(rec.e0, st);
+  on = true;
+}
+ProfScope::~ProfScope() {
+  if (!on) return;
+  cudaEventRecord(rec.e1, st);
+  c->prof_pending.push_back(rec);
+}
+
 }  // namespace vo
+
+int vo_ctx::prof_stage_id(const char* name) {
+  for (size_t i = 0; i < prof_stages.size(); ++i)
+    if (prof_stages[i].name == name) return (int)i;
+  vo::ProfStage ps; ps.name = name;
+  prof_stages.push_back(ps);
+  return (int)prof_stages.size() - 1;
+}
+
+void vo_ctx::prof_collect() {
+  for (auto& r : prof_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess)
+      prof_stages[r.stage].ms += ms;
+    prof_pool.push_back(r.e0); prof_pool.push_back(r.e1);
+  }
+  prof_pending.clear();
+}
 
 int vo_ctx::dev(const char* name, size_t bytes, void** out) {
   vo::Scratch& s = scratch[name];
@@ -103,6 +138,8 @@ void vo_ctx_destroy(vo_ctx* c) {
   cudaStreamSynchronize(c->stream);
   if (c->sift_plan) vo::sift_plan_destroy(c->sift_plan);
   if (c->frame_plan) vo::frame_plan_destroy(c->frame_plan);
+  c->prof_collect();
+  for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   for (auto& kv : c->scratch) {
     if (!kv.second.ptr) continue;
     if (kv.second.host) cudaFreeHost(kv.second.ptr);
@@ -119,5 +156,32 @@ int vo_ctx_sync(vo_ctx* c) {
 }
 
 void* vo_ctx_stream(vo_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int vo_profile_enable(vo_ctx* c, int on) {
+  VO_CHECK_ARG(c != nullptr, "ctx is null");
+  c->prof_collect();
+  c->prof_enabled = on != 0;
+  c->prof_stages.clear();
+  return VO_OK;
+}
+
+long long vo_kernel_launches(vo_ctx* c) { return c ? c->kernel_launches : 0; }
+
+int vo_profile_count(vo_ctx* c) {
+  if (!c) return 0;
+  c->prof_collect();
+  return (int)c->prof_stages.size();
+}
+
+int vo_profile_get(vo_ctx* c, int i, char* name, int name_cap, double* ms, long long* launches, double* bytes, double* flops) {
+  VO_CHECK_ARG(c != nullptr && i >= 0 && i < (int)c->prof_stages.size(), "bad stage index");
+  const vo::ProfStage& ps = c->prof_stages[i];
+  if (name && name_cap > 0) { strncpy(name, ps.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (ms) *ms = ps.ms;
+  if (launches) *launches = ps.launches;
+  if (bytes) *bytes = ps.bytes;
+  if (flops) *flops = ps.flops;
+  return VO_OK;
+}
 
 }  // extern "C"

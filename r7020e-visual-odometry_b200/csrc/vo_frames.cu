@@ -55,9 +55,9 @@ gather_points_kernel(const vo_keypoint* __restrict__ kps, int kp_cap, const uint
 
 using namespace vo;
 
-extern "C" int vo_frames(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n, int rows, int cols,
-                         const double P1[12], const double P2[12], const vo_frames_opts* opts, double* rel_pose,
-                         int* status, int* counts) {
+static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int on_device, int n, int rows, int cols,
+                       const double P1[12], const double P2[12], const vo_frames_opts* opts, double* rel_pose,
+                       int* status, int* counts) {
   VO_CHECK_ARG(ctx && left && right && P1 && P2 && rel_pose && status, "null argument");
   VO_CHECK_ARG(n >= 1 && rows > 0 && cols > 0, "bad size");
   VO_CUDA(cudaSetDevice(ctx->device));
@@ -72,8 +72,9 @@ extern "C" int vo_frames(vo_ctx* ctx, const uint8_t* left, const uint8_t* right,
   const int kc = sift_plan_kp_cap(plan);
   const size_t img_bytes = (size_t)rows * cols;
   uint8_t* dimg = sift_plan_images(plan);
-  VO_CUDA(cudaMemcpy2DAsync(dimg, 2 * img_bytes, left, img_bytes, img_bytes, n, cudaMemcpyHostToDevice, st));
-  VO_CUDA(cudaMemcpy2DAsync(dimg + img_bytes, 2 * img_bytes, right, img_bytes, img_bytes, n, cudaMemcpyHostToDevice, st));
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  VO_CUDA(cudaMemcpy2DAsync(dimg, 2 * img_bytes, left, img_bytes, img_bytes, n, kind, st));
+  VO_CUDA(cudaMemcpy2DAsync(dimg + img_bytes, 2 * img_bytes, right, img_bytes, img_bytes, n, kind, st));
   VO_TRY(sift_run_device(ctx, plan, 2 * n, so, st));
   const float* desc = sift_plan_desc(plan);
   const vo_keypoint* kps = sift_plan_keypoints(plan);
@@ -111,6 +112,7 @@ extern "C" int vo_frames(vo_ctx* ctx, const uint8_t* left, const uint8_t* right,
       VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t));
       VO_TRY(match_batch_select(ctx, t, A, B, np, mo, a1, b1, nullptr, kc, K + n, 1, st));
       compose_kernel<<<cg, 256, 0, st>>>(oL1, l0, oR1, r0, b1, K + n, kc);            // VO.m:287-290
+      ctx->kernel_launches += 6;   // 5 compose launches + gather_points below
     }
     // M2 = matchFeatures(cur.r_desc, old.r_desc)                                 VO.m:293
     {
@@ -149,7 +151,11 @@ extern "C" int vo_frames(vo_ctx* ctx, const uint8_t* left, const uint8_t* right,
   VO_CUDA(cudaMemcpyAsync(dP, hP, sizeof(hP), cudaMemcpyHostToDevice, st));
   if (np > 0) {
     gather_points_kernel<<<cg, 256, 0, st>>>(kps, kc, oL2, oR2, cL3, a4, b4, K + 4 * n, old_l, old_r, cur_l);
-    VO_TRY(triangulate_batch_device(old_l, old_r, K + 4 * n, 1, kc, np, dP, world, st));
+    {
+      ProfScope ps(ctx, st, "triangulate");
+      VO_TRY(triangulate_batch_device(old_l, old_r, K + 4 * n, 1, kc, np, dP, world, st));
+    }
+    ProfScope ps(ctx, st, "p3p_msac", 0.0, 0.0, 2);
     vo_p3p_opts pp = po;
     pp.seed = po.seed + (uint64_t)(first_frame + 1) * 0x9E3779B97F4A7C15ull;
     VO_TRY(p3p_batch_device(ctx, cur_l, world, K + 4 * n, kc, np, dP + 24, pp, dA, nullptr, dstat, dstat + n, st));
@@ -188,4 +194,15 @@ extern "C" int vo_frames(vo_ctx* ctx, const uint8_t* left, const uint8_t* right,
     }
   }
   return rc;
+}
+
+extern "C" {
+int vo_frames(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n, int rows, int cols, const double P1[12],
+              const double P2[12], const vo_frames_opts* opts, double* rel_pose, int* status, int* counts) {
+  return frames_core(ctx, left, right, 0, n, rows, cols, P1, P2, opts, rel_pose, status, counts);
+}
+int vo_frames_dev(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n, int rows, int cols, const double P1[12],
+                  const double P2[12], const vo_frames_opts* opts, double* rel_pose, int* status, int* counts) {
+  return frames_core(ctx, left, right, 1, n, rows, cols, P1, P2, opts, rel_pose, status, counts);
+}
 }

@@ -45,6 +45,11 @@ struct Scratch {
   bool host = false;
 };
 
+// Optional stage profiler: when enabled, every stage launch is bracketed by CUDA events on the
+// launching stream; totals (ms, launches, algorithmic bytes / flops) are read back per stage name.
+struct ProfRec { int stage; cudaEvent_t e0, e1; };
+struct ProfStage { std::string name; double ms = 0; long long launches = 0; double bytes = 0; double flops = 0; };
+
 struct SiftPlan;   // vo_sift.cu
 struct FramePlan;  // vo_frames.cu
 
@@ -56,6 +61,13 @@ struct vo_ctx {
   cudaStream_t stream = nullptr;
   std::map<std::string, vo::Scratch> scratch;
   int match_stats[4] = {0, 0, 0, 0};
+  long long kernel_launches = 0;   // kernels launched by this context (bench.py's gpu_launches)
+  bool prof_enabled = false;
+  std::vector<vo::ProfStage> prof_stages;
+  std::vector<vo::ProfRec> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  int prof_stage_id(const char* name);
+  void prof_collect();
   vo::SiftPlan* sift_plan = nullptr;
   vo::FramePlan* frame_plan = nullptr;
 
@@ -91,4 +103,11 @@ void sift_plan_destroy(SiftPlan*);
 void frame_plan_destroy(FramePlan*);
 
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// RAII bracket around one or more launches of a stage
+struct ProfScope {
+  vo_ctx* c; cudaStream_t st; ProfRec rec; bool on;
+  ProfScope(vo_ctx* ctx, cudaStream_t s, const char* name, double bytes = 0, double flops = 0, int kernels = 1);
+  ~ProfScope();
+};
 }  // namespace vo

@@ -688,8 +688,12 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   if (A.cap <= 0 || n_prob <= 0) return VO_OK;
 
   const size_t prep_smem = (size_t)PREP_ROWS * (dim + 1) * sizeof(float);
-  match_prep_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, kp, 0, opA, rawA, invA, ctl);
-  match_prep_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, kp, 1, opB, rawB, invB, ctl);
+  const bool exact_sizes = (n_prob == 1 && !A.gather && !B.gather);   // caps are the live sizes
+  {
+    ProfScope ps(ctx, st, "match_prep", exact_sizes ? ((double)A.cap + B.cap) * dim * 4.0 : 0.0, 0.0, 2);
+    match_prep_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, kp, 0, opA, rawA, invA, ctl);
+    match_prep_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, kp, 1, opB, rawB, invB, ctl);
+  }
   VO_CUDA(cudaGetLastError());
 
   const int m_blocks = a_alloc / BM;
@@ -713,12 +717,14 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
       g_attr_set = true;
     }
     dim3 grid(m_blocks, n_splits, n_prob);
+    ProfScope ps(ctx, st, "match_gemm_topk", 0.0, exact_sizes ? 2.0 * A.cap * B.cap * dim : 0.0);
     match_topk_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, invB, b_alloc, A.count, A.count_stride, A.cap, B.count,
                                                              B.count_stride, B.cap, ctl, kp / BK, n_splits, cand, cand_stride,
                                                              dbg_c, B.cap);
     VO_CUDA(cudaGetLastError());
     ctx->match_stats[2] = 1;
   }
+  ProfScope ps_fin(ctx, st, "match_finalize_rowscan", 0.0, 0.0, B.cap > 0 ? 2 : 1);
   match_finalize_kernel<<<dim3(div_up(A.cap, 128), n_prob), 128, 0, st>>>(
       cand, cand_stride, n_slots, ra, rb, dim, invA, a_alloc, invB, b_alloc, A.count, A.count_stride, A.cap, B.count,
       B.count_stride, B.cap, ctl, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
@@ -747,6 +753,7 @@ int match_batch_select(vo_ctx* ctx, const MatchTop2& t, const MatchOperand& A, c
   (void)ctx;
   if (n_prob <= 0) return VO_OK;
   const float thr = o.match_threshold * 0.04f;
+  ProfScope ps(ctx, st, "match_select");
   match_select_block_kernel<<<n_prob, 1024, 0, st>>>(t.j1, t.s1, t.s2, t.row_stride, A.count, A.count_stride, A.cap, B.count,
                                                      B.count_stride, B.cap, thr, o.max_ratio, o.index_base, idx1, idx2, metric,
                                                      out_stride, n_pairs, np_stride);
@@ -764,6 +771,7 @@ static int single_operands(vo_ctx* ctx, const float* f1, int n1, const float* f2
                            cudaStream_t st, Single* s) {
   VO_TRY(dev_buf(ctx, (std::string("m_counts_") + tag).c_str(), 8, &s->counts));
   match_set_counts_kernel<<<1, 32, 0, st>>>(s->counts, n1, n2);
+  ctx->kernel_launches += 1;
   s->A = MatchOperand(); s->B = MatchOperand();
   s->A.base = f1; s->A.count = s->counts; s->A.cap = n1; s->A.col_major = col_major; s->A.ld = n1;
   s->B.base = f2; s->B.count = s->counts + 1; s->B.cap = n2; s->B.col_major = col_major; s->B.ld = n2;
@@ -795,6 +803,7 @@ static int match_device(vo_ctx* ctx, const float* f1, int n1, const float* f2, i
   const int nb = div_up(n1, SEL_BLOCK);
   int* blk; VO_TRY(dev_buf(ctx, "m_blk", (size_t)nb + 1, &blk));
   const float thr = o.match_threshold * 0.04f;
+  ctx->kernel_launches += 3;
   match_count_kernel<<<nb, SEL_BLOCK, 0, st>>>(t.j1, t.s1, t.s2, bj1, s.counts, s.counts + 1, thr, o.max_ratio, blk);
   match_scan_kernel<<<1, 1024, 0, st>>>(blk, nb, n_pairs_dev);
   match_scatter_kernel<<<nb, SEL_BLOCK, 0, st>>>(t.j1, t.s1, t.s2, bj1, s.counts, s.counts + 1, thr, o.max_ratio, o.index_base, blk,

@@ -772,18 +772,25 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
   const int nl = p->nl;
   VO_CUDA(cudaMemsetAsync(p->counters, 0, (size_t)batch * 4 * sizeof(int), st));
   // pyramid
+  ProfScope* ps_base = new ProfScope(ctx, st, "sift_base_upsample_blur", (double)batch * ((double)p->rows * p->cols + (double)p->h[0] * p->w[0] * 4.0));
   if (p->base_taps.r == 5)
     VO_TRY((launch_blur_t<5, true>(nullptr, p->img, p->G(0, 0), nullptr, p->h[0], p->w[0], p->pitch[0], p->rows, p->cols, batch, p->base_taps, st)));
   else
     VO_TRY((launch_blur_t<0, true>(nullptr, p->img, p->G(0, 0), nullptr, p->h[0], p->w[0], p->pitch[0], p->rows, p->cols, batch, p->base_taps, st)));
+  delete ps_base;
   // note: layer_elems uses p->batch; kernels index images with the plan's batch stride
   for (int oc = 0; oc < p->n_oct; ++oc) {
+    const double px = (double)batch * p->h[oc] * p->w[oc];
     if (oc > 0) {
+      ProfScope ps(ctx, st, "sift_downsample", px * 8.0);
       dim3 g(div_up(p->w[oc], 256), p->h[oc], batch);
       sift_downsample_kernel<<<g, 256, 0, st>>>(p->G(oc - 1, nl), p->G(oc, 0), p->h[oc - 1], p->pitch[oc - 1], p->h[oc], p->w[oc], p->pitch[oc]);
     }
-    for (int i = 1; i < nl + 3; ++i)
+    char nm[32]; snprintf(nm, sizeof(nm), oc == 0 ? "sift_blur_dog_oct0" : (oc == 1 ? "sift_blur_dog_oct1" : "sift_blur_dog_oct2+"));
+    for (int i = 1; i < nl + 3; ++i) {
+      ProfScope ps(ctx, st, nm, px * 12.0);   // read G[l], write G[l+1], write D[l]
       VO_TRY(launch_blur(p->G(oc, i - 1), p->G(oc, i), p->D(oc, i - 1), p->h[oc], p->w[oc], p->pitch[oc], batch, p->taps[i], st));
+    }
   }
   VO_CUDA(cudaGetLastError());
   // extrema
@@ -792,6 +799,7 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
   for (int oc = 0; oc < p->n_oct; ++oc) {
     if (p->h[oc] <= 2 * SIFT_BORDER || p->w[oc] <= 2 * SIFT_BORDER) continue;
     dim3 g(div_up(p->w[oc], 32), div_up(p->h[oc], 8), batch * nl);
+    ProfScope ps(ctx, st, "sift_extrema", (double)batch * p->h[oc] * p->w[oc] * 4.0 * (nl + 2));
     sift_extrema_kernel<<<g, 256, 0, st>>>(p->D(oc, 0), oc, nl, p->batch, p->h[oc], p->w[oc], p->pitch[oc], threshold, p->cand, p->cand_cap, p->counters);
   }
   OctInfo oi;
@@ -799,15 +807,18 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
   for (int oc = 0; oc < p->n_oct; ++oc) { oi.h[oc] = p->h[oc]; oi.w[oc] = p->w[oc]; oi.pitch[oc] = p->pitch[oc]; oi.goff[oc] = p->goff[oc]; oi.doff[oc] = p->doff[oc]; }
   {
     dim3 g(ctx->num_sms * 4 / (batch > 4 ? 4 : 1), batch);
+    ProfScope ps(ctx, st, "sift_refine_orient");
     sift_refine_orient_kernel<<<g, 128, 0, st>>>(p->gauss, p->dog, oi, p->batch, nl, contrast_cv, o.edge_threshold, o.sigma, p->cand, p->cand_cap, p->counters, p->raw, p->kp_cap);
   }
   {
     dim3 g(p->kp_cap / 256, batch);
+    ProfScope ps(ctx, st, "sift_sort_dedupe", 0.0, 0.0, 2);
     sift_rank_kernel<<<g, 256, 0, st>>>(p->raw, p->kp_cap, p->counters, p->sorted);
     sift_dedupe_kernel<<<batch, 1024, 0, st>>>(p->sorted, p->kp_cap, p->counters, p->final_kp, (float)o.index_base);
   }
   {
     dim3 g(ctx->num_sms * 4 / (batch > 4 ? 4 : 1), batch);
+    ProfScope ps(ctx, st, "sift_descriptor");
     sift_descriptor_kernel<<<g, 128, 0, st>>>(p->gauss, oi, p->batch, nl, p->final_kp, p->kp_cap, p->counters, (float)o.index_base, p->desc);
   }
   VO_CUDA(cudaGetLastError());

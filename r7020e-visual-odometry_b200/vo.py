@@ -107,13 +107,18 @@ class VisualOdometry:
         return rel
 
 
-def run_frames(left, right, P1, P2, seed=0, first_frame=0, max_keypoints=8192, ctx=None):
-    """Batched device-resident loop body (vo_frames).  left/right: [n, rows, cols] uint8.
+def run_frames(left, right, P1, P2, seed=0, first_frame=0, max_keypoints=8192, ctx=None, device_ptrs=None):
+    """Batched device-resident loop body (vo_frames).  left/right: [n, rows, cols] uint8 host
+    arrays (NumPy, or pinned torch CPU tensors via .numpy()).  With ``device_ptrs=(lptr, rptr,
+    n, rows, cols)`` the images are already in HBM (vo_frames_dev) and left/right are ignored.
     Returns (rel_pose [n,4,4], status [n], counts [n,8])."""
     ctx = ctx or api.default_context()
-    left = np.ascontiguousarray(left, dtype=np.uint8)
-    right = np.ascontiguousarray(right, dtype=np.uint8)
-    n, rows, cols = left.shape
+    if device_ptrs is None:
+        left = np.ascontiguousarray(left, dtype=np.uint8)
+        right = np.ascontiguousarray(right, dtype=np.uint8)
+        n, rows, cols = left.shape
+    else:
+        n, rows, cols = device_ptrs[2:]
     P1 = np.ascontiguousarray(P1, dtype=np.float64).reshape(12)
     P2 = np.ascontiguousarray(P2, dtype=np.float64).reshape(12)
     o = _lib.FramesOpts()
@@ -126,9 +131,14 @@ def run_frames(left, right, P1, P2, seed=0, first_frame=0, max_keypoints=8192, c
     status = np.zeros(n, dtype=np.int32)
     counts = np.zeros((n, 8), dtype=np.int32)
     p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
-    check(_lib.lib().vo_frames(ctx.handle, p(left, C.c_uint8), p(right, C.c_uint8), n, rows, cols,
-                               p(P1, C.c_double), p(P2, C.c_double), C.byref(o), p(rel, C.c_double),
-                               p(status, C.c_int), p(counts, C.c_int)))
+    if device_ptrs is None:
+        check(_lib.lib().vo_frames(ctx.handle, p(left, C.c_uint8), p(right, C.c_uint8), n, rows, cols,
+                                   p(P1, C.c_double), p(P2, C.c_double), C.byref(o), p(rel, C.c_double),
+                                   p(status, C.c_int), p(counts, C.c_int)))
+    else:
+        check(_lib.lib().vo_frames_dev(ctx.handle, C.c_void_p(device_ptrs[0]), C.c_void_p(device_ptrs[1]),
+                                       n, rows, cols, p(P1, C.c_double), p(P2, C.c_double), C.byref(o),
+                                       p(rel, C.c_double), p(status, C.c_int), p(counts, C.c_int)))
     return rel, status, counts
 
 
