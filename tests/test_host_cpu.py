@@ -1,0 +1,112 @@
+"""CPU suite: host-side logic -- sharding arithmetic (gloo, world_size 2), the KITTI evaluator, the
+synthetic generator, and the VO loop mirror driven by the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_frame_and_row_chunks():
+    from vo_b200 import shard
+    for n in (1, 2, 7, 33, 4541):
+        for w in (1, 2, 3, 4, 8):
+            ch = shard.frame_chunks(n, w)
+            assert ch[0][0] == 1 and ch[-1][1] == max(n, 1)
+            assert all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+            sizes = [h - l for l, h in ch]
+            assert max(sizes) - min(sizes) <= 1
+    assert shard.row_chunks(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from vo_b200 import shard
+    from oracle import oracle
+    # (1) frame sharding: fake per-frame result = f(frame index) so stitching errors are visible
+    n_frames = 11
+
+    def load(lo, hi):
+        return np.arange(lo, hi), np.arange(lo, hi)
+
+    def run(left, right, first):
+        n = len(left)
+        rel = np.tile(np.eye(4), (n, 1, 1))
+        rel[:, 0, 3] = left * 10.0 + 1.0
+        assert left[0] == first
+        return rel, np.full(n, 0), None
+    rel, status = shard.run_sequence_sharded(load, n_frames, run, rank, world, dist, batch=3)
+    ok1 = np.array_equal(rel[1:, 0, 3], np.arange(1, n_frames) * 10.0 + 1.0) and np.array_equal(rel[0], np.eye(4))
+    # (2) row-sharded best-2 + all-gather equals the unsharded result bit for bit
+    rng = np.random.default_rng(0)
+    q_ = np.rint(np.abs(rng.normal(0, 40, (37, 128)))).astype(np.float32)
+    l_ = np.rint(np.abs(rng.normal(0, 40, (50, 128)))).astype(np.float32)
+    j1, s1, s2 = shard.match_top2_row_sharded(q_, l_, oracle.match_top2, rank, world, dist)
+    r1, r2, r3 = oracle.match_top2(q_, l_)
+    ok2 = np.array_equal(j1, r1) and np.array_equal(s1.view(np.uint32), r2.view(np.uint32)) and np.array_equal(s2.view(np.uint32), r3.view(np.uint32))
+    q.put((rank, bool(ok1), bool(ok2)))
+    dist.destroy_process_group()
+
+
+def test_sharding_with_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=180) for _ in ps]
+    for p in ps:
+        p.join(60)
+    assert sorted(res) == [(0, True, True), (1, True, True)]
+
+
+def test_kitti_eval_on_reference_ground_truth():
+    from vo_b200 import kitti_eval
+    k = np.load(os.path.join(G, "kitti00_reference_data.npz"))
+    gt = np.tile(np.eye(4), (len(k["poses"]), 1, 1)); gt[:, :3, :] = k["poses"]      # kitti/poses/00.txt
+    t, r, n = kitti_eval.kitti_errors(gt, gt)
+    assert n > 0 and t < 1e-12 and r < 1e-7
+    assert kitti_eval.xz_error(gt, gt).max() == 0
+    # a 1 % scale error on every step -> t_err = 1 %
+    rel = [np.linalg.inv(gt[i - 1]) @ gt[i] for i in range(1, len(gt))]
+    for a in rel:
+        a[:3, 3] *= 1.01
+    est = [np.eye(4)]
+    for a in rel:
+        est.append(est[-1] @ a)
+    t, r, n = kitti_eval.kitti_errors(np.array(est), gt)
+    assert 0.006 < t <= 0.0101 and r < 1e-6       # chord <= path length on curved segments
+    # reference's off-by-one (PlotOnMap.m compares pose k with truth row k): error is one step length
+    e = kitti_eval.xz_error(np.array(est)[1:], gt)
+    assert 0.3 < np.median(e[50:]) < 2.0
+
+
+def test_synth_streams():
+    from vo_b200 import synth
+    l, r = synth.shift_stream(3, seed=1, h=64, w=200, disparity=12, shift=3)
+    assert l.shape == (3, 64, 200) and l.dtype == np.uint8
+    assert np.array_equal(l[0][:, 12:], r[0][:, :-12])              # x_left - x_right = +12
+    assert np.array_equal(l[1][:, :-3], l[0][:, 3:])                # +3 px per frame
+    assert np.array_equal(synth.texture(32, 48, 5), synth.texture(32, 48, 5))
+    a, z = synth.shift_stream_truth()
+    assert abs(z - 32.18) < 0.01 and abs(a[0, 3] - 0.1343) < 1e-3
+
+
+def test_vo_loop_with_oracle_recovers_motion():
+    from vo_b200 import vo, synth
+    from oracle_ops import OracleOps
+    l, r = synth.shift_stream(3, seed=11, h=188, w=620)
+    o = vo.VisualOdometry(synth.KITTI_P0, synth.KITTI_P1, OracleOps(seed=1))
+    for i in range(3):
+        rel = o.step(l[i], r[i])
+    truth, _ = synth.shift_stream_truth()
+    assert np.allclose(rel[:3, 3], truth[:3, 3], atol=0.03) and np.allclose(rel[:3, :3], np.eye(3), atol=5e-3)
+    assert len(o.all_poses) == 2 and np.allclose(o.all_poses[-1], o.all_poses[0] @ rel)
+    assert o.log[-1]["k4"] <= o.log[-1]["k3"] <= min(o.log[-1]["k1"], o.log[-1]["k2"])
