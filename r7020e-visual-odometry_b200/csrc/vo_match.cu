@@ -418,10 +418,14 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
   const float* invb = invb_base + (size_t)prob * invb_stride;
   const float* a = ra.base + (size_t)prob * ra.prob_stride + (size_t)i * dim;
   const float* b_rows = rb.base + (size_t)prob * rb.prob_stride;
+  // exact-integer path: the tensor-core dot is the oracle's dot, so the epilogue key is already exact;
+  // split path: re-score the candidates with the oracle's sequential FP32 dot
+  const bool general = (*nonint_flag) != 0;
   float s[3]; int nc = 0;
   for (int q = 0; q < 3; ++q) {
     if (j[q] == 0xFFFFFFFFu) { s[q] = INFINITY; continue; }
-    s[q] = score_from_key(exact_key(a, b_rows + (size_t)j[q] * dim, dim, invb[j[q]]), ia);
+    const float key = general ? exact_key(a, b_rows + (size_t)j[q] * dim, dim, invb[j[q]]) : k[q];
+    s[q] = score_from_key(key, ia);
     ++nc;
   }
   uint32_t jj[3] = {j[0], j[1], j[2]};
@@ -438,7 +442,7 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
     certified = false;
   } else {
     float kb = k[2];
-    if (*nonint_flag) kb = kb + SPLIT_EPS * ((ia > 0.f) ? __fdiv_rn(1.0f, ia) : 0.f);
+    if (general) kb = kb + SPLIT_EPS * ((ia > 0.f) ? __fdiv_rn(1.0f, ia) : 0.f);
     const float sb = score_from_key(kb, ia);
     certified = (sb > s[0]) && (sb >= s[1]);
   }

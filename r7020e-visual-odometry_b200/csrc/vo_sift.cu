@@ -50,7 +50,7 @@ struct SiftPlan {
   int cand_cap = 0, kp_cap = 0;
   uint32_t* cand = nullptr; int* counters = nullptr;   // counters[b*4 + {0:cand,1:raw kp,2:final}]
   vo_keypoint* raw = nullptr; vo_keypoint* sorted = nullptr; vo_keypoint* final_kp = nullptr;
-  float* desc = nullptr;
+  float* desc = nullptr; float2* trig = nullptr;
   size_t layer_elems(int o) const { return (size_t)batch * h[o] * pitch[o]; }
   float* G(int o, int l) const { return gauss + goff[o] + (size_t)l * layer_elems(o); }
   float* D(int o, int l) const { return dog + doff[o] + (size_t)l * layer_elems(o); }
@@ -59,7 +59,7 @@ struct SiftPlan {
 void sift_plan_destroy(SiftPlan* p) {
   if (!p) return;
   cudaFree(p->gauss); cudaFree(p->dog); cudaFree(p->img); cudaFree(p->img_t); cudaFree(p->cand);
-  cudaFree(p->counters); cudaFree(p->raw); cudaFree(p->sorted); cudaFree(p->final_kp); cudaFree(p->desc);
+  cudaFree(p->counters); cudaFree(p->raw); cudaFree(p->sorted); cudaFree(p->final_kp); cudaFree(p->desc); cudaFree(p->trig);
   delete p;
 }
 
@@ -254,51 +254,75 @@ sift_downsample_kernel(const float* __restrict__ src, float* __restrict__ dst, i
 }
 
 // ----------------------------------------------------------------------- extrema detection
-// grid (ceil(w/32), ceil(h/8), batch * nl); candidate word = oct<<28 | layer<<25 | y<<13 | x
-__global__ void __launch_bounds__(256)
-sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int nl, int batch, int h, int w, int pitch,
+// 3x3x3 extrema of the DoG stack, separable and barrier-free.  A pixel of layer l is a maximum iff
+// val >= max3x3(l-1), max3x3(l), max3x3(l+1) (its own 3x3 max contains val itself), symmetrically
+// for minima -- the same predicate as comparing with all 26 neighbours.  One warp sweeps a strip
+// of 30 columns (lanes 1..30; lanes 0 and 31 are halo) down EX_ROWS rows: the horizontal 3-max/min
+// comes from two warp shuffles, the vertical one from a rolling 3-row register window, all NL+2
+// layers are carried together, so every DoG value is loaded from HBM once (coalesced 128-byte rows)
+// and there is no shared memory and no barrier.  Candidates are compacted with warp ballots.
+// candidate word = oct<<28 | layer<<25 | y<<13 | x
+constexpr int EX_COLS = 30, EX_ROWS = 32;
+template <int NL>
+__global__ void __launch_bounds__(128)
+sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int batch, int h, int w, int pitch,
                     float threshold, uint32_t* __restrict__ cand, int cand_cap, int* __restrict__ counters) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  const int b = blockIdx.z / nl, layer = 1 + blockIdx.z % nl;
+  constexpr int L = NL + 2;
+  const int lane = threadIdx.x & 31;
+  const int strip = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int x = strip * EX_COLS - 1 + lane;
+  if (strip * EX_COLS >= w) return;                       // warp-uniform
+  const int xc = min(max(x, 0), w - 1);
+  const int y0 = blockIdx.y * EX_ROWS;
+  const int b = blockIdx.z;
   const size_t layer_stride = (size_t)batch * h * pitch;
-  const float* cur = dog_oct + (size_t)layer * layer_stride + (size_t)b * h * pitch;
-  bool ext = false;
-  if (x >= SIFT_BORDER && x < w - SIFT_BORDER && y >= SIFT_BORDER && y < h - SIFT_BORDER) {
-    const size_t q = (size_t)y * pitch + x;
-    const float val = __ldg(cur + q);
-    if (fabsf(val) > threshold) {
-      const float* prv = cur - layer_stride;
-      const float* nxt = cur + layer_stride;
-      ext = true;
-      if (val > 0) {
+  const float* img = dog_oct + (size_t)b * h * pitch + xc;
+  float hxA[L], hxB[L], hxC[L], hnA[L], hnB[L], hnC[L], cB[L], cC[L];
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
+  for (int l = 0; l < L; ++l) { hxA[l] = hxB[l] = hxC[l] = hnA[l] = hnB[l] = hnC[l] = cB[l] = cC[l] = 0.f; }
+  const bool col_ok = lane >= 1 && lane <= EX_COLS && x >= SIFT_BORDER && x < w - SIFT_BORDER;
+  const int y_end = min(y0 + EX_ROWS, h - SIFT_BORDER);    // last row (exclusive) that can hold a keypoint
+  for (int r = y0 - 1; r <= y_end; ++r) {
+    const int rc = min(max(r, 0), h - 1);
+    float v[L];
 #pragma unroll
-          for (int dx = -1; dx <= 1; ++dx) {
-            const size_t qq = q + dy * pitch + dx;
-            ext = ext && val >= __ldg(cur + qq) && val >= __ldg(prv + qq) && val >= __ldg(nxt + qq);
-          }
-      } else {
+    for (int l = 0; l < L; ++l) v[l] = __ldg(img + (size_t)l * layer_stride + (size_t)rc * pitch);
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-          for (int dx = -1; dx <= 1; ++dx) {
-            const size_t qq = q + dy * pitch + dx;
-            ext = ext && val <= __ldg(cur + qq) && val <= __ldg(prv + qq) && val <= __ldg(nxt + qq);
-          }
-      }
+    for (int l = 0; l < L; ++l) {
+      const float lf = __shfl_up_sync(0xffffffffu, v[l], 1), rt = __shfl_down_sync(0xffffffffu, v[l], 1);
+      hxA[l] = hxB[l]; hxB[l] = hxC[l]; hnA[l] = hnB[l]; hnB[l] = hnC[l]; cB[l] = cC[l];
+      hxC[l] = fmaxf(fmaxf(lf, v[l]), rt);
+      hnC[l] = fminf(fminf(lf, v[l]), rt);
+      cC[l] = v[l];
     }
-  }
-  const unsigned mask = __ballot_sync(0xffffffffu, ext);
-  if (mask) {
-    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&counters[b * 4 + 0], __popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (ext) {
-      const int slot = base + __popc(mask & ((1u << lane) - 1u));
-      if (slot < cand_cap)
-        cand[(size_t)b * cand_cap + slot] = ((uint32_t)oct << 28) | ((uint32_t)layer << 25) | ((uint32_t)y << 13) | (uint32_t)x;
+    const int y = r - 1;                                   // the row whose 3x3 windows are now complete
+    if (y < y0 || y < SIFT_BORDER || y >= y_end) continue;  // warp-uniform
+    float mx[L], mn[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      mx[l] = fmaxf(fmaxf(hxA[l], hxB[l]), hxC[l]);
+      mn[l] = fminf(fminf(hnA[l], hnB[l]), hnC[l]);
+    }
+#pragma unroll
+    for (int layer = 1; layer <= NL; ++layer) {
+      const float val = cB[layer];
+      bool ext = false;
+      if (col_ok && fabsf(val) > threshold) {
+        if (val > 0) ext = val >= mx[layer - 1] && val >= mx[layer] && val >= mx[layer + 1];
+        else ext = val <= mn[layer - 1] && val <= mn[layer] && val <= mn[layer + 1];
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, ext);
+      if (mask) {
+        const int leader = __ffs(mask) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&counters[b * 4 + 0], __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (ext) {
+          const int slot = base + __popc(mask & ((1u << lane) - 1u));
+          if (slot < cand_cap)
+            cand[(size_t)b * cand_cap + slot] = ((uint32_t)oct << 28) | ((uint32_t)layer << 25) | ((uint32_t)y << 13) | (uint32_t)x;
+        }
+      }
     }
   }
 }
@@ -555,16 +579,40 @@ sift_dedupe_kernel(const vo_keypoint* __restrict__ sorted, int kp_cap, int* __re
 }
 
 // ------------------------------------------------------------------------------ descriptors
+// Per-keypoint rotation (float)cos/sin of the descriptor orientation, evaluated in FP64 like the
+// oracle; kept out of the descriptor kernel so that kernel stays at a low register count.
+__global__ void __launch_bounds__(256)
+sift_trig_kernel(const vo_keypoint* __restrict__ kps, int kp_cap, const int* __restrict__ counters, float2* __restrict__ trig) {
+  const int b = blockIdx.y;
+  const int n = min(counters[b * 4 + 2], kp_cap);
+  for (int k = blockIdx.x * 256 + threadIdx.x; k < n; k += gridDim.x * 256) {
+    float ori = 360.f - kps[(size_t)b * kp_cap + k].angle;
+    if (fabsf(ori - 360.f) < FLT_EPSILON) ori = 0.f;
+    const double ang = (double)ori * (3.14159265358979323846 / 180.0);
+    trig[(size_t)b * kp_cap + k] = make_float2((float)cos(ang), (float)sin(ang));
+  }
+}
+
+// Warp per keypoint.  The (2r+1)^2 window is scanned 32 samples at a time with a cheap accept test
+// (inside the rotated 4x4 bin grid and the image); accepted samples are compacted through a small
+// per-warp queue so the expensive part (gradient, exp, atan2, trilinear scatter) always runs on a
+// full warp.  The scatter uses integer shared-memory atomics into 4 privatised copies of the
+// 6x6x10 histogram (copy = lane & 3) to cut same-address serialisation; integer sums make the
+// result independent of the order and of the copy assignment.
+constexpr int DESC_COPIES = 4;
 __global__ void __launch_bounds__(128)
 sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int batch, int nl,
-                       const vo_keypoint* __restrict__ kps, int kp_cap, const int* __restrict__ counters,
-                       float loc_offset, float* __restrict__ desc) {
+                       const vo_keypoint* __restrict__ kps, const float2* __restrict__ trig, int kp_cap,
+                       const int* __restrict__ counters, float loc_offset, float* __restrict__ desc) {
   constexpr int D = 4, N = 8, HLEN = (D + 2) * (D + 2) * (N + 2);
-  __shared__ uint32_t s_hist[4][HLEN];
+  __shared__ uint32_t s_hist[4][DESC_COPIES * HLEN];
+  __shared__ uint32_t s_queue[4][64];
   __shared__ float s_vec[4][128];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int n = min(counters[b * 4 + 2], kp_cap);
+  uint32_t* hist = s_hist[wib] + (lane & (DESC_COPIES - 1)) * HLEN;
+  uint32_t* queue = s_queue[wib];
   for (int ki = blockIdx.x * 4 + wib; ki < n; ki += gridDim.x * 4) {
     const vo_keypoint kp = kps[(size_t)b * kp_cap + ki];
     int oc = kp.octave & 255; const int layer = (kp.octave >> 8) & 255;
@@ -579,26 +627,24 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
     const float ptx = (kp.x - loc_offset) * scale, pty = (kp.y - loc_offset) * scale;
     const float scl = size * 0.5f;
     const int px = __float2int_rn(ptx), py = __float2int_rn(pty);
-    const double ang = (double)ori * (3.14159265358979323846 / 180.0);
-    float cos_t = (float)cos(ang), sin_t = (float)sin(ang);
+    const float2 cs = trig[(size_t)b * kp_cap + ki];
     const float bins_per_rad = N / 360.f, exp_scale = -1.f / (D * D * 0.5f);
     const float hist_width = 3.0f * scl;
     int radius = __float2int_rn(hist_width * 1.4142135623730951f * (D + 1) * 0.5f);
     const int diag = (int)sqrt((double)cols * cols + (double)rows * rows);
     if (radius > diag) radius = diag;
-    cos_t = __fdiv_rn(cos_t, hist_width); sin_t = __fdiv_rn(sin_t, hist_width);
-    for (int k = lane; k < HLEN; k += 32) s_hist[wib][k] = 0;
+    const float cos_t = __fdiv_rn(cs.x, hist_width), sin_t = __fdiv_rn(cs.y, hist_width);
+    for (int k = lane; k < DESC_COPIES * HLEN; k += 32) s_hist[wib][k] = 0;
     __syncwarp();
-    const int side = 2 * radius + 1;
-    for (int idx = lane; idx < side * side; idx += 32) {
-      const int i = idx / side - radius, j = idx % side - radius;
+
+    auto process = [&](int i, int j) {
       const float c_rot = j * cos_t - i * sin_t;
       const float r_rot = j * sin_t + i * cos_t;
       float rbin = r_rot + D / 2 - 0.5f, cbin = c_rot + D / 2 - 0.5f;
       const int r = py + i, c = px + j;
-      if (!(rbin > -1 && rbin < D && cbin > -1 && cbin < D && r > 0 && r < rows - 1 && c > 0 && c < cols - 1)) continue;
-      const float dx = img[(size_t)r * pitch + c + 1] - img[(size_t)r * pitch + c - 1];
-      const float dy = img[(size_t)(r - 1) * pitch + c] - img[(size_t)(r + 1) * pitch + c];
+      const float* q = img + (size_t)r * pitch + c;
+      const float dx = q[1] - q[-1];
+      const float dy = q[-pitch] - q[pitch];
       const float wgt = vo_expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
       const float a = vo_atan2deg(dy, dx);
       const float mag = __fsqrt_rn(fmaf(dx, dx, dy * dy)) * wgt;
@@ -615,7 +661,7 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
       const float v101 = v_rc10 * obin, v100 = v_rc10 - v101;
       const float v011 = v_rc01 * obin, v010 = v_rc01 - v011;
       const float v001 = v_rc00 * obin, v000 = v_rc00 - v001;
-      uint32_t* hp = &s_hist[wib][((r0 + 1) * (D + 2) + c0 + 1) * (N + 2) + o0];
+      uint32_t* hp = hist + ((r0 + 1) * (D + 2) + c0 + 1) * (N + 2) + o0;
       atomicAdd(hp, (uint32_t)__float2int_rn(v000 * SIFT_FIX));
       atomicAdd(hp + 1, (uint32_t)__float2int_rn(v001 * SIFT_FIX));
       atomicAdd(hp + (N + 2), (uint32_t)__float2int_rn(v010 * SIFT_FIX));
@@ -624,27 +670,67 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
       atomicAdd(hp + (D + 2) * (N + 2) + 1, (uint32_t)__float2int_rn(v101 * SIFT_FIX));
       atomicAdd(hp + (D + 3) * (N + 2), (uint32_t)__float2int_rn(v110 * SIFT_FIX));
       atomicAdd(hp + (D + 3) * (N + 2) + 1, (uint32_t)__float2int_rn(v111 * SIFT_FIX));
+    };
+
+    const int side = 2 * radius + 1, total = side * side;
+    int i = lane / side - radius, j = lane % side - radius;     // this lane's sample of the first group
+    int qn = 0;                                                 // queue fill (warp-uniform)
+    for (int base = 0; base < total; base += 32) {
+      bool acc = false;
+      if (base + lane < total) {
+        const float c_rot = j * cos_t - i * sin_t;
+        const float r_rot = j * sin_t + i * cos_t;
+        const float rbin = r_rot + D / 2 - 0.5f, cbin = c_rot + D / 2 - 0.5f;
+        const int r = py + i, c = px + j;
+        acc = rbin > -1 && rbin < D && cbin > -1 && cbin < D && r > 0 && r < rows - 1 && c > 0 && c < cols - 1;
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, acc);
+      if (acc) queue[qn + __popc(mask & ((1u << lane) - 1u))] = ((uint32_t)(i + 32768) << 16) | (uint32_t)(j + 32768);
+      qn += __popc(mask);
+      j += 32;
+      while (j > radius) { j -= side; ++i; }
+      if (qn >= 32) {
+        __syncwarp();
+        const uint32_t e = queue[lane];
+        const uint32_t rest = queue[32 + lane];
+        process((int)(e >> 16) - 32768, (int)(e & 0xFFFF) - 32768);
+        __syncwarp();
+        qn -= 32;
+        if (lane < qn) queue[lane] = rest;
+        __syncwarp();
+      }
     }
     __syncwarp();
-    // fold the circular orientation bins and flatten to 128 floats
+    if (lane < qn) {
+      const uint32_t e = queue[lane];
+      process((int)(e >> 16) - 32768, (int)(e & 0xFFFF) - 32768);
+    }
+    __syncwarp();
+    // fold the copies and the circular orientation bins, flatten to 128 floats
     for (int e = lane; e < 128; e += 32) {
-      const int k = e & 7, cell = e >> 3, i = cell >> 2, j = cell & 3;
-      const int idx = ((i + 1) * (D + 2) + (j + 1)) * (N + 2);
-      uint32_t v = s_hist[wib][idx + k];
-      if (k < 2) v += s_hist[wib][idx + N + k];
+      const int k = e & 7, cell = e >> 3, ci = cell >> 2, cj = cell & 3;
+      const int idx = ((ci + 1) * (D + 2) + (cj + 1)) * (N + 2);
+      uint32_t v = 0;
+#pragma unroll
+      for (int cp = 0; cp < DESC_COPIES; ++cp) {
+        v += s_hist[wib][cp * HLEN + idx + k];
+        if (k < 2) v += s_hist[wib][cp * HLEN + idx + N + k];
+      }
       s_vec[wib][e] = (float)v * SIFT_INV_FIX;
     }
     __syncwarp();
     float nrm2 = 0.f;
+#pragma unroll 8
     for (int k = 0; k < 128; ++k) nrm2 = fmaf(s_vec[wib][k], s_vec[wib][k], nrm2);   // oracle order
     const float thr = __fsqrt_rn(nrm2) * 0.2f;
     nrm2 = 0.f;
+#pragma unroll 8
     for (int k = 0; k < 128; ++k) {
       const float v = fminf(s_vec[wib][k], thr);
       nrm2 = fmaf(v, v, nrm2);
     }
-    const float s = __fsqrt_rn(nrm2);
-    const float sc = __fdiv_rn(512.f, fmaxf(s, FLT_EPSILON));
+    const float sn = __fsqrt_rn(nrm2);
+    const float sc = __fdiv_rn(512.f, fmaxf(sn, FLT_EPSILON));
     float4 o4;
     float* ov = reinterpret_cast<float*>(&o4);
 #pragma unroll
@@ -762,6 +848,7 @@ static int get_plan(vo_ctx* ctx, int rows, int cols, int batch, const vo_sift_op
   A((void**)&p->cand, (size_t)batch * p->cand_cap * sizeof(uint32_t)); A((void**)&p->counters, (size_t)batch * 4 * sizeof(int));
   A((void**)&p->raw, (size_t)batch * kp_cap * sizeof(vo_keypoint)); A((void**)&p->sorted, (size_t)batch * kp_cap * sizeof(vo_keypoint));
   A((void**)&p->final_kp, (size_t)batch * kp_cap * sizeof(vo_keypoint)); A((void**)&p->desc, (size_t)batch * kp_cap * 128 * sizeof(float));
+  A((void**)&p->trig, (size_t)batch * kp_cap * sizeof(float2));
   if (e != cudaSuccess) { set_error("vo_sift: device allocation failed: %s", cudaGetErrorString(e)); sift_plan_destroy(p); return VO_ERR_CUDA; }
   ctx->sift_plan = p; *out = p;
   return VO_OK;
@@ -798,9 +885,17 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
   const float threshold = (float)(int)std::floor(0.5 * contrast_cv / nl * 255.0);
   for (int oc = 0; oc < p->n_oct; ++oc) {
     if (p->h[oc] <= 2 * SIFT_BORDER || p->w[oc] <= 2 * SIFT_BORDER) continue;
-    dim3 g(div_up(p->w[oc], 32), div_up(p->h[oc], 8), batch * nl);
+    dim3 g(div_up(div_up(p->w[oc], EX_COLS), 4), div_up(p->h[oc], EX_ROWS), batch);
     ProfScope ps(ctx, st, "sift_extrema", (double)batch * p->h[oc] * p->w[oc] * 4.0 * (nl + 2));
-    sift_extrema_kernel<<<g, 256, 0, st>>>(p->D(oc, 0), oc, nl, p->batch, p->h[oc], p->w[oc], p->pitch[oc], threshold, p->cand, p->cand_cap, p->counters);
+#define VO_EXTREMA(NLV) sift_extrema_kernel<NLV><<<g, 128, 0, st>>>(p->D(oc, 0), oc, p->batch, p->h[oc], p->w[oc], p->pitch[oc], threshold, p->cand, p->cand_cap, p->counters)
+    switch (nl) {
+      case 1: VO_EXTREMA(1); break;
+      case 2: VO_EXTREMA(2); break;
+      case 3: VO_EXTREMA(3); break;
+      case 4: VO_EXTREMA(4); break;
+      default: VO_EXTREMA(5); break;
+    }
+#undef VO_EXTREMA
   }
   OctInfo oi;
   memset(&oi, 0, sizeof(oi));
@@ -818,8 +913,9 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
   }
   {
     dim3 g(ctx->num_sms * 4 / (batch > 4 ? 4 : 1), batch);
-    ProfScope ps(ctx, st, "sift_descriptor");
-    sift_descriptor_kernel<<<g, 128, 0, st>>>(p->gauss, oi, p->batch, nl, p->final_kp, p->kp_cap, p->counters, (float)o.index_base, p->desc);
+    ProfScope ps(ctx, st, "sift_descriptor", 0.0, 0.0, 2);
+    sift_trig_kernel<<<dim3(8, batch), 256, 0, st>>>(p->final_kp, p->kp_cap, p->counters, p->trig);
+    sift_descriptor_kernel<<<g, 128, 0, st>>>(p->gauss, oi, p->batch, nl, p->final_kp, p->trig, p->kp_cap, p->counters, (float)o.index_base, p->desc);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
