@@ -36,10 +36,10 @@ constexpr int A_KBLOCK_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;    // 32 KB
 constexpr int MAX_KBLOCKS = 6;                // K' <= 384  (dim <= 128 split, or dim <= 384 exact)
 constexpr int B_STAGES = 4;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;              // 4 TMEM lane quarters x 4 column quarters of 64
 constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
 constexpr int NCAND = 3;
-constexpr int SMEM_BYTES = MAX_KBLOCKS * A_KBLOCK_BYTES + B_STAGES * B_STAGE_BYTES + 1024 + 256;
+constexpr int SMEM_BYTES = MAX_KBLOCKS * A_KBLOCK_BYTES + B_STAGES * B_STAGE_BYTES + 128 + 2 * BN * 4;   // 231,552 <= 232,448
 constexpr float SPLIT_EPS = 1.0f / 8192.0f;   // |approx key - oracle key| <= 2^-13 * ||a||
 
 // ------------------------------------------------------------------------------- PTX helpers
@@ -107,7 +107,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.ld is asynchronous: its destination registers are only valid after tcgen05.wait::ld.  The
+// registers are passed through the wait as read-write operands so the compiler cannot copy or
+// repack them (e.g. to form f32x2 pairs) before the data has landed.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
+
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
 
 struct Top3 {
   float k1, k2, k3;
@@ -133,7 +147,7 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
                   const int* __restrict__ nonint_flag, int kp_blocks, int n_splits,
                   uint2* __restrict__ cand_base, size_t cand_stride, float* __restrict__ dbg_c, int dbg_ld) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B-swizzled operand tiles need 1024-byte alignment
   const int prob = blockIdx.z;
   const int n1 = min(n1p[prob * n1_stride], cap1), n2 = min(n2p[prob * n2_stride], cap2);
   const int m0 = blockIdx.x * BM;
@@ -143,16 +157,16 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int split = blockIdx.y;
   const int t_begin = (int)((long long)split * tiles_total / n_splits);
   const int t_end = (int)((long long)(split + 1) * tiles_total / n_splits);
-  const int n_slots = n_splits * 2;
+  const int n_slots = n_splits * 4;
   uint2* cand = cand_base + (size_t)prob * cand_stride;
   const float* invb = invb_base + (size_t)prob * invb_stride;
 
   if (t_begin >= t_end) {  // nothing to contract: publish empty candidate slots
     if (warp >= 2) {
-      const int e = warp - 2, quarter = warp & 3, half = e >> 2;
+      const int e = warp - 2, quarter = warp & 3, cq = e >> 2;
       const int row = m0 + quarter * 32 + lane;
       if (row < n1) {
-        uint2* out = cand + ((size_t)row * n_slots + split * 2 + half) * NCAND;
+        uint2* out = cand + ((size_t)row * n_slots + split * 4 + cq) * NCAND;
         for (int c = 0; c < NCAND; ++c) out[c] = make_uint2(__float_as_uint(-INFINITY), 0xFFFFFFFFu);
       }
     }
@@ -160,7 +174,8 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   const int kblocks = (*nonint_flag) ? 3 * kp_blocks : kp_blocks;
 
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) __trap();
   const uint32_t sA = base;
   const uint32_t sB = sA + MAX_KBLOCKS * A_KBLOCK_BYTES;
   const uint32_t bars = sB + B_STAGES * B_STAGE_BYTES;
@@ -170,6 +185,7 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t bar_t_full = bar_b_empty + 8 * B_STAGES;  // [2]
   const uint32_t bar_t_empty = bar_t_full + 16;            // [2]
   const uint32_t tmem_slot = bar_t_empty + 16;
+  float* s_invb = reinterpret_cast<float*>(smem_raw + (bars + 128 - smem_u32(smem_raw)));   // [2][BN]
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   if (warp == 0 && lane == 0) {
@@ -230,59 +246,86 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ===== epilogue: thread = (row, column half); running top-3 over all tiles of the split =====
-    const int e = warp - 2, quarter = warp & 3, half = e >> 2;
+    // ===== epilogue: thread = (row, 64-column quarter); running top-3 over all tiles of the split.
+    // 1/||b_j|| of the NEXT tile is prefetched into registers and published to shared memory at the
+    // end of the current tile; the TMEM load of chunk c+1 is in flight while chunk c is reduced.
+    const int e = warp - 2, quarter = warp & 3, cq = e >> 2;
+    const int etid = threadIdx.x - 64;                       // 0..511 among the epilogue threads
     const int row = m0 + quarter * 32 + lane;
     Top3 top; top.init();
+    if (etid < BN) s_invb[etid] = __ldg(invb + (size_t)t_begin * BN + etid);
+    asm volatile("bar.sync 1, 512;" ::: "memory");
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = t_begin; t < t_end; ++t) {
+      const int buf = (t - t_begin) & 1;
+      float nxt = 0.f;
+      if (etid < BN && t + 1 < t_end) nxt = __ldg(invb + (size_t)(t + 1) * BN + etid);
       mbar_wait(bar_t_full + 8 * acc, acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int chunk = 0; chunk < 4; ++chunk) {
-        const int col_in_tile = half * 128 + chunk * 32;
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + cq * 64);
+      uint32_t r0[32], r1[32];
+      tmem_ld32(tbase, r0);
+#pragma unroll
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        const int col_in_tile = cq * 64 + chunk * 32;
         const int j0 = t * BN + col_in_tile;
-        if (j0 >= n2) break;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_in_tile), r);
-        float ib[32];
-        const float4* ibp = reinterpret_cast<const float4*>(invb + j0);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 v4 = __ldg(ibp + q);
-          ib[4 * q] = v4.x; ib[4 * q + 1] = v4.y; ib[4 * q + 2] = v4.z; ib[4 * q + 3] = v4.w;
-        }
-        tmem_ld_wait();
-        if (dbg_c != nullptr && row < n1) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (j0 + c < n2) dbg_c[(size_t)row * dbg_ld + j0 + c] = __uint_as_float(r[c]);
-        }
-        float v[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * ib[c];
-        if (j0 + 32 <= n2) {
-          float m = v[0];
-#pragma unroll
-          for (int c = 1; c < 32; ++c) m = fmaxf(m, v[c]);
-          if (m > top.k3) {
+        uint32_t (&r)[32] = chunk == 0 ? r0 : r1;
+        tmem_ld_wait(r);
+        if (chunk == 0) tmem_ld32(tbase + 32, r1);
+        if (j0 < n2) {
+          if (dbg_c != nullptr && row < n1) {
 #pragma unroll
             for (int c = 0; c < 32; ++c)
-              if (v[c] > top.k3) top.insert(v[c], (uint32_t)(j0 + c));
+              if (j0 + c < n2) dbg_c[(size_t)row * dbg_ld + j0 + c] = __uint_as_float(r[c]);
           }
-        } else {
+          float v[32];
+          const float4* ibp = reinterpret_cast<const float4*>(s_invb + buf * BN + col_in_tile);
 #pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (j0 + c < n2 && v[c] > top.k3) top.insert(v[c], (uint32_t)(j0 + c));
+          for (int q = 0; q < 8; ++q) {
+            const float4 i4 = ibp[q];
+            const unsigned long long a0 = ((unsigned long long)r[4 * q + 1] << 32) | r[4 * q];
+            const unsigned long long a1 = ((unsigned long long)r[4 * q + 3] << 32) | r[4 * q + 2];
+            const unsigned long long b0 = ((unsigned long long)__float_as_uint(i4.y) << 32) | __float_as_uint(i4.x);
+            const unsigned long long b1 = ((unsigned long long)__float_as_uint(i4.w) << 32) | __float_as_uint(i4.z);
+            const unsigned long long p0 = f2_mul(a0, b0), p1 = f2_mul(a1, b1);
+            v[4 * q] = __uint_as_float((uint32_t)p0); v[4 * q + 1] = __uint_as_float((uint32_t)(p0 >> 32));
+            v[4 * q + 2] = __uint_as_float((uint32_t)p1); v[4 * q + 3] = __uint_as_float((uint32_t)(p1 >> 32));
+          }
+          if (j0 + 32 <= n2) {
+            float g[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float m01 = fmaxf(fmaxf(v[8 * q], v[8 * q + 1]), v[8 * q + 2]);
+              const float m23 = fmaxf(fmaxf(v[8 * q + 3], v[8 * q + 4]), v[8 * q + 5]);
+              g[q] = fmaxf(fmaxf(m01, m23), fmaxf(v[8 * q + 6], v[8 * q + 7]));
+            }
+            const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+            if (m > top.k3) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (g[q] > top.k3) {
+#pragma unroll
+                  for (int c = 8 * q; c < 8 * q + 8; ++c)
+                    if (v[c] > top.k3) top.insert(v[c], (uint32_t)(j0 + c));
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (j0 + c < n2 && v[c] > top.k3) top.insert(v[c], (uint32_t)(j0 + c));
+          }
         }
       }
       tc_fence_before();
+      if (etid < BN && t + 1 < t_end) s_invb[(buf ^ 1) * BN + etid] = nxt;
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
     if (row < n1) {
-      uint2* out = cand + ((size_t)row * n_slots + split * 2 + half) * NCAND;
+      uint2* out = cand + ((size_t)row * n_slots + split * 4 + cq) * NCAND;
       out[0] = make_uint2(__float_as_uint(top.k1), top.i1);
       out[1] = make_uint2(__float_as_uint(top.k2), top.i2);
       out[2] = make_uint2(__float_as_uint(top.k3), top.i3);
@@ -707,7 +750,7 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
     if (n_splits > b_tiles) n_splits = b_tiles;
     if (n_splits < 1) n_splits = 1;
   }
-  const int n_slots = n_splits * 2;
+  const int n_slots = n_splits * 4;
   const size_t cand_stride = (size_t)a_alloc * n_slots * NCAND;
   uint2* cand; VO_TRY(dev_buf(ctx, nm("m_cand").c_str(), (size_t)n_prob * cand_stride, &cand));
   int* scan_list; VO_TRY(dev_buf(ctx, nm("m_scanlist").c_str(), (size_t)n_prob * a_alloc, &scan_list));
