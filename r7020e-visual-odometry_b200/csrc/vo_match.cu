@@ -39,7 +39,7 @@ constexpr int B_STAGES = 4;
 constexpr int NUM_EPI_WARPS = 16;              // 4 TMEM lane quarters x 4 column quarters of 64
 constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
 constexpr int NCAND = 3;
-constexpr int SMEM_BYTES = MAX_KBLOCKS * A_KBLOCK_BYTES + B_STAGES * B_STAGE_BYTES + 128 + 2 * BN * 4;   // 231,552 <= 232,448
+constexpr int SMEM_BYTES = MAX_KBLOCKS * A_KBLOCK_BYTES + B_STAGES * B_STAGE_BYTES + 128 + 2 * BN * 4 + BM * 4;   // 232,064 <= 232,448
 constexpr float SPLIT_EPS = 1.0f / 8192.0f;   // |approx key - oracle key| <= 2^-13 * ||a||
 
 // ------------------------------------------------------------------------------- PTX helpers
@@ -72,6 +72,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -184,8 +188,11 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t bar_b_empty = bar_b_full + 8 * B_STAGES;  // [B_STAGES]
   const uint32_t bar_t_full = bar_b_empty + 8 * B_STAGES;  // [2]
   const uint32_t bar_t_empty = bar_t_full + 16;            // [2]
-  const uint32_t tmem_slot = bar_t_empty + 16;
-  float* s_invb = reinterpret_cast<float*>(smem_raw + (bars + 128 - smem_u32(smem_raw)));   // [2][BN]
+  const uint32_t bar_i_full = bar_t_empty + 16;            // [2]  1/||b|| slice of the tile has landed
+  const uint32_t tmem_slot = bar_i_full + 16;
+  const uint32_t s_invb_addr = bars + 128;                 // [2][BN] floats, filled by bulk TMA copies
+  float* s_invb = reinterpret_cast<float*>(smem_raw + (s_invb_addr - smem_u32(smem_raw)));
+  float* s_thr = s_invb + 2 * BN;                          // [BM] per-row lower bound of the third-best key
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   if (warp == 0 && lane == 0) {
@@ -193,9 +200,10 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     mbar_init(bar_a_full, 1);
     for (int s = 0; s < B_STAGES; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, NUM_EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, NUM_EPI_WARPS); mbar_init(bar_i_full + 8 * s, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + BM) s_thr[threadIdx.x - 64] = -INFINITY;
   if (warp == 1) {  // whole warp: allocate all 512 TMEM columns (2 accumulator stages x 256)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -228,6 +236,9 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
+        // the epilogue of tile t-2 has drained this stage: its 1/||b|| slot can be refilled
+        mbar_expect_tx(bar_i_full + 8 * acc, BN * 4);
+        bulk_load_1d(s_invb_addr + acc * BN * 4, invb + (size_t)t * BN, BN * 4, bar_i_full + 8 * acc);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_b_full + 8 * stage, phase);
@@ -247,21 +258,21 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ===== epilogue: thread = (row, 64-column quarter); running top-3 over all tiles of the split.
-    // 1/||b_j|| of the NEXT tile is prefetched into registers and published to shared memory at the
-    // end of the current tile; the TMEM load of chunk c+1 is in flight while chunk c is reduced.
+    // The four threads that share a row (one per column quarter) exchange a lower bound of the row's
+    // third-best key through s_thr: an element at or below that bound can never enter the merged
+    // top-3, so it is skipped (every skipped element still satisfies key <= final k3, which is all
+    // the certification in match_finalize_kernel relies on).  The TMEM load of chunk c+1 is in
+    // flight while chunk c is reduced; warps are decoupled from each other (no CTA barrier).
     const int e = warp - 2, quarter = warp & 3, cq = e >> 2;
-    const int etid = threadIdx.x - 64;                       // 0..511 among the epilogue threads
-    const int row = m0 + quarter * 32 + lane;
+    const int row_in_cta = quarter * 32 + lane;
+    const int row = m0 + row_in_cta;
     Top3 top; top.init();
-    if (etid < BN) s_invb[etid] = __ldg(invb + (size_t)t_begin * BN + etid);
-    asm volatile("bar.sync 1, 512;" ::: "memory");
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = t_begin; t < t_end; ++t) {
-      const int buf = (t - t_begin) & 1;
-      float nxt = 0.f;
-      if (etid < BN && t + 1 < t_end) nxt = __ldg(invb + (size_t)(t + 1) * BN + etid);
+      mbar_wait(bar_i_full + 8 * acc, acc_phase);
       mbar_wait(bar_t_full + 8 * acc, acc_phase);
       tc_fence_after();
+      float thr = fmaxf(top.k3, s_thr[row_in_cta]);
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + cq * 64);
       uint32_t r0[32], r1[32];
       tmem_ld32(tbase, r0);
@@ -279,7 +290,7 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (j0 + c < n2) dbg_c[(size_t)row * dbg_ld + j0 + c] = __uint_as_float(r[c]);
           }
           float v[32];
-          const float4* ibp = reinterpret_cast<const float4*>(s_invb + buf * BN + col_in_tile);
+          const float4* ibp = reinterpret_cast<const float4*>(s_invb + acc * BN + col_in_tile);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 i4 = ibp[q];
@@ -300,28 +311,27 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               g[q] = fmaxf(fmaxf(m01, m23), fmaxf(v[8 * q + 6], v[8 * q + 7]));
             }
             const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
-            if (m > top.k3) {
+            if (m > thr) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                if (g[q] > top.k3) {
+                if (g[q] > thr) {
 #pragma unroll
                   for (int c = 8 * q; c < 8 * q + 8; ++c)
-                    if (v[c] > top.k3) top.insert(v[c], (uint32_t)(j0 + c));
+                    if (v[c] > thr) { top.insert(v[c], (uint32_t)(j0 + c)); thr = fmaxf(thr, top.k3); }
                 }
               }
             }
           } else {
 #pragma unroll
             for (int c = 0; c < 32; ++c)
-              if (j0 + c < n2 && v[c] > top.k3) top.insert(v[c], (uint32_t)(j0 + c));
+              if (j0 + c < n2 && v[c] > thr) { top.insert(v[c], (uint32_t)(j0 + c)); thr = fmaxf(thr, top.k3); }
           }
         }
       }
       tc_fence_before();
-      if (etid < BN && t + 1 < t_end) s_invb[(buf ^ 1) * BN + etid] = nxt;
+      if (top.k3 > s_thr[row_in_cta]) s_thr[row_in_cta] = top.k3;   // racy max: any stored value is a valid bound
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
-      asm volatile("bar.sync 1, 512;" ::: "memory");
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
     if (row < n1) {
