@@ -155,7 +155,7 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
       ProfScope ps(ctx, st, "triangulate");
       VO_TRY(triangulate_batch_device(old_l, old_r, K + 4 * n, 1, kc, np, dP, world, st));
     }
-    ProfScope ps(ctx, st, "p3p_msac", 0.0, 0.0, 2);
+    ProfScope ps(ctx, st, "p3p_msac", 0.0, 0.0, 4);
     vo_p3p_opts pp = po;
     pp.seed = po.seed + (uint64_t)(first_frame + 1) * 0x9E3779B97F4A7C15ull;
     VO_TRY(p3p_batch_device(ctx, cur_l, world, K + 4 * n, kc, np, dP + 24, pp, dA, nullptr, dstat, dstat + n, st));

@@ -294,11 +294,13 @@ __global__ void __launch_bounds__(128)
 p3p_hypothesis_kernel(const double* __restrict__ img_base, const double* __restrict__ world_base,
                       const int* __restrict__ n_ptr, int cap, const double* __restrict__ K4,
                       uint64_t seed, int max_trials, double tau, double* __restrict__ hyp_cost,
-                      int* __restrict__ hyp_ninl, double* __restrict__ hyp_rt) {
+                      int* __restrict__ hyp_ninl, double* __restrict__ hyp_rt, int trial0,
+                      const int* __restrict__ trial_bound) {
   const int prob = blockIdx.y;
-  const int trial = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int trial = trial0 + blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (trial >= max_trials) return;
+  if (trial_bound != nullptr && trial >= trial_bound[prob]) return;   // MSAC would never draw this trial
   const int n = n_ptr[prob] < cap ? n_ptr[prob] : cap;
   const size_t hidx = (size_t)prob * max_trials + trial;
   if (n < 4) { if (lane == 0) { hyp_cost[hidx] = DBL_MAX; hyp_ninl[hidx] = 0; } return; }
@@ -347,6 +349,46 @@ p3p_hypothesis_kernel(const double* __restrict__ img_base, const double* __restr
   }
 }
 
+// MSAC's sequential loop over precomputed per-trial costs: trial tr is visited iff tr < T, and T shrinks
+// whenever the best cost improves (smallest k with (1 - w^4)^k <= 1 - confidence).
+__device__ void msac_replay(const double* __restrict__ cost, const int* __restrict__ ninls, int n, int max_trials,
+                            int upto, int adaptive, double confidence, int* best_out, int* t_run_out, int* T_out) {
+  double best_cost = DBL_MAX; int T = max_trials, best = -1, t_run = 0;
+  for (int tr = 0; tr < upto; ++tr) {
+    if (adaptive && tr >= T) break;
+    ++t_run;
+    const double c = cost[tr];
+    if (c < best_cost) {
+      best_cost = c; best = tr;
+      if (adaptive) {
+        const double w = (double)ninls[tr] / (double)n;
+        const double pg = w * w * w * w;
+        const double miss = 1.0 - pg, target = 1.0 - 0.01 * confidence;
+        int Tn = T;
+        if (pg > 0) {
+          double prod = 1.0; Tn = 0;
+          while (Tn < T) { prod *= miss; ++Tn; if (prod <= target) break; }
+        }
+        if (Tn < T) T = Tn;
+      }
+    }
+  }
+  *best_out = best; *t_run_out = t_run; *T_out = T;
+}
+
+// after the first `head` trials: the largest trial index MSAC can still reach
+__global__ void p3p_bound_kernel(const int* __restrict__ n_ptr, int n_prob, int cap, int max_trials, int head, int adaptive,
+                                 double confidence, const double* __restrict__ hyp_cost,
+                                 const int* __restrict__ hyp_ninl, int* __restrict__ bound) {
+  const int prob = blockIdx.x * blockDim.x + threadIdx.x;
+  if (prob >= n_prob) return;
+  const int n = n_ptr[prob] < cap ? n_ptr[prob] : cap;
+  int best, t_run, T = max_trials;
+  if (n >= 4) msac_replay(hyp_cost + (size_t)prob * max_trials, hyp_ninl + (size_t)prob * max_trials, n, max_trials,
+                          head < max_trials ? head : max_trials, adaptive, confidence, &best, &t_run, &T);
+  bound[prob] = adaptive ? T : max_trials;
+}
+
 // one warp per problem: replay the sequential MSAC loop, then emit pose + inliers
 __global__ void __launch_bounds__(32)
 p3p_select_kernel(const double* __restrict__ img_base, const double* __restrict__ world_base,
@@ -369,28 +411,7 @@ p3p_select_kernel(const double* __restrict__ img_base, const double* __restrict_
   const double* cost = hyp_cost + (size_t)prob * max_trials;
   const int* ninls = hyp_ninl + (size_t)prob * max_trials;
   int best = -1, t_run = 0;
-  if (lane == 0) {
-    double best_cost = DBL_MAX; int T = max_trials;
-    for (int tr = 0; tr < max_trials; ++tr) {
-      if (adaptive && tr >= T) break;
-      ++t_run;
-      const double c = cost[tr];
-      if (c < best_cost) {
-        best_cost = c; best = tr;
-        if (adaptive) {
-          const double w = (double)ninls[tr] / (double)n;
-          const double pg = w * w * w * w;
-          const double miss = 1.0 - pg, target = 1.0 - 0.01 * confidence;
-          int Tn = T;
-          if (pg > 0) {
-            double prod = 1.0; Tn = 0;
-            while (Tn < T) { prod *= miss; ++Tn; if (prod <= target) break; }
-          }
-          if (Tn < T) T = Tn;
-        }
-      }
-    }
-  }
+  if (lane == 0) { int T; msac_replay(cost, ninls, n, max_trials, max_trials, adaptive, confidence, &best, &t_run, &T); }
   best = __shfl_sync(0xffffffffu, best, 0);
   t_run = __shfl_sync(0xffffffffu, t_run, 0);
   int ninl = 0;
@@ -441,8 +462,18 @@ int p3p_batch_device(vo_ctx* ctx, const double* img, const double* world, const 
   VO_TRY(dev_buf(ctx, "p3p_ninl", (size_t)n_prob * o.max_num_trials, &hn));
   VO_TRY(dev_buf(ctx, "p3p_rt", (size_t)n_prob * o.max_num_trials * 12, &hrt));
   const double tau = o.max_reproj_error * o.max_reproj_error;
-  dim3 grid(div_up(o.max_num_trials, 4), n_prob);
-  p3p_hypothesis_kernel<<<grid, 128, 0, st>>>(img, world, n_dev, cap, K4_dev, o.seed, o.max_num_trials, tau, hc, hn, hrt);
+  // pass 1: the first P3P_HEAD trials; then the adaptive bound they imply; pass 2: only trials MSAC can
+  // still reach (the rest exit immediately) -- identical result, a fraction of the work when inliers abound
+  constexpr int P3P_HEAD = 32;
+  int* bound; VO_TRY(dev_buf(ctx, "p3p_bound", (size_t)n_prob, &bound));
+  const int head = o.max_num_trials < P3P_HEAD ? o.max_num_trials : P3P_HEAD;
+  p3p_hypothesis_kernel<<<dim3(div_up(head, 4), n_prob), 128, 0, st>>>(img, world, n_dev, cap, K4_dev, o.seed, o.max_num_trials, tau,
+                                                                      hc, hn, hrt, 0, nullptr);
+  if (o.max_num_trials > head) {
+    p3p_bound_kernel<<<div_up(n_prob, 64), 64, 0, st>>>(n_dev, n_prob, cap, o.max_num_trials, head, o.adaptive, o.confidence, hc, hn, bound);
+    p3p_hypothesis_kernel<<<dim3(div_up(o.max_num_trials - head, 4), n_prob), 128, 0, st>>>(
+        img, world, n_dev, cap, K4_dev, o.seed, o.max_num_trials, tau, hc, hn, hrt, head, bound);
+  }
   p3p_select_kernel<<<n_prob, 32, 0, st>>>(img, world, n_dev, cap, K4_dev, o.max_num_trials, tau, o.confidence, o.adaptive,
                                            hc, hn, hrt, A_dev, inliers_dev, status_dev, info_dev);
   VO_CUDA(cudaGetLastError());

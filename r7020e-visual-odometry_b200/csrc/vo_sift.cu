@@ -22,6 +22,7 @@
 // no implicit contraction (-fmad=false), polynomial exp/atan2, histogram contributions rounded to
 // 1/4096 and summed as integers, so results do not depend on thread scheduling.
 #include "vo_internal.h"
+#include "vo_ptx.cuh"
 #include <cfloat>
 #include <cmath>
 
@@ -47,6 +48,7 @@ struct SiftPlan {
   uint8_t* img = nullptr;       // [batch][rows][cols]
   uint8_t* img_t = nullptr;     // staging for column-major input
   Taps taps[8]; Taps base_taps;
+  CUtensorMap tm_gauss[MAX_OCT];   // {w, h, layer*batch} view of every octave's Gaussian stack (blur input via TMA)
   int cand_cap = 0, kp_cap = 0;
   uint32_t* cand = nullptr; int* counters = nullptr;   // counters[b*4 + {0:cand,1:raw kp,2:final}]
   vo_keypoint* raw = nullptr; vo_keypoint* sorted = nullptr; vo_keypoint* final_kp = nullptr;
@@ -260,6 +262,146 @@ __device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.
 __device__ __forceinline__ u64 f2_add(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 f2_mul(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 f2_bcast(float k) { const float2 v = make_float2(k, k); return *reinterpret_cast<const u64*>(&v); }
+
+// TMA-staged variant (the one used for the large octaves).  Input rows arrive in 16-row groups through
+// cp.async.bulk.tensor.3d (tensor map {w, h, layer*batch}; out-of-image columns are zero-filled and
+// then patched with the reflect-101 values, which are already inside the box) into a double-buffered
+// stage; the load of group g+2 is issued right after group g has been row-filtered, i.e. a whole
+// chunk of compute ahead of its use, so no warp waits on HBM latency.  The ring holds 4 groups
+// (64 rows): the column pass of chunk c reads groups c..c+2 while group c+3 is being written, which
+// leaves a single __syncthreads per chunk.
+constexpr int TS_W = 128, TS_G = 16, TS_HALO = 16, TS_BOXW = TS_W + 2 * TS_HALO;   // 160-float box rows
+template <int R>
+__global__ void __launch_bounds__(256, 3)
+sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* __restrict__ dst,
+                     float* __restrict__ dog, const float* __restrict__ src, int h, int w, int pitch,
+                     int seg_rows, const Taps taps) {
+  static_assert(R <= TS_HALO, "halo too small");
+  constexpr int RING = 64;
+  extern __shared__ __align__(128) uint8_t tsm[];      // > 48 KB: dynamic shared memory (opt-in)
+  float (*stage)[TS_G][TS_BOXW] = reinterpret_cast<float (*)[TS_G][TS_BOXW]>(tsm);                        // [2]
+  float (*ring)[TS_W] = reinterpret_cast<float (*)[TS_W]>(tsm + 2 * TS_G * TS_BOXW * 4);                   // [RING]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(tsm + 2 * TS_G * TS_BOXW * 4 + RING * TS_W * 4);
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * TS_W;
+  const int ys = blockIdx.y * seg_rows, ye = min(ys + seg_rows, h);
+  const size_t img_off = (size_t)b * h * pitch;
+  const float* img = src + img_off;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const bool edge = (x0 - R < 0) || (x0 + TS_W + R > w);
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  const uint32_t stage0 = smem_u32(&stage[0][0][0]);
+  constexpr uint32_t STAGE_BYTES = TS_G * TS_BOXW * 4;
+  if (tid == 0) {
+    mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // group g = rows [ys + 16(g-1), ys + 16g); chunk c needs groups c .. c+2
+  const int n_chunks = (ye - ys + TS_G - 1) / TS_G;
+  const int n_groups = n_chunks + 2;
+  auto issue = [&](int g) {   // one thread
+    const uint32_t bar = bar0 + 8 * (g & 1);
+    mbar_expect_tx(bar, STAGE_BYTES);
+    tma_load_3d(stage0 + (g & 1) * STAGE_BYTES, &tm, bar, x0 - TS_HALO, ys + TS_G * (g - 1), z_base + b);
+  };
+  if (tid == 0) { issue(0); if (n_groups > 1) issue(1); }
+
+  auto row_pass_group = [&](int g) {
+    mbar_wait(bar0 + 8 * (g & 1), (uint32_t)((g >> 1) & 1));
+    float (*sg)[TS_BOXW] = stage[g & 1];
+    const int row0 = ys + TS_G * (g - 1);
+    if (edge) {   // block-uniform: patch the zero-filled out-of-image halo columns with reflect-101 values
+      for (int idx = tid; idx < TS_G * R; idx += 256) {
+        const int r = idx / R, k = idx - r * R;
+        if (x0 == 0) sg[r][TS_HALO - 1 - k] = sg[r][TS_HALO + 1 + k];          // x = -1-k  <-  x = 1+k
+        if (x0 + TS_W + R > w) {
+          const int cr = w + k - x0 + TS_HALO, sr = w - 2 - k - x0 + TS_HALO;  // x = w+k   <-  x = w-2-k
+          if (cr < TS_BOXW && sr >= 0) sg[r][cr] = sg[r][sr];
+        }
+      }
+      __syncthreads();
+    }
+    for (int rr = wrp; rr < TS_G; rr += 8) {
+      const int row = row0 + rr;
+      if (row < 0 || row >= h || row < ys - R) continue;        // warp-uniform
+      const float* p = &sg[rr][4 * lane];                       // box col 0 <-> x0 - 16
+      constexpr int Q0 = (TS_HALO - R) / 4, Q1 = (TS_HALO + 4 + R + 3) / 4;   // float4s that hold needed taps
+      float win[4 * (Q1 - Q0)];
+#pragma unroll
+      for (int q = Q0; q < Q1; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(p + 4 * q);
+        win[4 * (q - Q0)] = v.x; win[4 * (q - Q0) + 1] = v.y; win[4 * (q - Q0) + 2] = v.z; win[4 * (q - Q0) + 3] = v.w;
+      }
+      constexpr int C = TS_HALO - 4 * Q0;                        // index of output 0's centre tap in win
+      float acc[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] = taps.k[0] * win[C + o];
+#pragma unroll
+      for (int i = 1; i <= R; ++i) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o] = fmaf(taps.k[i], win[C + o - i] + win[C + o + i], acc[o]);
+      }
+      *reinterpret_cast<float4*>(&ring[row & (RING - 1)][4 * lane]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+  };
+
+  const int cp = tid & 63, rg = tid >> 6;
+  const int x = x0 + 2 * cp;
+  row_pass_group(0);
+  __syncthreads();
+  if (tid == 0 && 2 < n_groups) issue(2);
+  if (n_groups > 1) row_pass_group(1);
+  __syncthreads();
+  if (tid == 0 && 3 < n_groups) issue(3);
+  for (int c = 0; c < n_chunks; ++c) {
+    row_pass_group(c + 2);
+    __syncthreads();
+    if (tid == 0 && c + 4 < n_groups) issue(c + 4);
+    const int yf = ys + c * TS_G + rg * 4;
+    if (yf < ye && x < w) {
+      u64 win[4 + 2 * R];
+      const int s0 = (yf - R) & (RING - 1);
+      if (yf - R >= 0 && yf + 3 + R < h) {
+        if (s0 + 4 + 2 * R <= RING) {          // contiguous slots: one base address, immediate offsets
+          const float* base = &ring[s0][2 * cp];
+#pragma unroll
+          for (int q = 0; q < 4 + 2 * R; ++q) win[q] = *reinterpret_cast<const u64*>(base + q * TS_W);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4 + 2 * R; ++q) win[q] = *reinterpret_cast<const u64*>(&ring[(s0 + q) & (RING - 1)][2 * cp]);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4 + 2 * R; ++q) {
+          const int ry = reflect101(yf - R + q, h);
+          win[q] = *reinterpret_cast<const u64*>(&ring[ry & (RING - 1)][2 * cp]);
+        }
+      }
+      u64 acc[4];
+      const u64 k0 = f2_bcast(taps.k[0]);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] = f2_mul(k0, win[R + o]);
+#pragma unroll
+      for (int i = 1; i <= R; ++i) {
+        const u64 ki = f2_bcast(taps.k[i]);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o] = f2_fma(ki, f2_add(win[R + o - i], win[R + o + i]), acc[o]);
+      }
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int y = yf + o;
+        if (y < ye) {
+          const size_t g = (size_t)y * pitch + x;
+          const float2 cc = __ldg(reinterpret_cast<const float2*>(img + g));
+          const float2 v = *reinterpret_cast<const float2*>(&acc[o]);
+          *reinterpret_cast<float2*>(dst + img_off + g) = v;
+          *reinterpret_cast<float2*>(dog + img_off + g) = make_float2(v.x - cc.x, v.y - cc.y);
+        }
+      }
+    }
+  }
+}
 
 constexpr int ST_W = 128, ST_CH = 16;
 template <int R>
@@ -900,15 +1042,37 @@ static int launch_stream_t(const float* src, float* dst, float* dog, int h, int 
   return VO_OK;
 }
 
-static int launch_blur(const float* src, float* dst, float* dog, int h, int w, int pitch, int batch, const Taps& t,
-                       int num_sms, cudaStream_t st) {
+template <int R>
+static int launch_tma_t(const CUtensorMap& tm, int z_base, const float* src, float* dst, float* dog, int h, int w, int pitch,
+                        int batch, const Taps& t, int num_sms, cudaStream_t st) {
+  const int strips = div_up(w, TS_W);
+  int n_seg = 1;
+  const int target = num_sms * 6;
+  if (strips * batch < target) n_seg = div_up(target, strips * batch);
+  int seg_rows = div_up(div_up(h, n_seg), TS_G) * TS_G;
+  if (seg_rows < 4 * TS_G) seg_rows = 4 * TS_G;
+  n_seg = div_up(h, seg_rows);
+  dim3 grid(strips, n_seg, batch);
+  constexpr int smem = 2 * TS_G * TS_BOXW * 4 + 64 * TS_W * 4 + 64;
+  static bool attr = false;
+  if (!attr) {
+    VO_CUDA(cudaFuncSetAttribute(sift_blur_tma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  sift_blur_tma_kernel<R><<<grid, 256, smem, st>>>(tm, z_base, dst, dog, src, h, w, pitch, seg_rows, t);
+  return VO_OK;
+}
+
+// tm/z_base: tensor map of the octave's Gaussian stack and the z index of image 0 of the source layer
+static int launch_blur(const CUtensorMap& tm, int z_base, const float* src, float* dst, float* dog, int h, int w, int pitch,
+                       int batch, const Taps& t, int num_sms, cudaStream_t st) {
   if (h >= 64 && w >= 96) {
     switch (t.r) {
-      case 5: return launch_stream_t<5>(src, dst, dog, h, w, pitch, batch, t, num_sms, st);
-      case 6: return launch_stream_t<6>(src, dst, dog, h, w, pitch, batch, t, num_sms, st);
-      case 8: return launch_stream_t<8>(src, dst, dog, h, w, pitch, batch, t, num_sms, st);
-      case 10: return launch_stream_t<10>(src, dst, dog, h, w, pitch, batch, t, num_sms, st);
-      case 13: return launch_stream_t<13>(src, dst, dog, h, w, pitch, batch, t, num_sms, st);
+      case 5: return launch_tma_t<5>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
+      case 6: return launch_tma_t<6>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
+      case 8: return launch_tma_t<8>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
+      case 10: return launch_tma_t<10>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
+      case 13: return launch_tma_t<13>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
       default: break;
     }
   }
@@ -980,6 +1144,20 @@ static int get_plan(vo_ctx* ctx, int rows, int cols, int batch, const vo_sift_op
   A((void**)&p->final_kp, (size_t)batch * kp_cap * sizeof(vo_keypoint)); A((void**)&p->desc, (size_t)batch * kp_cap * 128 * sizeof(float));
   A((void**)&p->trig, (size_t)batch * kp_cap * sizeof(float2));
   if (e != cudaSuccess) { set_error("vo_sift: device allocation failed: %s", cudaGetErrorString(e)); sift_plan_destroy(p); return VO_ERR_CUDA; }
+  {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) { set_error("cuTensorMapEncodeTiled driver entry point not available"); sift_plan_destroy(p); return VO_ERR_CUDA; }
+    for (int oc = 0; oc < p->n_oct; ++oc) {
+      cuuint64_t gdim[3] = {(cuuint64_t)p->w[oc], (cuuint64_t)p->h[oc], (cuuint64_t)(nl + 3) * batch};
+      cuuint64_t gstr[2] = {(cuuint64_t)p->pitch[oc] * 4, (cuuint64_t)p->h[oc] * p->pitch[oc] * 4};
+      cuuint32_t box[3] = {(cuuint32_t)TS_BOXW, (cuuint32_t)TS_G, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = enc(&p->tm_gauss[oc], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)(p->gauss + p->goff[oc]), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("vo_sift: cuTensorMapEncodeTiled failed (%d) for octave %d", (int)r, oc); sift_plan_destroy(p); return VO_ERR_CUDA; }
+    }
+  }
   ctx->sift_plan = p; *out = p;
   return VO_OK;
 }
@@ -1006,7 +1184,7 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
     char nm[32]; snprintf(nm, sizeof(nm), oc == 0 ? "sift_blur_dog_oct0" : (oc == 1 ? "sift_blur_dog_oct1" : "sift_blur_dog_oct2+"));
     for (int i = 1; i < nl + 3; ++i) {
       ProfScope ps(ctx, st, nm, px * 12.0);   // read G[l], write G[l+1], write D[l]
-      VO_TRY(launch_blur(p->G(oc, i - 1), p->G(oc, i), p->D(oc, i - 1), p->h[oc], p->w[oc], p->pitch[oc], batch, p->taps[i], ctx->num_sms, st));
+      VO_TRY(launch_blur(p->tm_gauss[oc], (i - 1) * p->batch, p->G(oc, i - 1), p->G(oc, i), p->D(oc, i - 1), p->h[oc], p->w[oc], p->pitch[oc], batch, p->taps[i], ctx->num_sms, st));
     }
   }
   VO_CUDA(cudaGetLastError());
