@@ -109,6 +109,32 @@ struct Top3 {
   }
 };
 
+// Handles the (rare) "this chunk holds a new top-3 candidate" events of one thread.  g[q] is the max of
+// v[8q..8q+7], m the chunk max.  Each iteration takes the current chunk maximum (lowest column on
+// ties), inserts it, masks it out and re-reduces only its 8-group; ends when nothing beats thr.
+template <int Q>
+__device__ __forceinline__ void top3_take_from_group(float (&v)[32], float (&g)[4], float m, Top3& top, uint32_t j0) {
+  int e = 7;
+#pragma unroll
+  for (int c = 6; c >= 0; --c) e = (v[8 * Q + c] == m) ? c : e;
+  top.insert(m, j0 + 8 * Q + e);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[8 * Q + c] = (c == e) ? -INFINITY : v[8 * Q + c];
+  const float m01 = fmaxf(fmaxf(v[8 * Q], v[8 * Q + 1]), v[8 * Q + 2]);
+  const float m23 = fmaxf(fmaxf(v[8 * Q + 3], v[8 * Q + 4]), v[8 * Q + 5]);
+  g[Q] = fmaxf(fmaxf(m01, m23), fmaxf(v[8 * Q + 6], v[8 * Q + 7]));
+}
+__device__ __forceinline__ void top3_events(float (&v)[32], float (&g)[4], float m, float& thr, Top3& top, uint32_t j0) {
+  while (m > thr) {
+    if (g[0] == m) top3_take_from_group<0>(v, g, m, top, j0);
+    else if (g[1] == m) top3_take_from_group<1>(v, g, m, top, j0);
+    else if (g[2] == m) top3_take_from_group<2>(v, g, m, top, j0);
+    else top3_take_from_group<3>(v, g, m, top, j0);
+    thr = fmaxf(thr, top.k3);
+    m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+  }
+}
+
 // ------------------------------------------------------------------------- the GEMM kernel
 // grid (row panels, column splits, problems).  Counts are read from device memory, so the launch
 // shape depends only on capacities; CTAs outside the live problem exit (or publish empty slots).
@@ -119,6 +145,7 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const int* __restrict__ nonint_flag, int kp_blocks, int n_splits,
                   uint2* __restrict__ cand_base, size_t cand_stride, float* __restrict__ dbg_c, int dbg_ld) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B-swizzled operand tiles need 1024-byte alignment
+  if (*nonint_flag == 0) return;   // exact-integer inputs are handled by match_topk_fat_kernel
   const int prob = blockIdx.z;
   const int n1 = min(n1p[prob * n1_stride], cap1), n2 = min(n2p[prob * n2_stride], cap2);
   const int m0 = blockIdx.x * BM;
@@ -143,7 +170,7 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     return;
   }
-  const int kblocks = (*nonint_flag) ? 3 * kp_blocks : kp_blocks;
+  const int kblocks = 3 * kp_blocks;
 
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();
@@ -278,16 +305,7 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               g[q] = fmaxf(fmaxf(m01, m23), fmaxf(v[8 * q + 6], v[8 * q + 7]));
             }
             const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
-            if (m > thr) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (g[q] > thr) {
-#pragma unroll
-                  for (int c = 8 * q; c < 8 * q + 8; ++c)
-                    if (v[c] > thr) { top.insert(v[c], (uint32_t)(j0 + c)); thr = fmaxf(thr, top.k3); }
-                }
-              }
-            }
+            if (m > thr) top3_events(v, g, m, thr, top, (uint32_t)j0);
           } else {
 #pragma unroll
             for (int c = 0; c < 32; ++c)
@@ -303,6 +321,211 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     if (row < n1) {
       uint2* out = cand + ((size_t)row * n_slots + split * 4 + cq) * NCAND;
+      out[0] = make_uint2(__float_as_uint(top.k1), top.i1);
+      out[1] = make_uint2(__float_as_uint(top.k2), top.i2);
+      out[2] = make_uint2(__float_as_uint(top.k3), top.i3);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ------------------------------------------------------------ the GEMM kernel, exact-integer path
+// Same pipeline as match_topk_kernel, re-tiled for the case that matters (SIFT descriptors are
+// integers 0..255, K = 128): the CTA keeps TWO 128-row A panels resident (M = 256) and streams
+// 128-column B tiles, so every B byte fetched through L2 feeds twice as many MMAs (the thin kernel's
+// epilogue warps were waiting on the operand feed).  TMEM: 2 stages x (2 panels x 128 columns).
+// Epilogue thread = (panel, TMEM lane quarter, 64-column half).  Candidate slot = split*2 + half.
+constexpr int FBM = 256, FBN = 128;
+constexpr int FB_STAGE_BYTES = FBN * BK * 2;    // 16 KB
+constexpr int FB_STAGES = 8;
+constexpr int F_KBLOCKS = 2;                    // K = 128 only (dim <= 128)
+constexpr int FAT_SMEM_BYTES = 2 * F_KBLOCKS * A_KBLOCK_BYTES + FB_STAGES * FB_STAGE_BYTES + 256 + 2 * FBN * 4 + FBM * 4;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+match_topk_fat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const float* __restrict__ invb_base, int invb_stride, const int* __restrict__ n1p,
+                      int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
+                      const int* __restrict__ nonint_flag, int kp_blocks, int n_splits,
+                      uint2* __restrict__ cand_base, size_t cand_stride, int slots_per_row,
+                      float* __restrict__ dbg_c, int dbg_ld) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if (*nonint_flag != 0) return;   // general floats: match_topk_kernel (split-bf16) handles them
+  const int prob = blockIdx.z;
+  const int n1 = min(n1p[prob * n1_stride], cap1), n2 = min(n2p[prob * n2_stride], cap2);
+  const int m0 = blockIdx.x * FBM;
+  if (m0 >= n1) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_total = (n2 + FBN - 1) / FBN;
+  const int split = blockIdx.y;
+  const int t_begin = (int)((long long)split * tiles_total / n_splits);
+  const int t_end = (int)((long long)(split + 1) * tiles_total / n_splits);
+  uint2* cand = cand_base + (size_t)prob * cand_stride;
+  const float* invb = invb_base + (size_t)prob * invb_stride;
+  const int kblocks = kp_blocks;   // <= F_KBLOCKS
+
+  if (t_begin >= t_end) {
+    if (warp >= 2) {
+      const int e = warp - 2, quarter = warp & 3, panel = e >> 3, half = (e >> 2) & 1;
+      const int row = m0 + panel * 128 + quarter * 32 + lane;
+      if (row < n1) {
+        uint2* out = cand + ((size_t)row * slots_per_row + split * 2 + half) * NCAND;
+        for (int c = 0; c < NCAND; ++c) out[c] = make_uint2(__float_as_uint(-INFINITY), 0xFFFFFFFFu);
+      }
+    }
+    return;
+  }
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) __trap();
+  const uint32_t sA = base;                                        // [2 panels][F_KBLOCKS] x 16 KB
+  const uint32_t sB = sA + 2 * F_KBLOCKS * A_KBLOCK_BYTES;         // [FB_STAGES] x 16 KB
+  const uint32_t bars = sB + FB_STAGES * FB_STAGE_BYTES;
+  const uint32_t bar_a_full = bars;
+  const uint32_t bar_b_full = bars + 8;
+  const uint32_t bar_b_empty = bar_b_full + 8 * FB_STAGES;
+  const uint32_t bar_t_full = bar_b_empty + 8 * FB_STAGES;
+  const uint32_t bar_t_empty = bar_t_full + 16;
+  const uint32_t bar_i_full = bar_t_empty + 16;
+  const uint32_t tmem_slot = bar_i_full + 16;
+  const uint32_t s_invb_addr = bars + 256;                         // [2][FBN]
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - base));
+  float* s_invb = reinterpret_cast<float*>(smem_raw + (s_invb_addr - base));
+  float* s_thr = s_invb + 2 * FBN;                                 // [FBM]
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    mbar_init(bar_a_full, 1);
+    for (int s = 0; s < FB_STAGES; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, NUM_EPI_WARPS); mbar_init(bar_i_full + 8 * s, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + FBM) s_thr[threadIdx.x - 64] = -INFINITY;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      mbar_expect_tx(bar_a_full, 2 * kblocks * A_KBLOCK_BYTES);
+      for (int pn = 0; pn < 2; ++pn)
+        for (int kb = 0; kb < kblocks; ++kb)
+          tma_load_3d(sA + (pn * F_KBLOCKS + kb) * A_KBLOCK_BYTES, &tmA, bar_a_full, kb * BK, m0 + pn * 128, prob);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t)
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+          mbar_expect_tx(bar_b_full + 8 * stage, FB_STAGE_BYTES);
+          tma_load_3d(sB + stage * FB_STAGE_BYTES, &tmB, bar_b_full + 8 * stage, kb * BK, t * FBN, prob);
+          if (++stage == FB_STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer: D=f32, A=B=bf16, K-major, N=128, M=128 (two panels) =====
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      mbar_wait(bar_a_full, 0);
+      tc_fence_after();
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        mbar_expect_tx(bar_i_full + 8 * acc, FBN * 4);
+        bulk_load_1d(s_invb_addr + acc * FBN * 4, invb + (size_t)t * FBN, FBN * 4, bar_i_full + 8 * acc);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(bar_b_full + 8 * stage, phase);
+          tc_fence_after();
+#pragma unroll
+          for (int pn = 0; pn < 2; ++pn) {
+            const uint32_t d_tmem = tmem_base + acc * 256 + pn * FBN;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t ad = umma_desc_sw128(sA + (pn * F_KBLOCKS + kb) * A_KBLOCK_BYTES + k * UMMA_K * 2);
+              const uint64_t bd = umma_desc_sw128(sB + stage * FB_STAGE_BYTES + k * UMMA_K * 2);
+              tc_mma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            }
+          }
+          tc_commit(bar_b_empty + 8 * stage);
+          if (++stage == FB_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(bar_t_full + 8 * acc);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int e = warp - 2, quarter = warp & 3, panel = e >> 3, half = (e >> 2) & 1;
+    const int row_in_cta = panel * 128 + quarter * 32 + lane;
+    const int row = m0 + row_in_cta;
+    Top3 top; top.init();
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(bar_i_full + 8 * acc, acc_phase);
+      mbar_wait(bar_t_full + 8 * acc, acc_phase);
+      tc_fence_after();
+      float thr = fmaxf(top.k3, s_thr[row_in_cta]);
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + panel * FBN + half * 64);
+      uint32_t r0[32], r1[32];
+      tmem_ld32(tbase, r0);
+#pragma unroll
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        const int col_in_tile = half * 64 + chunk * 32;
+        const int j0 = t * FBN + col_in_tile;
+        uint32_t (&r)[32] = chunk == 0 ? r0 : r1;
+        tmem_ld_wait(r);
+        if (chunk == 0) tmem_ld32(tbase + 32, r1);
+        if (j0 < n2) {
+          if (dbg_c != nullptr && row < n1) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (j0 + c < n2) dbg_c[(size_t)row * dbg_ld + j0 + c] = __uint_as_float(r[c]);
+          }
+          float v[32];
+          const float4* ibp = reinterpret_cast<const float4*>(s_invb + acc * FBN + col_in_tile);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 i4 = ibp[q];
+            const unsigned long long a0 = ((unsigned long long)r[4 * q + 1] << 32) | r[4 * q];
+            const unsigned long long a1 = ((unsigned long long)r[4 * q + 3] << 32) | r[4 * q + 2];
+            const unsigned long long b0 = ((unsigned long long)__float_as_uint(i4.y) << 32) | __float_as_uint(i4.x);
+            const unsigned long long b1 = ((unsigned long long)__float_as_uint(i4.w) << 32) | __float_as_uint(i4.z);
+            const unsigned long long p0 = f2_mul(a0, b0), p1 = f2_mul(a1, b1);
+            v[4 * q] = __uint_as_float((uint32_t)p0); v[4 * q + 1] = __uint_as_float((uint32_t)(p0 >> 32));
+            v[4 * q + 2] = __uint_as_float((uint32_t)p1); v[4 * q + 3] = __uint_as_float((uint32_t)(p1 >> 32));
+          }
+          if (j0 + 32 <= n2) {
+            float g[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float m01 = fmaxf(fmaxf(v[8 * q], v[8 * q + 1]), v[8 * q + 2]);
+              const float m23 = fmaxf(fmaxf(v[8 * q + 3], v[8 * q + 4]), v[8 * q + 5]);
+              g[q] = fmaxf(fmaxf(m01, m23), fmaxf(v[8 * q + 6], v[8 * q + 7]));
+            }
+            const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+            if (m > thr) top3_events(v, g, m, thr, top, (uint32_t)j0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (j0 + c < n2 && v[c] > thr) { top.insert(v[c], (uint32_t)(j0 + c)); thr = fmaxf(thr, top.k3); }
+          }
+        }
+      }
+      tc_fence_before();
+      if (top.k3 > s_thr[row_in_cta]) s_thr[row_in_cta] = top.k3;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+    if (row < n1) {
+      uint2* out = cand + ((size_t)row * slots_per_row + split * 2 + half) * NCAND;
       out[0] = make_uint2(__float_as_uint(top.k1), top.i1);
       out[1] = make_uint2(__float_as_uint(top.k2), top.i2);
       out[2] = make_uint2(__float_as_uint(top.k3), top.i3);
@@ -421,8 +644,10 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
   if (n2 <= 0) { j1_out[orow] = 0xFFFFFFFFu; s1_out[orow] = INFINITY; s2_out[orow] = INFINITY; return; }
   float k[3] = {-INFINITY, -INFINITY, -INFINITY};
   uint32_t j[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  // row stride is n_slots (thin kernel: 4 slots per split); the fat kernel fills the first half only
   const uint2* c = cand_base + (size_t)prob * cand_stride + (size_t)i * n_slots * NCAND;
-  for (int s = 0; s < n_slots * NCAND; ++s) {
+  const int used = (*nonint_flag) ? n_slots * NCAND : (n_slots / 2) * NCAND;
+  for (int s = 0; s < used; ++s) {
     const uint2 e = c[s];
     if (e.y >= (uint32_t)n2) continue;
     const float key = __uint_as_float(e.x);
@@ -684,7 +909,7 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   auto nm = [&](const char* base) { return std::string(base) + "_" + tag; };
   const int kp = div_up(dim, BK) * BK;
   if (3 * kp > MAX_KBLOCKS * BK) { set_error("vo_match: dim %d > 128 is not supported by the tensor-core path", dim); return VO_ERR_ARG; }
-  const int a_alloc = div_up(A.cap > 0 ? A.cap : 1, BM) * BM;
+  const int a_alloc = div_up(A.cap > 0 ? A.cap : 1, FBM) * FBM;   // whole 256-row panels (fat kernel)
   const int b_tiles = div_up(B.cap > 0 ? B.cap : 1, BN);
   const int b_alloc = b_tiles * BN;   // multiple of 256, so the epilogue's 32-wide invb loads stay in bounds
 
@@ -720,7 +945,8 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   }
   VO_CUDA(cudaGetLastError());
 
-  const int m_blocks = a_alloc / BM;
+  // column splits: only when the row panels alone cannot cover the SMs (sized for the fat kernel)
+  const int m_blocks = a_alloc / FBM;
   int n_splits = 1;
   if (m_blocks * n_prob < ctx->num_sms) {
     n_splits = ctx->num_sms / (m_blocks * n_prob);
@@ -733,22 +959,27 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   int* scan_list; VO_TRY(dev_buf(ctx, nm("m_scanlist").c_str(), (size_t)n_prob * a_alloc, &scan_list));
 
   if (B.cap > 0) {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmB128;
     VO_TRY(make_operand_map(&tmA, opA, a_alloc, kp, n_prob, BM));
     VO_TRY(make_operand_map(&tmB, opB, b_alloc, kp, n_prob, BN));
+    VO_TRY(make_operand_map(&tmB128, opB, b_alloc, kp, n_prob, FBN));
     if (!g_attr_set) {
       VO_CUDA(cudaFuncSetAttribute(match_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      VO_CUDA(cudaFuncSetAttribute(match_topk_fat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FAT_SMEM_BYTES));
       g_attr_set = true;
     }
-    dim3 grid(m_blocks, n_splits, n_prob);
-    ProfScope ps(ctx, st, "match_gemm_topk", 0.0, exact_sizes ? 2.0 * A.cap * B.cap * dim : 0.0);
-    match_topk_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, invB, b_alloc, A.count, A.count_stride, A.cap, B.count,
-                                                             B.count_stride, B.cap, ctl, kp / BK, n_splits, cand, cand_stride,
-                                                             dbg_c, B.cap);
+    // both variants are launched; each reads the device-side "non-integer input" flag and one of them
+    // returns at once (no host synchronisation to pick the path)
+    ProfScope ps(ctx, st, "match_gemm_topk", 0.0, exact_sizes ? 2.0 * A.cap * B.cap * dim : 0.0, 2);
+    match_topk_kernel<<<dim3(a_alloc / BM, n_splits, n_prob), NUM_THREADS, SMEM_BYTES, st>>>(
+        tmA, tmB, invB, b_alloc, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap, ctl, kp / BK, n_splits, cand,
+        cand_stride, dbg_c, B.cap);
+    match_topk_fat_kernel<<<dim3(m_blocks, n_splits, n_prob), NUM_THREADS, FAT_SMEM_BYTES, st>>>(
+        tmA, tmB128, invB, b_alloc, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap, ctl, kp / BK, n_splits, cand,
+        cand_stride, n_slots, dbg_c, B.cap);
     VO_CUDA(cudaGetLastError());
     ctx->match_stats[2] = 1;
   }
-  ProfScope ps_fin(ctx, st, "match_finalize_rowscan", 0.0, 0.0, B.cap > 0 ? 2 : 1);
   match_finalize_kernel<<<dim3(div_up(A.cap, 128), n_prob), 128, 0, st>>>(
       cand, cand_stride, n_slots, ra, rb, dim, invA, a_alloc, invB, b_alloc, A.count, A.count_stride, A.cap, B.count,
       B.count_stride, B.cap, ctl, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
