@@ -52,6 +52,18 @@ int vo_ctx::prof_stage_id(const char* name) {
 }
 
 void vo_ctx::prof_collect() {
+  if (prof_late_stage >= 0 && prof_late_stage < (int)prof_stages.size()) {
+    auto it = scratch.find("prof_desc_bytes");
+    if (it != scratch.end() && it->second.ptr) {
+      unsigned long long h[64];
+      cudaStreamSynchronize(stream);
+      if (cudaMemcpy(h, it->second.ptr, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+        double tot = 0;
+        for (int i = 0; i < 64; ++i) tot += (double)h[i];
+        prof_stages[prof_late_stage].bytes = tot;
+      }
+    }
+  }
   for (auto& r : prof_pending) {
     float ms = 0.f;
     if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess)
@@ -162,6 +174,11 @@ int vo_profile_enable(vo_ctx* c, int on) {
   c->prof_collect();
   c->prof_enabled = on != 0;
   c->prof_stages.clear();
+  c->prof_late_stage = -1;
+  {
+    void* p = nullptr;
+    if (c->dev("prof_desc_bytes", 64 * sizeof(unsigned long long), &p) == VO_OK) cudaMemsetAsync(p, 0, 64 * sizeof(unsigned long long), c->stream);
+  }
   return VO_OK;
 }
 

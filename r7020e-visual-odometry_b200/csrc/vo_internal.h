@@ -50,6 +50,7 @@ struct Scratch {
 struct ProfRec { int stage; cudaEvent_t e0, e1; };
 struct ProfStage { std::string name; double ms = 0; long long launches = 0; double bytes = 0; double flops = 0; };
 
+
 struct SiftPlan;   // vo_sift.cu
 struct FramePlan;  // vo_frames.cu
 
@@ -66,6 +67,7 @@ struct vo_ctx {
   std::vector<vo::ProfStage> prof_stages;
   std::vector<vo::ProfRec> prof_pending;
   std::vector<cudaEvent_t> prof_pool;
+  int prof_late_stage = -1;   // stage whose bytes are accumulated on the device (scratch "prof_desc_bytes")
   int prof_stage_id(const char* name);
   void prof_collect();
   vo::SiftPlan* sift_plan = nullptr;

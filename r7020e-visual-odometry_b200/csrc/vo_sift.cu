@@ -849,7 +849,8 @@ constexpr int DESC_COPIES = 4;
 __global__ void __launch_bounds__(128)
 sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int batch, int nl,
                        const vo_keypoint* __restrict__ kps, const float2* __restrict__ trig, int kp_cap,
-                       const int* __restrict__ counters, float loc_offset, float* __restrict__ desc) {
+                       const int* __restrict__ counters, float loc_offset, float* __restrict__ desc,
+                       unsigned long long* __restrict__ algo_bytes) {
   constexpr int D = 4, N = 8, HLEN = (D + 2) * (D + 2) * (N + 2);
   __shared__ uint32_t s_hist[4][DESC_COPIES * HLEN];
   __shared__ uint32_t s_queue[4][64];
@@ -859,6 +860,7 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
   const int n = min(counters[b * 4 + 2], kp_cap);
   uint32_t* hist = s_hist[wib] + (lane & (DESC_COPIES - 1)) * HLEN;
   uint32_t* queue = s_queue[wib];
+  unsigned long long my_bytes = 0;
   for (int ki = blockIdx.x * 4 + wib; ki < n; ki += gridDim.x * 4) {
     const vo_keypoint kp = kps[(size_t)b * kp_cap + ki];
     int oc = kp.octave & 255; const int layer = (kp.octave >> 8) & 255;
@@ -919,6 +921,7 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
     };
 
     const int side = 2 * radius + 1, total = side * side;
+    my_bytes += (unsigned long long)total * 4ull + 512ull;   // patch read + descriptor written
     int i = lane / side - radius, j = lane % side - radius;     // this lane's sample of the first group
     int qn = 0;                                                 // queue fill (warp-uniform)
     for (int base = 0; base < total; base += 32) {
@@ -987,6 +990,7 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
     reinterpret_cast<float4*>(desc + ((size_t)b * kp_cap + ki) * 128)[lane] = o4;
     __syncwarp();
   }
+  if (algo_bytes != nullptr && lane == 0 && my_bytes) atomicAdd(algo_bytes + ((blockIdx.x * 4 + wib) & 63), my_bytes);
 }
 
 // --------------------------------------------------------------------------- host plumbing
@@ -1181,7 +1185,8 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
       dim3 g(div_up(p->w[oc], 256), p->h[oc], batch);
       sift_downsample_kernel<<<g, 256, 0, st>>>(p->G(oc - 1, nl), p->G(oc, 0), p->h[oc - 1], p->pitch[oc - 1], p->h[oc], p->w[oc], p->pitch[oc]);
     }
-    char nm[32]; snprintf(nm, sizeof(nm), oc == 0 ? "sift_blur_dog_oct0" : (oc == 1 ? "sift_blur_dog_oct1" : "sift_blur_dog_oct2+"));
+    const bool tma = p->h[oc] >= 64 && p->w[oc] >= 96;   // same test as launch_blur
+    const char* nm = tma ? (oc == 0 ? "sift_blur_dog_tma_oct0" : "sift_blur_dog_tma_oct1+") : "sift_blur_dog_small";
     for (int i = 1; i < nl + 3; ++i) {
       ProfScope ps(ctx, st, nm, px * 12.0);   // read G[l], write G[l+1], write D[l]
       VO_TRY(launch_blur(p->tm_gauss[oc], (i - 1) * p->batch, p->G(oc, i - 1), p->G(oc, i), p->D(oc, i - 1), p->h[oc], p->w[oc], p->pitch[oc], batch, p->taps[i], ctx->num_sms, st));
@@ -1221,9 +1226,16 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
   }
   {
     dim3 g(ctx->num_sms * 4 / (batch > 4 ? 4 : 1), batch);
+    // when profiling, the kernel also accumulates its data-dependent algorithmic bytes (SURVEY 8d:
+    // (2r+1)^2*4 + 512 per keypoint) into 64 spread counters owned by the context
+    unsigned long long* ab = nullptr;
+    if (ctx->prof_enabled) {
+      VO_TRY(dev_buf(ctx, "prof_desc_bytes", 64, &ab));
+      ctx->prof_late_stage = ctx->prof_stage_id("sift_descriptor");
+    }
     ProfScope ps(ctx, st, "sift_descriptor", 0.0, 0.0, 2);
     sift_trig_kernel<<<dim3(8, batch), 256, 0, st>>>(p->final_kp, p->kp_cap, p->counters, p->trig);
-    sift_descriptor_kernel<<<g, 128, 0, st>>>(p->gauss, oi, p->batch, nl, p->final_kp, p->trig, p->kp_cap, p->counters, (float)o.index_base, p->desc);
+    sift_descriptor_kernel<<<g, 128, 0, st>>>(p->gauss, oi, p->batch, nl, p->final_kp, p->trig, p->kp_cap, p->counters, (float)o.index_base, p->desc, ab);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
