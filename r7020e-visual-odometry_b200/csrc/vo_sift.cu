@@ -845,7 +845,8 @@ sift_trig_kernel(const vo_keypoint* __restrict__ kps, int kp_cap, const int* __r
 // full warp.  The scatter uses integer shared-memory atomics into 4 privatised copies of the
 // 6x6x10 histogram (copy = lane & 3) to cut same-address serialisation; integer sums make the
 // result independent of the order and of the copy assignment.
-constexpr int DESC_COPIES = 4;
+constexpr int DESC_COPIES = 2;
+constexpr int DESC_MAX_ROWS = 160;   // window rows handled by the interval scan (radius <= 79)
 __global__ void __launch_bounds__(128)
 sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int batch, int nl,
                        const vo_keypoint* __restrict__ kps, const float2* __restrict__ trig, int kp_cap,
@@ -853,13 +854,13 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
                        unsigned long long* __restrict__ algo_bytes) {
   constexpr int D = 4, N = 8, HLEN = (D + 2) * (D + 2) * (N + 2);
   __shared__ uint32_t s_hist[4][DESC_COPIES * HLEN];
-  __shared__ uint32_t s_queue[4][64];
+  __shared__ int s_rowoff[4][DESC_MAX_ROWS + 1];
+  __shared__ short s_rowj[4][DESC_MAX_ROWS];
   __shared__ float s_vec[4][128];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int n = min(counters[b * 4 + 2], kp_cap);
   uint32_t* hist = s_hist[wib] + (lane & (DESC_COPIES - 1)) * HLEN;
-  uint32_t* queue = s_queue[wib];
   unsigned long long my_bytes = 0;
   for (int ki = blockIdx.x * 4 + wib; ki < n; ki += gridDim.x * 4) {
     const vo_keypoint kp = kps[(size_t)b * kp_cap + ki];
@@ -890,6 +891,8 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
       const float r_rot = j * sin_t + i * cos_t;
       float rbin = r_rot + D / 2 - 0.5f, cbin = c_rot + D / 2 - 0.5f;
       const int r = py + i, c = px + j;
+      // the exact acceptance test of the contract (the row intervals below are only a superset)
+      if (!(rbin > -1 && rbin < D && cbin > -1 && cbin < D && r > 0 && r < rows - 1 && c > 0 && c < cols - 1)) return;
       const float* q = img + (size_t)r * pitch + c;
       const float dx = q[1] - q[-1];
       const float dy = q[-pitch] - q[pitch];
@@ -922,37 +925,57 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
 
     const int side = 2 * radius + 1, total = side * side;
     my_bytes += (unsigned long long)total * 4ull + 512ull;   // patch read + descriptor written
-    int i = lane / side - radius, j = lane % side - radius;     // this lane's sample of the first group
-    int qn = 0;                                                 // queue fill (warp-uniform)
-    for (int base = 0; base < total; base += 32) {
-      bool acc = false;
-      if (base + lane < total) {
-        const float c_rot = j * cos_t - i * sin_t;
-        const float r_rot = j * sin_t + i * cos_t;
-        const float rbin = r_rot + D / 2 - 0.5f, cbin = c_rot + D / 2 - 0.5f;
-        const int r = py + i, c = px + j;
-        acc = rbin > -1 && rbin < D && cbin > -1 && cbin < D && r > 0 && r < rows - 1 && c > 0 && c < cols - 1;
+    if (side <= DESC_MAX_ROWS) {
+      // Per window row i the accepted samples lie in one j-interval: |j*cos_t - i*sin_t| < 2.5 and
+      // |j*sin_t + i*cos_t| < 2.5 (bin units), clipped to the window and the image.  Lanes compute a
+      // conservative integer superset per row (floor/ceil of the real bounds), a warp scan turns the
+      // row counts into offsets, then the warp sweeps the packed candidate list 32 at a time.
+      int carry = 0;
+      for (int rb = 0; rb < side; rb += 32) {
+        const int ri = rb + lane;
+        int jlo = 0, cntr = 0;
+        if (ri < side) {
+          const int i = ri - radius;
+          float lo = (float)-radius, hi = (float)radius;
+          const float ic = i * cos_t, is = i * sin_t;
+          if (fabsf(cos_t) > 1e-6f) {       // |j*cos_t - is| < 2.5
+            const float a0 = __fdividef(is - 2.5f, cos_t), a1 = __fdividef(is + 2.5f, cos_t);
+            lo = fmaxf(lo, fminf(a0, a1)); hi = fminf(hi, fmaxf(a0, a1));
+          } else if (!(fabsf(is) < 2.6f)) hi = lo - 1.f;
+          if (fabsf(sin_t) > 1e-6f) {       // |j*sin_t + ic| < 2.5
+            const float b0 = __fdividef(-ic - 2.5f, sin_t), b1 = __fdividef(-ic + 2.5f, sin_t);
+            lo = fmaxf(lo, fminf(b0, b1)); hi = fminf(hi, fmaxf(b0, b1));
+          } else if (!(fabsf(ic) < 2.6f)) hi = lo - 1.f;
+          int l = (int)floorf(lo), h2 = (int)ceilf(hi);
+          l = max(l, max(-radius, 1 - px)); h2 = min(h2, min(radius, cols - 2 - px));
+          const int r = py + i;
+          if (r > 0 && r < rows - 1 && h2 >= l) { jlo = l; cntr = h2 - l + 1; }
+        }
+        int incl = cntr;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += y;
+        }
+        if (ri < side) { s_rowoff[wib][ri + 1] = carry + incl; s_rowj[wib][ri] = (short)jlo; }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
       }
-      const unsigned mask = __ballot_sync(0xffffffffu, acc);
-      if (acc) queue[qn + __popc(mask & ((1u << lane) - 1u))] = ((uint32_t)(i + 32768) << 16) | (uint32_t)(j + 32768);
-      qn += __popc(mask);
-      j += 32;
-      while (j > radius) { j -= side; ++i; }
-      if (qn >= 32) {
-        __syncwarp();
-        const uint32_t e = queue[lane];
-        const uint32_t rest = queue[32 + lane];
-        process((int)(e >> 16) - 32768, (int)(e & 0xFFFF) - 32768);
-        __syncwarp();
-        qn -= 32;
-        if (lane < qn) queue[lane] = rest;
-        __syncwarp();
+      if (lane == 0) s_rowoff[wib][0] = 0;
+      __syncwarp();
+      const int ncand = carry;
+      int row = 0;
+      for (int k = lane; k < ncand; k += 32) {
+        while (k >= s_rowoff[wib][row + 1]) ++row;
+        process(row - radius, (int)s_rowj[wib][row] + (k - s_rowoff[wib][row]));
       }
-    }
-    __syncwarp();
-    if (lane < qn) {
-      const uint32_t e = queue[lane];
-      process((int)(e >> 16) - 32768, (int)(e & 0xFFFF) - 32768);
+    } else {
+      // very large windows (non-default options): plain scan of the whole window
+      int i = lane / side - radius, j = lane % side - radius;
+      for (int base = 0; base < total; base += 32) {
+        if (base + lane < total) process(i, j);
+        j += 32;
+        while (j > radius) { j -= side; ++i; }
+      }
     }
     __syncwarp();
     // fold the copies and the circular orientation bins, flatten to 128 floats
