@@ -97,10 +97,11 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
     MatchOperand o = raw_op(first_img); o.gather = g; o.gather_stride = kc; o.count = c; o.count_stride = 1; return o;
   };
   MatchTop2 t;
+  const MatchFilter mflt = make_match_filter(mo);
   // matched = matchFeatures(l_desc, r_desc)                                      VO.m:87
   {
     MatchOperand A = raw_op(0), B = raw_op(1);
-    VO_TRY(match_batch_top2(ctx, A, B, n, 128, "fr", nullptr, st, &t));
+    VO_TRY(match_batch_top2(ctx, A, B, n, 128, "fr", nullptr, st, &t, &mflt));
     VO_TRY(match_batch_select(ctx, t, A, B, n, mo, l0, r0, nullptr, kc, K, 1, st));
   }
   const int np = n - 1;
@@ -109,7 +110,7 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
     // M1 = matchFeatures(cur.l_desc, old.l_desc)                                 VO.m:283
     {
       MatchOperand A = raw_op(2), B = gath_op(0, l0, K);
-      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t));
+      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t, &mflt));
       VO_TRY(match_batch_select(ctx, t, A, B, np, mo, a1, b1, nullptr, kc, K + n, 1, st));
       compose_kernel<<<cg, 256, 0, st>>>(oL1, l0, oR1, r0, b1, K + n, kc);            // VO.m:287-290
       ctx->kernel_launches += 6;   // 5 compose launches + gather_points below
@@ -117,14 +118,14 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
     // M2 = matchFeatures(cur.r_desc, old.r_desc)                                 VO.m:293
     {
       MatchOperand A = raw_op(3), B = gath_op(1, oR1, K + n);
-      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t));
+      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t, &mflt));
       VO_TRY(match_batch_select(ctx, t, A, B, np, mo, a2, b2, nullptr, kc, K + 2 * n, 1, st));
       compose_kernel<<<cg, 256, 0, st>>>(oL2, oL1, oR2, oR1, b2, K + 2 * n, kc);      // VO.m:297-300
     }
     // M3 = matchFeatures(cur.l_desc(M1(:,1)), cur.r_desc(M2(:,1)))               VO.m:305-311
     {
       MatchOperand A = gath_op(2, a1, K + n), B = gath_op(3, a2, K + 2 * n);
-      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t));
+      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t, &mflt));
       VO_TRY(match_batch_select(ctx, t, A, B, np, mo, a3, b3, nullptr, kc, K + 3 * n, 1, st));
       compose_kernel<<<cg, 256, 0, st>>>(cL3, a1, nullptr, nullptr, a3, K + 3 * n, kc);  // VO.m:314-315
       compose_kernel<<<cg, 256, 0, st>>>(cR3, a2, nullptr, nullptr, b3, K + 3 * n, kc);  // VO.m:316-317
@@ -132,7 +133,7 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
     // M4 = matchFeatures(cur.l_desc, old.l_desc)                                 VO.m:323
     {
       MatchOperand A = gath_op(2, cL3, K + 3 * n), B = gath_op(0, oL2, K + 2 * n);
-      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t));
+      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t, &mflt));
       VO_TRY(match_batch_select(ctx, t, A, B, np, mo, a4, b4, nullptr, kc, K + 4 * n, 1, st));
     }
   }

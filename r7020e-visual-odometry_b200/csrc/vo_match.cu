@@ -335,38 +335,57 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ------------------------------------------------------------ the GEMM kernel, exact-integer path
-// Same pipeline as match_topk_kernel, re-tiled for the case that matters (SIFT descriptors are
-// integers 0..255, K = 128): the CTA keeps TWO 128-row A panels resident (M = 256) and streams
-// 128-column B tiles, so every B byte fetched through L2 feeds twice as many MMAs (the thin kernel's
-// epilogue warps were waiting on the operand feed).  TMEM: 2 stages x (2 panels x 128 columns).
-// Epilogue thread = (panel, TMEM lane quarter, 64-column half).  Candidate slot = split*2 + half.
-constexpr int FBM = 256, FBN = 128;
-constexpr int FB_STAGE_BYTES = FBN * BK * 2;    // 16 KB
-constexpr int FB_STAGES = 8;
-constexpr int F_KBLOCKS = 2;                    // K = 128 only (dim <= 128)
-constexpr int FAT_SMEM_BYTES = 2 * F_KBLOCKS * A_KBLOCK_BYTES + FB_STAGES * FB_STAGE_BYTES + 256 + 2 * FBN * 4 + FBM * 4;
+// SIFT descriptors are integers 0..255 and K = 128, so the operands are stored as u8 and contracted by
+// tcgen05.mma.kind::i8 (u8 x u8 -> s32, K = 32 per instruction): half the shared-memory operand bytes
+// per MMA of the bf16 form and twice the MACs per issue slot, and the s32 accumulator IS the oracle's
+// dot product (sum < 2^23).  The CTA keeps TWO 128-row A panels resident (M = 256) and streams
+// 128-column B tiles (16 KB, one 128B-swizzled K block) through an 8-stage ring.
+// TMEM: 2 accumulator stages x (2 panels x 128 columns).
+//
+// Epilogue thread = (panel, TMEM lane quarter, 64-column half); candidate slot = split*2 + half.
+// The epilogue never forms key = dot * 1/||b_j|| on the fast path.  A row only needs columns whose
+// key can beat its current bound thr (third-best key so far, or the caller's score bound, below), and
+//     dot <= thr_raw = floor(thr / max_j 1/||b_j||) - 2   implies   fl(dot * 1/||b_j||) <= thr,
+// so a chunk of 32 accumulators costs one integer max tree (16 VIMNMX3) and one compare.  Only chunks
+// that pass go through the exact path (convert, scale by 1/||b_j||, strict '>' insert into the top-3).
+//
+// Score bound ("thresholded" mode, used by matchFeatures): a row is only kept when s1 <= T and
+// s1/s2 <= R, so columns with score above T/R can never change the row's outcome.  thr starts at the
+// key of that score (key_floor / inva_i) instead of -inf; match_finalize_kernel proves, per row, that
+// the decision and (j1, s1) are exactly the oracle's, or sends the row to the exact scan.
+constexpr int UBM = 256, UBN = 128;
+constexpr int U_TILE_BYTES = 128 * 128;         // 128 rows x 128 u8
+constexpr int U_STAGES = 8;
+constexpr int U_SMEM_BYTES = 2 * U_TILE_BYTES + U_STAGES * U_TILE_BYTES + 256 + UBM * 4;
+
+__device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }
+__device__ __forceinline__ int raw_bound(float thr, float bnorm) {
+  // largest integer dot that provably cannot reach a key above thr (bnorm = 1 / max_j invb_j, 0 if none)
+  if (!(thr > 0.f) || !(bnorm > 0.f)) return -1;
+  const float q = fminf(__fmul_rn(thr, bnorm), 1.0e9f);
+  return __float2int_rd(q) - 2;
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-match_topk_fat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const float* __restrict__ invb_base, int invb_stride, const int* __restrict__ n1p,
-                      int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
-                      const int* __restrict__ nonint_flag, int kp_blocks, int n_splits,
-                      uint2* __restrict__ cand_base, size_t cand_stride, int slots_per_row,
-                      float* __restrict__ dbg_c, int dbg_ld) {
+match_topk_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const float* __restrict__ invb_base, int invb_stride, const float* __restrict__ inva_base,
+                     int inva_stride, const int* __restrict__ invb_max_bits, const int* __restrict__ n1p,
+                     int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
+                     const int* __restrict__ nonint_flag, int n_splits, uint2* __restrict__ cand_base,
+                     size_t cand_stride, int slots_per_row, float key_floor, float* __restrict__ dbg_c, int dbg_ld) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if (*nonint_flag != 0) return;   // general floats: match_topk_kernel (split-bf16) handles them
   const int prob = blockIdx.z;
   const int n1 = min(n1p[prob * n1_stride], cap1), n2 = min(n2p[prob * n2_stride], cap2);
-  const int m0 = blockIdx.x * FBM;
+  const int m0 = blockIdx.x * UBM;
   if (m0 >= n1) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_total = (n2 + FBN - 1) / FBN;
+  const int tiles_total = (n2 + UBN - 1) / UBN;
   const int split = blockIdx.y;
   const int t_begin = (int)((long long)split * tiles_total / n_splits);
   const int t_end = (int)((long long)(split + 1) * tiles_total / n_splits);
   uint2* cand = cand_base + (size_t)prob * cand_stride;
   const float* invb = invb_base + (size_t)prob * invb_stride;
-  const int kblocks = kp_blocks;   // <= F_KBLOCKS
 
   if (t_begin >= t_end) {
     if (warp >= 2) {
@@ -381,30 +400,36 @@ match_topk_fat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();
-  const uint32_t sA = base;                                        // [2 panels][F_KBLOCKS] x 16 KB
-  const uint32_t sB = sA + 2 * F_KBLOCKS * A_KBLOCK_BYTES;         // [FB_STAGES] x 16 KB
-  const uint32_t bars = sB + FB_STAGES * FB_STAGE_BYTES;
+  const uint32_t sA = base;                              // [2 panels] x 16 KB
+  const uint32_t sB = sA + 2 * U_TILE_BYTES;             // [U_STAGES] x 16 KB
+  const uint32_t bars = sB + U_STAGES * U_TILE_BYTES;
   const uint32_t bar_a_full = bars;
   const uint32_t bar_b_full = bars + 8;
-  const uint32_t bar_b_empty = bar_b_full + 8 * FB_STAGES;
-  const uint32_t bar_t_full = bar_b_empty + 8 * FB_STAGES;
+  const uint32_t bar_b_empty = bar_b_full + 8 * U_STAGES;
+  const uint32_t bar_t_full = bar_b_empty + 8 * U_STAGES;
   const uint32_t bar_t_empty = bar_t_full + 16;
-  const uint32_t bar_i_full = bar_t_empty + 16;
-  const uint32_t tmem_slot = bar_i_full + 16;
-  const uint32_t s_invb_addr = bars + 256;                         // [2][FBN]
+  const uint32_t tmem_slot = bar_t_empty + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - base));
-  float* s_invb = reinterpret_cast<float*>(smem_raw + (s_invb_addr - base));
-  float* s_thr = s_invb + 2 * FBN;                                 // [FBM]
+  float* s_thr = reinterpret_cast<float*>(smem_raw + (bars + 256 - base));   // [UBM]
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     mbar_init(bar_a_full, 1);
-    for (int s = 0; s < FB_STAGES; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, NUM_EPI_WARPS); mbar_init(bar_i_full + 8 * s, 1); }
+    for (int s = 0; s < U_STAGES; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + FBM) s_thr[threadIdx.x - 64] = -INFINITY;
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + UBM) {
+    // initial per-row key bound: the caller's score bound in key units, or -inf
+    const int r = threadIdx.x - 64;
+    float t0 = -INFINITY;
+    if (key_floor > 0.f && m0 + r < n1) {
+      const float ia = inva_base[(size_t)prob * inva_stride + m0 + r];
+      if (ia > 0.f) t0 = __fdiv_rn(key_floor, ia);
+    }
+    s_thr[r] = t0;
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -416,47 +441,43 @@ match_topk_fat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
-      mbar_expect_tx(bar_a_full, 2 * kblocks * A_KBLOCK_BYTES);
-      for (int pn = 0; pn < 2; ++pn)
-        for (int kb = 0; kb < kblocks; ++kb)
-          tma_load_3d(sA + (pn * F_KBLOCKS + kb) * A_KBLOCK_BYTES, &tmA, bar_a_full, kb * BK, m0 + pn * 128, prob);
+      mbar_expect_tx(bar_a_full, 2 * U_TILE_BYTES);
+      for (int pn = 0; pn < 2; ++pn) tma_load_3d(sA + pn * U_TILE_BYTES, &tmA, bar_a_full, 0, m0 + pn * 128, prob);
       int stage = 0; uint32_t phase = 0;
-      for (int t = t_begin; t < t_end; ++t)
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
-          mbar_expect_tx(bar_b_full + 8 * stage, FB_STAGE_BYTES);
-          tma_load_3d(sB + stage * FB_STAGE_BYTES, &tmB, bar_b_full + 8 * stage, kb * BK, t * FBN, prob);
-          if (++stage == FB_STAGES) { stage = 0; phase ^= 1; }
-        }
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+        mbar_expect_tx(bar_b_full + 8 * stage, U_TILE_BYTES);
+        tma_load_3d(sB + stage * U_TILE_BYTES, &tmB, bar_b_full + 8 * stage, 0, t * UBN, prob);
+        if (++stage == U_STAGES) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer: D=f32, A=B=bf16, K-major, N=128, M=128 (two panels) =====
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (lane == 0) {  // ===== MMA issuer: D=s32, A=B=u8, K-major, N=128, M=128 (two panels), K=32 per MMA =====
+      const uint32_t idesc = (2u << 4) | ((uint32_t)(UBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(bar_a_full, 0);
       tc_fence_after();
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);
+        mbar_wait(bar_b_full + 8 * stage, phase);
         tc_fence_after();
-        mbar_expect_tx(bar_i_full + 8 * acc, FBN * 4);
-        bulk_load_1d(s_invb_addr + acc * FBN * 4, invb + (size_t)t * FBN, FBN * 4, bar_i_full + 8 * acc);
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(bar_b_full + 8 * stage, phase);
-          tc_fence_after();
 #pragma unroll
-          for (int pn = 0; pn < 2; ++pn) {
-            const uint32_t d_tmem = tmem_base + acc * 256 + pn * FBN;
+        for (int pn = 0; pn < 2; ++pn) {
+          const uint32_t d_tmem = tmem_base + acc * 256 + pn * UBN;
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t ad = umma_desc_sw128(sA + (pn * F_KBLOCKS + kb) * A_KBLOCK_BYTES + k * UMMA_K * 2);
-              const uint64_t bd = umma_desc_sw128(sB + stage * FB_STAGE_BYTES + k * UMMA_K * 2);
-              tc_mma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
-            }
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = umma_desc_sw128(sA + pn * U_TILE_BYTES + k * 32);
+            const uint64_t bd = umma_desc_sw128(sB + stage * U_TILE_BYTES + k * 32);
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                ::"r"(d_tmem), "l"(ad), "l"(bd), "r"(idesc), "r"((uint32_t)(k != 0))
+                : "memory");
           }
-          tc_commit(bar_b_empty + 8 * stage);
-          if (++stage == FB_STAGES) { stage = 0; phase ^= 1; }
         }
+        tc_commit(bar_b_empty + 8 * stage);
         tc_commit(bar_t_full + 8 * acc);
+        if (++stage == U_STAGES) { stage = 0; phase ^= 1; }
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
     }
@@ -465,63 +486,68 @@ match_topk_fat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int e = warp - 2, quarter = warp & 3, panel = e >> 3, half = (e >> 2) & 1;
     const int row_in_cta = panel * 128 + quarter * 32 + lane;
     const int row = m0 + row_in_cta;
+    const float bmax = __int_as_float(invb_max_bits[prob]);
+    const float bnorm = bmax > 0.f ? __fdiv_rn(1.0f, bmax) : 0.f;
     Top3 top; top.init();
+    float thr = s_thr[row_in_cta];
+    int thr_raw = raw_bound(thr, bnorm);
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = t_begin; t < t_end; ++t) {
-      mbar_wait(bar_i_full + 8 * acc, acc_phase);
       mbar_wait(bar_t_full + 8 * acc, acc_phase);
       tc_fence_after();
-      float thr = fmaxf(top.k3, s_thr[row_in_cta]);
-      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + panel * FBN + half * 64);
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + panel * UBN + half * 64);
       uint32_t r0[32], r1[32];
       tmem_ld32(tbase, r0);
+      tmem_ld32(tbase + 32, r1);
+      const float shared_thr = s_thr[row_in_cta];
+      if (shared_thr > thr) { thr = shared_thr; thr_raw = raw_bound(thr, bnorm); }
+      tmem_ld_wait(r0);
+      tmem_ld_wait(r1);
+      // the accumulators are in registers: hand the TMEM stage back to the MMA warp at once
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
 #pragma unroll
       for (int chunk = 0; chunk < 2; ++chunk) {
-        const int col_in_tile = half * 64 + chunk * 32;
-        const int j0 = t * FBN + col_in_tile;
         uint32_t (&r)[32] = chunk == 0 ? r0 : r1;
-        tmem_ld_wait(r);
-        if (chunk == 0) tmem_ld32(tbase + 32, r1);
-        if (j0 < n2) {
-          if (dbg_c != nullptr && row < n1) {
+        const int j0 = t * UBN + half * 64 + chunk * 32;
+        if (dbg_c != nullptr && row < n1) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (j0 + c < n2) dbg_c[(size_t)row * dbg_ld + j0 + c] = __uint_as_float(r[c]);
-          }
-          float v[32];
-          const float4* ibp = reinterpret_cast<const float4*>(s_invb + acc * FBN + col_in_tile);
+          for (int c = 0; c < 32; ++c)
+            if (j0 + c < n2) dbg_c[(size_t)row * dbg_ld + j0 + c] = (float)(int)r[c];
+        }
+        int l1[12];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 i4 = ibp[q];
-            const unsigned long long a0 = ((unsigned long long)r[4 * q + 1] << 32) | r[4 * q];
-            const unsigned long long a1 = ((unsigned long long)r[4 * q + 3] << 32) | r[4 * q + 2];
-            const unsigned long long b0 = ((unsigned long long)__float_as_uint(i4.y) << 32) | __float_as_uint(i4.x);
-            const unsigned long long b1 = ((unsigned long long)__float_as_uint(i4.w) << 32) | __float_as_uint(i4.z);
-            const unsigned long long p0 = f2_mul(a0, b0), p1 = f2_mul(a1, b1);
-            v[4 * q] = __uint_as_float((uint32_t)p0); v[4 * q + 1] = __uint_as_float((uint32_t)(p0 >> 32));
-            v[4 * q + 2] = __uint_as_float((uint32_t)p1); v[4 * q + 3] = __uint_as_float((uint32_t)(p1 >> 32));
-          }
-          if (j0 + 32 <= n2) {
-            float g[4];
+        for (int q = 0; q < 10; ++q) l1[q] = imax3((int)r[3 * q], (int)r[3 * q + 1], (int)r[3 * q + 2]);
+        l1[10] = (int)r[30]; l1[11] = (int)r[31];
+        const int a0 = imax3(l1[0], l1[1], l1[2]), a1 = imax3(l1[3], l1[4], l1[5]);
+        const int a2 = imax3(l1[6], l1[7], l1[8]), a3 = imax3(l1[9], l1[10], l1[11]);
+        const int m = max(imax3(a0, a1, a2), a3);
+        if (m > thr_raw) {
+          // exact path (rare once thr is tight): ascending columns, strict '>' keeps the lowest column on ties
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float m01 = fmaxf(fmaxf(v[8 * q], v[8 * q + 1]), v[8 * q + 2]);
-              const float m23 = fmaxf(fmaxf(v[8 * q + 3], v[8 * q + 4]), v[8 * q + 5]);
-              g[q] = fmaxf(fmaxf(m01, m23), fmaxf(v[8 * q + 6], v[8 * q + 7]));
+          for (int q = 0; q < 4; ++q) {
+            const int gq = max(imax3(imax3((int)r[8 * q], (int)r[8 * q + 1], (int)r[8 * q + 2]),
+                                     imax3((int)r[8 * q + 3], (int)r[8 * q + 4], (int)r[8 * q + 5]), (int)r[8 * q + 6]),
+                               (int)r[8 * q + 7]);
+            if (gq > thr_raw) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const int x = (int)r[8 * q + c];
+                const int j = j0 + 8 * q + c;
+                if (x > thr_raw && j < n2) {
+                  const float key = __fmul_rn((float)x, invb[j]);
+                  if (key > thr) {
+                    top.insert(key, (uint32_t)j);
+                    if (top.k3 > thr) { thr = top.k3; thr_raw = raw_bound(thr, bnorm); }
+                  }
+                }
+              }
             }
-            const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
-            if (m > thr) top3_events(v, g, m, thr, top, (uint32_t)j0);
-          } else {
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (j0 + c < n2 && v[c] > thr) { top.insert(v[c], (uint32_t)(j0 + c)); thr = fmaxf(thr, top.k3); }
           }
         }
       }
-      tc_fence_before();
-      if (top.k3 > s_thr[row_in_cta]) s_thr[row_in_cta] = top.k3;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
+      if (top.k3 > shared_thr) s_thr[row_in_cta] = top.k3;   // racy max: any stored value is a valid bound
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
     if (row < n1) {
@@ -550,8 +576,8 @@ __global__ void match_set_counts_kernel(int* counts, int n1, int n2) {
 constexpr int PREP_ROWS = 32;
 __global__ void __launch_bounds__(256)
 match_prep_kernel(const MatchOperand op, int rows_alloc, int dim, int kp, int is_b,
-                  __nv_bfloat16* __restrict__ out, float* __restrict__ raw_copy, float* __restrict__ inv,
-                  int* __restrict__ nonint_flag) {
+                  __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ out_u8, float* __restrict__ raw_copy,
+                  float* __restrict__ inv, int* __restrict__ nonint_flag, int* __restrict__ inv_max_bits) {
   extern __shared__ float tile[];  // [PREP_ROWS][dim + 1]
   const int prob = blockIdx.y;
   const int n = min(op.count[prob * op.count_stride], op.cap);
@@ -559,9 +585,14 @@ match_prep_kernel(const MatchOperand op, int rows_alloc, int dim, int kp, int is
   const int ldt = dim + 1;
   const int tid = threadIdx.x;
   float* inv_p = inv + (size_t)prob * rows_alloc;
+  uint32_t* u8_p = reinterpret_cast<uint32_t*>(out_u8 + ((size_t)prob * rows_alloc + row0) * 128);
   if (row0 >= n) {
+    // dead rows still feed the MMA as zero operands (the bf16 form is only read by live CTAs of the
+    // general kernel, whose dead rows are masked by inv = 0)
     for (int r = tid; r < PREP_ROWS; r += 256)
       if (row0 + r < rows_alloc) inv_p[row0 + r] = 0.f;
+    for (int idx = tid; idx < PREP_ROWS * 32; idx += 256)
+      if (row0 + idx / 32 < rows_alloc) u8_p[idx] = 0u;
     return;
   }
   const float* f = op.base + (size_t)prob * op.prob_stride;
@@ -592,9 +623,26 @@ match_prep_kernel(const MatchOperand op, int rows_alloc, int dim, int kp, int is
       acc = fmaf(v, v, acc);
       isint = isint && (v == truncf(v)) && (v >= 0.f) && (v <= 255.f);
     }
-    if (row0 + tid < rows_alloc)
-      inv_p[row0 + tid] = (acc == 0.f || row0 + tid >= n) ? 0.f : __fdiv_rn(1.0f, __fsqrt_rn(acc));
+    const float iv = (acc == 0.f || row0 + tid >= n) ? 0.f : __fdiv_rn(1.0f, __fsqrt_rn(acc));
+    if (row0 + tid < rows_alloc) inv_p[row0 + tid] = iv;
     if (!isint) atomicOr(nonint_flag, 1);
+    if (inv_max_bits != nullptr) {   // positive floats order like their bit patterns
+      int mx = __float_as_int(iv);
+      for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      if (tid == 0 && mx > 0) atomicMax(inv_max_bits + prob, mx);
+    }
+  }
+  // u8 operands for the exact-integer kernel (garbage, and unused, when some value is not 0..255)
+  for (int idx = tid; idx < PREP_ROWS * 32; idx += 256) {
+    const int r = idx >> 5, k4 = (idx & 31) * 4;
+    if (row0 + r >= rows_alloc) continue;
+    uint32_t w = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const float v = (k4 + b < dim) ? tile[r * ldt + k4 + b] : 0.f;
+      w |= (uint32_t)(__float2int_rz(fminf(fmaxf(v, 0.f), 255.f)) & 255) << (8 * b);
+    }
+    u8_p[idx] = w;
   }
   const int ld_out = 3 * kp;
   __nv_bfloat16* out_p = out + (size_t)prob * rows_alloc * ld_out;
@@ -625,6 +673,15 @@ __device__ __forceinline__ float score_from_key(float key, float inva) {
   return s < 0.f ? 0.f : s;
 }
 
+__device__ __forceinline__ bool keep_row(float s1, float s2, int n2, float thr, float max_ratio) {
+  if (!(s1 <= thr)) return false;
+  if (n2 >= 2) {
+    const float ratio = (s2 < 1e-6f) ? 1.0f : __fdiv_rn(s1, s2);
+    if (!(ratio <= max_ratio)) return false;
+  }
+  return true;
+}
+
 struct RawRows { const float* base; size_t prob_stride; };   // compact row-major fp32 rows per problem
 
 // thread per row: merge candidate slots, exact re-rank, certify or flag for the row scan
@@ -633,7 +690,7 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
                       int dim, const float* __restrict__ inva_base, int inva_stride,
                       const float* __restrict__ invb_base, int invb_stride, const int* __restrict__ n1p,
                       int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
-                      const int* __restrict__ nonint_flag, uint32_t* __restrict__ j1_out,
+                      const int* __restrict__ nonint_flag, MatchFilter flt, uint32_t* __restrict__ j1_out,
                       float* __restrict__ s1_out, float* __restrict__ s2_out, int row_stride,
                       int* __restrict__ scan_list, int* __restrict__ scan_count) {
   const int prob = blockIdx.y;
@@ -680,18 +737,36 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
         const float ts = s[q]; s[q] = s[q + 1]; s[q + 1] = ts;
         const uint32_t tj = jj[q]; jj[q] = jj[q + 1]; jj[q + 1] = tj;
       }
+  // Every column that is not a candidate has key <= kb: the third-best candidate key (each epilogue
+  // thread only skipped keys at or below a lower bound of it) or, on the exact-integer path with a
+  // score bound, the row's initial key bound.  The score is a monotone function of the key, so every
+  // such column has score >= sb.
+  float kb = (nc >= 3) ? k[2] : -INFINITY;
+  const bool bounded = !general && flt.key_floor > 0.f && ia > 0.f;
+  if (bounded) kb = fmaxf(kb, __fdiv_rn(flt.key_floor, ia));
   bool certified;
-  if (n2 <= 3) {
-    certified = (nc == n2);
-  } else if (nc < 3) {
-    certified = false;
+  float s2v = (n2 >= 2) ? s[1] : INFINITY;
+  if (kb == -INFINITY) {
+    certified = (nc == n2);            // nothing was skipped: the candidates are all the columns
   } else {
-    float kb = k[2];
     if (general) kb = kb + SPLIT_EPS * ((ia > 0.f) ? __fdiv_rn(1.0f, ia) : 0.f);
     const float sb = score_from_key(kb, ia);
-    certified = (sb > s[0]) && (sb >= s[1]);
+    if (!bounded) {
+      certified = (nc >= 2) && (sb > s[0]) && (sb >= s[1]);     // (j1, s1, s2) are exactly the oracle's
+    } else if (fminf(s[0], sb) > flt.thr_score) {
+      certified = true;                  // every score is above the match threshold: the row is rejected
+    } else if (!(sb > s[0])) {
+      certified = false;
+    } else if (nc >= 2 && sb >= s[1]) {
+      certified = true;                  // exact top-2
+    } else {
+      // j1 and s1 are exact; the true s2 lies in [sb, s[1]].  The row's outcome is already decided when
+      // it fails the threshold, or passes the ratio test even against the smallest possible s2.
+      s2v = (n2 >= 2) ? sb : INFINITY;
+      certified = !(s[0] <= flt.thr_score) || keep_row(s[0], s2v, n2, flt.thr_score, flt.max_ratio);
+    }
   }
-  j1_out[orow] = jj[0]; s1_out[orow] = s[0]; s2_out[orow] = (n2 >= 2) ? s[1] : INFINITY;
+  j1_out[orow] = jj[0]; s1_out[orow] = s[0]; s2_out[orow] = s2v;
   if (!certified) {
     const int slot = atomicAdd(scan_count, 1);
     scan_list[slot] = prob * row_stride + i;
@@ -746,15 +821,6 @@ match_rowscan_kernel(const int* __restrict__ scan_list, const int* __restrict__ 
 }
 
 // ---------------------------------------------------------------------- select + compaction
-__device__ __forceinline__ bool keep_row(float s1, float s2, int n2, float thr, float max_ratio) {
-  if (!(s1 <= thr)) return false;
-  if (n2 >= 2) {
-    const float ratio = (s2 < 1e-6f) ? 1.0f : __fdiv_rn(s1, s2);
-    if (!(ratio <= max_ratio)) return false;
-  }
-  return true;
-}
-
 // one block per problem: ordered compaction of the surviving rows (batched path, n1 <= ~16k)
 __global__ void __launch_bounds__(1024)
 match_select_block_kernel(const uint32_t* __restrict__ j1, const float* __restrict__ s1, const float* __restrict__ s2,
@@ -902,22 +968,53 @@ static int make_operand_map(CUtensorMap* map, const __nv_bfloat16* base, int row
   return VO_OK;
 }
 
+// u8 operands [n_prob][rows_alloc][128]: one 128-row x 128-byte box = one 128B-swizzled K block
+static int make_u8_map(CUtensorMap* map, const uint8_t* base, int rows_alloc, int n_prob) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled driver entry point not available"); return VO_ERR_CUDA; }
+  cuuint64_t gdim[3] = {128, (cuuint64_t)rows_alloc, (cuuint64_t)n_prob};
+  cuuint64_t gstride[2] = {128, (cuuint64_t)rows_alloc * 128};
+  cuuint32_t box[3] = {128, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (u8) failed (%d)", (int)r); return VO_ERR_CUDA; }
+  return VO_OK;
+}
+
 static bool g_attr_set = false;
 
+MatchFilter make_match_filter(const vo_match_opts& o) {
+  MatchFilter f{0.f, 0.f, 0.f};
+  f.thr_score = o.match_threshold * 0.04f;
+  f.max_ratio = o.max_ratio;
+  // scores above thr_score / max_ratio cannot change a row's outcome; as a key bound (c = 1 - s/2),
+  // loosened by 2^-10 so that match_finalize_kernel's exact check passes with room to spare
+  const double s_bound = (o.max_ratio > 0.f) ? (double)f.thr_score / (double)o.max_ratio : 4.0;
+  if (s_bound < 1.9) f.key_floor = (float)((1.0 - 0.5 * s_bound) * (1.0 - 1.0 / 1024.0));
+  return f;
+}
+
 int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, int n_prob, int dim,
-                     const char* tag, float* dbg_c, cudaStream_t st, MatchTop2* out) {
+                     const char* tag, float* dbg_c, cudaStream_t st, MatchTop2* out, const MatchFilter* filter) {
+  const MatchFilter flt = filter ? *filter : MatchFilter{0.f, 0.f, 0.f};
   auto nm = [&](const char* base) { return std::string(base) + "_" + tag; };
   const int kp = div_up(dim, BK) * BK;
-  if (3 * kp > MAX_KBLOCKS * BK) { set_error("vo_match: dim %d > 128 is not supported by the tensor-core path", dim); return VO_ERR_ARG; }
-  const int a_alloc = div_up(A.cap > 0 ? A.cap : 1, FBM) * FBM;   // whole 256-row panels (fat kernel)
+  if (dim > 128) { set_error("vo_match: dim %d > 128 is not supported by the tensor-core path", dim); return VO_ERR_ARG; }
+  const int a_alloc = div_up(A.cap > 0 ? A.cap : 1, UBM) * UBM;   // whole 256-row panels (u8 kernel)
   const int b_tiles = div_up(B.cap > 0 ? B.cap : 1, BN);
   const int b_alloc = b_tiles * BN;   // multiple of 256, so the epilogue's 32-wide invb loads stay in bounds
 
-  int* ctl; VO_TRY(dev_buf(ctx, nm("m_ctl").c_str(), 8, &ctl));
-  VO_CUDA(cudaMemsetAsync(ctl, 0, 8 * sizeof(int), st));
+  int* ctl; VO_TRY(dev_buf(ctx, nm("m_ctl").c_str(), 8 + (size_t)(n_prob > 0 ? n_prob : 1), &ctl));
+  VO_CUDA(cudaMemsetAsync(ctl, 0, (8 + (size_t)(n_prob > 0 ? n_prob : 1)) * sizeof(int), st));
+  int* invb_max = ctl + 8;   // [n_prob] bit pattern of max_j 1/||b_j||
+  uint8_t *u8A, *u8B;
+  VO_TRY(dev_buf(ctx, nm("m_u8A").c_str(), (size_t)(n_prob > 0 ? n_prob : 1) * a_alloc * 128, &u8A));
   __nv_bfloat16 *opA, *opB; float *invA, *invB, *rawA = nullptr, *rawB = nullptr;
   VO_TRY(dev_buf(ctx, nm("m_opA").c_str(), (size_t)n_prob * a_alloc * 3 * kp, &opA));
   VO_TRY(dev_buf(ctx, nm("m_opB").c_str(), (size_t)n_prob * b_alloc * 3 * kp, &opB));
+  VO_TRY(dev_buf(ctx, nm("m_u8B").c_str(), (size_t)(n_prob > 0 ? n_prob : 1) * b_alloc * 128, &u8B));
   VO_TRY(dev_buf(ctx, nm("m_invA").c_str(), (size_t)n_prob * a_alloc, &invA));
   VO_TRY(dev_buf(ctx, nm("m_invB").c_str(), (size_t)n_prob * b_alloc, &invB));
   RawRows ra{A.base, A.prob_stride}, rb{B.base, B.prob_stride};
@@ -940,13 +1037,13 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   const bool exact_sizes = (n_prob == 1 && !A.gather && !B.gather);   // caps are the live sizes
   {
     ProfScope ps(ctx, st, "match_prep", exact_sizes ? ((double)A.cap + B.cap) * dim * 4.0 : 0.0, 0.0, 2);
-    match_prep_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, kp, 0, opA, rawA, invA, ctl);
-    match_prep_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, kp, 1, opB, rawB, invB, ctl);
+    match_prep_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, kp, 0, opA, u8A, rawA, invA, ctl, nullptr);
+    match_prep_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, kp, 1, opB, u8B, rawB, invB, ctl, invb_max);
   }
   VO_CUDA(cudaGetLastError());
 
   // column splits: only when the row panels alone cannot cover the SMs (sized for the fat kernel)
-  const int m_blocks = a_alloc / FBM;
+  const int m_blocks = a_alloc / UBM;
   int n_splits = 1;
   if (m_blocks * n_prob < ctx->num_sms) {
     n_splits = ctx->num_sms / (m_blocks * n_prob);
@@ -959,13 +1056,14 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   int* scan_list; VO_TRY(dev_buf(ctx, nm("m_scanlist").c_str(), (size_t)n_prob * a_alloc, &scan_list));
 
   if (B.cap > 0) {
-    CUtensorMap tmA, tmB, tmB128;
+    CUtensorMap tmA, tmB, tmA8, tmB8;
     VO_TRY(make_operand_map(&tmA, opA, a_alloc, kp, n_prob, BM));
     VO_TRY(make_operand_map(&tmB, opB, b_alloc, kp, n_prob, BN));
-    VO_TRY(make_operand_map(&tmB128, opB, b_alloc, kp, n_prob, FBN));
+    VO_TRY(make_u8_map(&tmA8, u8A, a_alloc, n_prob));
+    VO_TRY(make_u8_map(&tmB8, u8B, b_alloc, n_prob));
     if (!g_attr_set) {
       VO_CUDA(cudaFuncSetAttribute(match_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      VO_CUDA(cudaFuncSetAttribute(match_topk_fat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FAT_SMEM_BYTES));
+      VO_CUDA(cudaFuncSetAttribute(match_topk_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM_BYTES));
       g_attr_set = true;
     }
     // both variants are launched; each reads the device-side "non-integer input" flag and one of them
@@ -974,15 +1072,15 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
     match_topk_kernel<<<dim3(a_alloc / BM, n_splits, n_prob), NUM_THREADS, SMEM_BYTES, st>>>(
         tmA, tmB, invB, b_alloc, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap, ctl, kp / BK, n_splits, cand,
         cand_stride, dbg_c, B.cap);
-    match_topk_fat_kernel<<<dim3(m_blocks, n_splits, n_prob), NUM_THREADS, FAT_SMEM_BYTES, st>>>(
-        tmA, tmB128, invB, b_alloc, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap, ctl, kp / BK, n_splits, cand,
-        cand_stride, n_slots, dbg_c, B.cap);
+    match_topk_u8_kernel<<<dim3(m_blocks, n_splits, n_prob), NUM_THREADS, U_SMEM_BYTES, st>>>(
+        tmA8, tmB8, invB, b_alloc, invA, a_alloc, invb_max, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap,
+        ctl, n_splits, cand, cand_stride, n_slots, flt.key_floor, dbg_c, B.cap);
     VO_CUDA(cudaGetLastError());
     ctx->match_stats[2] = 1;
   }
   match_finalize_kernel<<<dim3(div_up(A.cap, 128), n_prob), 128, 0, st>>>(
       cand, cand_stride, n_slots, ra, rb, dim, invA, a_alloc, invB, b_alloc, A.count, A.count_stride, A.cap, B.count,
-      B.count_stride, B.cap, ctl, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
+      B.count_stride, B.cap, ctl, flt, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
   if (B.cap > 0) {
     int scan_grid = ctx->num_sms * 2;
     match_rowscan_kernel<<<scan_grid, 256, 0, st>>>(scan_list, ctl + 1, ra, rb, dim, invA, a_alloc, invB, b_alloc, B.count,
@@ -1044,12 +1142,13 @@ static int match_device(vo_ctx* ctx, const float* f1, int n1, const float* f2, i
   }
   Single s; VO_TRY(single_operands(ctx, f1, n1, f2, n2, col_major, "f", st, &s));
   MatchTop2 t;
-  VO_TRY(match_batch_top2(ctx, s.A, s.B, 1, dim, "f", nullptr, st, &t));
+  const MatchFilter flt = make_match_filter(o);
+  VO_TRY(match_batch_top2(ctx, s.A, s.B, 1, dim, "f", nullptr, st, &t, &flt));
   const uint32_t* bj1 = nullptr;
   if (o.unique) {
     Single sb; VO_TRY(single_operands(ctx, f2, n2, f1, n1, col_major, "b", st, &sb));
     MatchTop2 tb;
-    VO_TRY(match_batch_top2(ctx, sb.A, sb.B, 1, dim, "b", nullptr, st, &tb));
+    VO_TRY(match_batch_top2(ctx, sb.A, sb.B, 1, dim, "b", nullptr, st, &tb, &flt));
     bj1 = tb.j1;
     ctx->match_stats[2] = 2;
   }

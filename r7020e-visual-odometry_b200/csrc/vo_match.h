@@ -25,9 +25,19 @@ struct MatchTop2 {       // device results, [n_prob][cap_a_pad]
   int* ctl;              // ctl[0] = non-integer flag, ctl[1] = rows sent to the exact scan
 };
 
+// Score bound for matchFeatures-style consumers: rows are only kept when s1 <= thr_score and
+// s1/s2 <= max_ratio, so columns scoring above thr_score/max_ratio never matter.  key_floor is that
+// bound as a cosine (0 = no bound: exact top-2 for every row).
+struct MatchFilter { float key_floor; float thr_score; float max_ratio; };
+MatchFilter make_match_filter(const vo_match_opts& o);
+
 // prep + tcgen05 GEMM top-3 + finalize + exact row scan.  No host synchronisation.
+// filter == nullptr: (j1, s1, s2) are the exact top-2 of every row.  With a filter, rows the filter
+// rejects may carry s1 = inf / j1 = 0xFFFFFFFF and s2 may be a lower bound; match_batch_select with
+// the same options returns exactly the pairs of the unfiltered run.
 int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, int n_prob, int dim,
-                     const char* tag, float* dbg_c, cudaStream_t st, MatchTop2* out);
+                     const char* tag, float* dbg_c, cudaStream_t st, MatchTop2* out,
+                     const MatchFilter* filter = nullptr);
 
 // threshold / ratio tests + ordered compaction, one block per problem.
 // idx1/idx2/metric: [n_prob][out_stride]; n_pairs[p*np_stride].
