@@ -339,7 +339,7 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // tcgen05.mma.kind::i8 (u8 x u8 -> s32, K = 32 per instruction): half the shared-memory operand bytes
 // per MMA of the bf16 form and twice the MACs per issue slot, and the s32 accumulator IS the oracle's
 // dot product (sum < 2^23).  The CTA keeps TWO 128-row A panels resident (M = 256) and streams
-// 128-column B tiles (16 KB, one 128B-swizzled K block) through an 8-stage ring.
+// 128-column B tiles (16 KB, one 128B-swizzled K block) through a 7-stage ring.
 // TMEM: 2 accumulator stages x (2 panels x 128 columns).
 //
 // Epilogue thread = (panel, TMEM lane quarter, 64-column half); candidate slot = split*2 + half.
@@ -355,8 +355,9 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // the decision and (j1, s1) are exactly the oracle's, or sends the row to the exact scan.
 constexpr int UBM = 256, UBN = 128;
 constexpr int U_TILE_BYTES = 128 * 128;         // 128 rows x 128 u8
-constexpr int U_STAGES = 8;
-constexpr int U_SMEM_BYTES = 2 * U_TILE_BYTES + U_STAGES * U_TILE_BYTES + 256 + UBM * 4;
+constexpr int U_STAGES = 7;
+constexpr int U_SCRATCH_INTS = 32 * 33;         // per epilogue warp: one 32 x 32 chunk, padded (transpose)
+constexpr int U_SMEM_BYTES = 2 * U_TILE_BYTES + U_STAGES * U_TILE_BYTES + 256 + UBM * 4 + NUM_EPI_WARPS * U_SCRATCH_INTS * 4;
 
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }
 __device__ __forceinline__ int raw_bound(float thr, float bnorm) {
@@ -488,6 +489,7 @@ match_topk_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int row = m0 + row_in_cta;
     const float bmax = __int_as_float(invb_max_bits[prob]);
     const float bnorm = bmax > 0.f ? __fdiv_rn(1.0f, bmax) : 0.f;
+    int* scr = reinterpret_cast<int*>(s_thr + UBM) + e * U_SCRATCH_INTS;
     Top3 top; top.init();
     float thr = s_thr[row_in_cta];
     int thr_raw = raw_bound(thr, bnorm);
@@ -523,28 +525,36 @@ match_topk_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int a0 = imax3(l1[0], l1[1], l1[2]), a1 = imax3(l1[3], l1[4], l1[5]);
         const int a2 = imax3(l1[6], l1[7], l1[8]), a3 = imax3(l1[9], l1[10], l1[11]);
         const int m = max(imax3(a0, a1, a2), a3);
-        if (m > thr_raw) {
-          // exact path (rare once thr is tight): ascending columns, strict '>' keeps the lowest column on ties
+        const unsigned flagged = __ballot_sync(0xffffffffu, m > thr_raw);
+        if (flagged) {
+          // Exact path, warp-cooperative and warp-uniform.  The chunk is transposed through a padded
+          // shared-memory scratch so that, for each flagged row L in turn, lane c holds column c:
+          // one convert + multiply gives all 32 exact keys of the row, a ballot picks the columns above
+          // the row's bound (ascending), and lane L alone updates its top-3.
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int gq = max(imax3(imax3((int)r[8 * q], (int)r[8 * q + 1], (int)r[8 * q + 2]),
-                                     imax3((int)r[8 * q + 3], (int)r[8 * q + 4], (int)r[8 * q + 5]), (int)r[8 * q + 6]),
-                               (int)r[8 * q + 7]);
-            if (gq > thr_raw) {
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const int x = (int)r[8 * q + c];
-                const int j = j0 + 8 * q + c;
-                if (x > thr_raw && j < n2) {
-                  const float key = __fmul_rn((float)x, invb[j]);
-                  if (key > thr) {
-                    top.insert(key, (uint32_t)j);
-                    if (top.k3 > thr) { thr = top.k3; thr_raw = raw_bound(thr, bnorm); }
-                  }
-                }
+          for (int c = 0; c < 32; ++c) scr[c * 33 + lane] = (int)r[c];
+          const int jc = j0 + lane;
+          const float ib = (jc < n2) ? invb[jc] : 0.f;
+          __syncwarp();
+          unsigned f = flagged;
+          while (f) {
+            const int L = __ffs(f) - 1;
+            f &= f - 1;
+            const float key = __fmul_rn((float)scr[lane * 33 + L], ib);
+            float thr_l = __shfl_sync(0xffffffffu, thr, L);
+            unsigned cm = __ballot_sync(0xffffffffu, jc < n2 && key > thr_l);
+            while (cm) {
+              const int c = __ffs(cm) - 1;
+              const float kk = __shfl_sync(0xffffffffu, key, c);
+              if (lane == L && kk > thr) {
+                top.insert(kk, (uint32_t)(j0 + c));
+                if (top.k3 > thr) { thr = top.k3; thr_raw = raw_bound(thr, bnorm); }
               }
+              thr_l = __shfl_sync(0xffffffffu, thr, L);
+              cm &= __ballot_sync(0xffffffffu, key > thr_l) & ~((2u << c) - 1u);
             }
           }
+          __syncwarp();
         }
       }
       if (top.k3 > shared_thr) s_thr[row_in_cta] = top.k3;   // racy max: any stored value is a valid bound
@@ -1042,13 +1052,21 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   }
   VO_CUDA(cudaGetLastError());
 
-  // column splits: only when the row panels alone cannot cover the SMs (sized for the fat kernel)
+  // column splits: equal-sized CTAs run in waves of num_sms, so pick the split count (<= 8) that
+  // minimises waves x (tiles per CTA + a fixed per-CTA prologue of ~6 tile times)
   const int m_blocks = a_alloc / UBM;
+  const int u_tiles = div_up(B.cap > 0 ? B.cap : 1, UBN);
   int n_splits = 1;
-  if (m_blocks * n_prob < ctx->num_sms) {
-    n_splits = ctx->num_sms / (m_blocks * n_prob);
+  {
+    long long best = -1;
+    for (int sp = 1; sp <= 8 && sp <= u_tiles; ++sp) {
+      const long long ctas = (long long)m_blocks * n_prob * sp;
+      const long long cost = ((ctas + ctx->num_sms - 1) / ctx->num_sms) * (div_up(u_tiles, sp) + 6);
+      if (best < 0 || cost < best) { best = cost; n_splits = sp; }
+    }
+    // many short problems (the frame loop): waves are plentiful, fewer and longer CTAs amortise best
+    if ((long long)m_blocks * n_prob >= 4LL * ctx->num_sms) n_splits = 1;
     if (n_splits > b_tiles) n_splits = b_tiles;
-    if (n_splits < 1) n_splits = 1;
   }
   const int n_slots = n_splits * 4;
   const size_t cand_stride = (size_t)a_alloc * n_slots * NCAND;
