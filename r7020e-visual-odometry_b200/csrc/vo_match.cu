@@ -493,6 +493,7 @@ match_topk_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     Top3 top; top.init();
     float thr = s_thr[row_in_cta];
     int thr_raw = raw_bound(thr, bnorm);
+    if (row >= n1) { thr = INFINITY; thr_raw = 0x7fffffff; }   // padding rows never take the exact path
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = t_begin; t < t_end; ++t) {
       mbar_wait(bar_t_full + 8 * acc, acc_phase);
