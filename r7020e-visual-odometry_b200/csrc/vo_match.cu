@@ -585,27 +585,10 @@ __global__ void match_set_counts_kernel(int* counts, int n1, int n2) {
 // inv[p][row] (0 for rows >= n), an optional compact row-major fp32 copy (needed when rows are
 // gathered or column-major), and ORs the "not an integer in 0..255" flag.
 constexpr int PREP_ROWS = 32;
-__global__ void __launch_bounds__(256)
-match_prep_kernel(const MatchOperand op, int rows_alloc, int dim, int kp, int is_b,
-                  __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ out_u8, float* __restrict__ raw_copy,
-                  float* __restrict__ inv, int* __restrict__ nonint_flag, int* __restrict__ inv_max_bits) {
-  extern __shared__ float tile[];  // [PREP_ROWS][dim + 1]
-  const int prob = blockIdx.y;
-  const int n = min(op.count[prob * op.count_stride], op.cap);
-  const int row0 = blockIdx.x * PREP_ROWS;
-  const int ldt = dim + 1;
-  const int tid = threadIdx.x;
-  float* inv_p = inv + (size_t)prob * rows_alloc;
-  uint32_t* u8_p = reinterpret_cast<uint32_t*>(out_u8 + ((size_t)prob * rows_alloc + row0) * 128);
-  if (row0 >= n) {
-    // dead rows still feed the MMA as zero operands (the bf16 form is only read by live CTAs of the
-    // general kernel, whose dead rows are masked by inv = 0)
-    for (int r = tid; r < PREP_ROWS; r += 256)
-      if (row0 + r < rows_alloc) inv_p[row0 + r] = 0.f;
-    for (int idx = tid; idx < PREP_ROWS * 32; idx += 256)
-      if (row0 + idx / 32 < rows_alloc) u8_p[idx] = 0u;
-    return;
-  }
+
+// rows [row0, row0 + PREP_ROWS) of problem `prob` -> tile[r][dim + 1] (zero beyond the live count)
+__device__ __forceinline__ void prep_load_tile(const MatchOperand& op, int prob, int row0, int n, int dim, float* tile) {
+  const int ldt = dim + 1, tid = threadIdx.x;
   const float* f = op.base + (size_t)prob * op.prob_stride;
   const uint32_t* g = op.gather ? op.gather + (size_t)prob * op.gather_stride : nullptr;
   if (!op.col_major) {
@@ -624,26 +607,60 @@ match_prep_kernel(const MatchOperand op, int rows_alloc, int dim, int kp, int is
       tile[r * ldt + k] = (row0 + r < n) ? f[(size_t)k * op.ld + row0 + r] : 0.f;
     }
   }
+}
+
+// Always runs: 1/||row|| in the oracle's arithmetic, the u8 operands of the exact-integer kernel, the
+// "some value is not an integer in 0..255" flag and max_j 1/||b_j||.  Eight threads share a row.  When the
+// row is all integers 0..255 every partial sum of squares is an integer below 2^24, hence exact in
+// fp32 in ANY order and equal to the oracle's sequential fmaf fold; otherwise one thread redoes the
+// fold sequentially.
+__global__ void __launch_bounds__(256)
+match_prep_kernel(const MatchOperand op, int rows_alloc, int dim, uint8_t* __restrict__ out_u8,
+                  float* __restrict__ inv, int* __restrict__ nonint_flag, int* __restrict__ inv_max_bits) {
+  extern __shared__ float tile[];  // [PREP_ROWS][dim + 1]
+  const int prob = blockIdx.y;
+  const int n = min(op.count[prob * op.count_stride], op.cap);
+  const int row0 = blockIdx.x * PREP_ROWS;
+  const int ldt = dim + 1;
+  const int tid = threadIdx.x;
+  float* inv_p = inv + (size_t)prob * rows_alloc;
+  uint32_t* u8_p = reinterpret_cast<uint32_t*>(out_u8 + ((size_t)prob * rows_alloc + row0) * 128);
+  if (row0 >= n) {   // dead rows still feed the MMA as zero operands
+    for (int r = tid; r < PREP_ROWS; r += 256)
+      if (row0 + r < rows_alloc) inv_p[row0 + r] = 0.f;
+    for (int idx = tid; idx < PREP_ROWS * 32; idx += 256)
+      if (row0 + idx / 32 < rows_alloc) u8_p[idx] = 0u;
+    return;
+  }
+  prep_load_tile(op, prob, row0, n, dim, tile);
   __syncthreads();
-  if (tid < PREP_ROWS) {
-    const float* x = tile + tid * ldt;
+  {
+    const int r = tid >> 3, part = tid & 7;
+    const float* x = tile + r * ldt;
     float acc = 0.f;
     bool isint = true;
-    for (int k = 0; k < dim; ++k) {
+    for (int k = part; k < dim; k += 8) {
       const float v = x[k];
       acc = fmaf(v, v, acc);
       isint = isint && (v == truncf(v)) && (v >= 0.f) && (v <= 255.f);
     }
-    const float iv = (acc == 0.f || row0 + tid >= n) ? 0.f : __fdiv_rn(1.0f, __fsqrt_rn(acc));
-    if (row0 + tid < rows_alloc) inv_p[row0 + tid] = iv;
-    if (!isint) atomicOr(nonint_flag, 1);
-    if (inv_max_bits != nullptr) {   // positive floats order like their bit patterns
-      int mx = __float_as_int(iv);
-      for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-      if (tid == 0 && mx > 0) atomicMax(inv_max_bits + prob, mx);
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      isint = __shfl_xor_sync(0xffffffffu, (int)isint, off) && isint;
+    }
+    if (part == 0) {
+      if (!isint) {
+        acc = 0.f;
+        for (int k = 0; k < dim; ++k) acc = fmaf(x[k], x[k], acc);
+        atomicOr(nonint_flag, 1);
+      }
+      const float iv = (acc == 0.f || row0 + r >= n) ? 0.f : __fdiv_rn(1.0f, __fsqrt_rn(acc));
+      if (row0 + r < rows_alloc) inv_p[row0 + r] = iv;
+      if (inv_max_bits != nullptr && iv > 0.f) atomicMax(inv_max_bits + prob, __float_as_int(iv));   // positive floats order like their bits
     }
   }
-  // u8 operands for the exact-integer kernel (garbage, and unused, when some value is not 0..255)
+  // u8 operands (garbage, and unused, when some value is not 0..255)
   for (int idx = tid; idx < PREP_ROWS * 32; idx += 256) {
     const int r = idx >> 5, k4 = (idx & 31) * 4;
     if (row0 + r >= rows_alloc) continue;
@@ -655,6 +672,23 @@ match_prep_kernel(const MatchOperand op, int rows_alloc, int dim, int kp, int is
     }
     u8_p[idx] = w;
   }
+}
+
+// Runs only when the non-integer flag is set (general float descriptors): bf16 hi/lo split operands
+// out[p][row][3*kp] (A: hi|hi|lo, B: hi|lo|hi) for match_topk_kernel and, for gathered or column-major
+// inputs, the compact row-major fp32 copy the exact re-scoring reads.
+__global__ void __launch_bounds__(256)
+match_prep_split_kernel(const MatchOperand op, int rows_alloc, int dim, int kp, int is_b,
+                        __nv_bfloat16* __restrict__ out, float* __restrict__ raw_copy, const int* __restrict__ nonint_flag) {
+  extern __shared__ float tile[];
+  if (*nonint_flag == 0) return;
+  const int prob = blockIdx.y;
+  const int n = min(op.count[prob * op.count_stride], op.cap);
+  const int row0 = blockIdx.x * PREP_ROWS;
+  if (row0 >= n) return;   // dead rows are masked by inv = 0
+  const int ldt = dim + 1, tid = threadIdx.x;
+  prep_load_tile(op, prob, row0, n, dim, tile);
+  __syncthreads();
   const int ld_out = 3 * kp;
   __nv_bfloat16* out_p = out + (size_t)prob * rows_alloc * ld_out;
   float* raw_p = raw_copy ? raw_copy + (size_t)prob * rows_alloc * dim : nullptr;
@@ -784,30 +818,52 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
   }
 }
 
-// exact FP32 scan of every column for the rows in scan_list (block per row, grid-stride)
+// exact scan of every column for the rows in scan_list (block per row, grid-stride).  General floats:
+// the oracle's sequential FP32 dot on the raw rows.  Exact-integer inputs: the u8 operands and an
+// integer dot product, which IS the oracle's dot (every partial sum < 2^24).
 __global__ void __launch_bounds__(256)
 match_rowscan_kernel(const int* __restrict__ scan_list, const int* __restrict__ scan_count, RawRows ra, RawRows rb,
-                     int dim, const float* __restrict__ inva_base, int inva_stride,
+                     const uint8_t* __restrict__ u8a, const uint8_t* __restrict__ u8b, int a_alloc, int b_alloc,
+                     const int* __restrict__ nonint_flag, int dim, const float* __restrict__ inva_base, int inva_stride,
                      const float* __restrict__ invb_base, int invb_stride, const int* __restrict__ n2p,
                      int n2_stride, int cap2, uint32_t* __restrict__ j1_out, float* __restrict__ s1_out,
                      float* __restrict__ s2_out, int row_stride) {
   __shared__ float sa[256];
+  __shared__ uint32_t sa8[32];
   __shared__ float rs1[256], rs2[256];
   __shared__ uint32_t rj1[256];
   const int count = *scan_count;
+  const bool general = (*nonint_flag) != 0;
   for (int f = blockIdx.x; f < count; f += gridDim.x) {
     const int code = scan_list[f];
     const int prob = code / row_stride, i = code - prob * row_stride;
     const int n2 = min(n2p[prob * n2_stride], cap2);
     const float* invb = invb_base + (size_t)prob * invb_stride;
-    const float* b_rows = rb.base + (size_t)prob * rb.prob_stride;
     __syncthreads();
-    for (int k = threadIdx.x; k < dim; k += blockDim.x) sa[k] = ra.base[(size_t)prob * ra.prob_stride + (size_t)i * dim + k];
+    if (general) {
+      for (int k = threadIdx.x; k < dim; k += blockDim.x) sa[k] = ra.base[(size_t)prob * ra.prob_stride + (size_t)i * dim + k];
+    } else if (threadIdx.x < 32) {
+      sa8[threadIdx.x] = reinterpret_cast<const uint32_t*>(u8a + ((size_t)prob * a_alloc + i) * 128)[threadIdx.x];
+    }
     __syncthreads();
     const float ia = inva_base[(size_t)prob * inva_stride + i];
     float b1 = INFINITY, b2 = INFINITY; uint32_t bj = 0xFFFFFFFFu;
     for (int jx = threadIdx.x; jx < n2; jx += blockDim.x) {
-      const float sc = score_from_key(exact_key(sa, b_rows + (size_t)jx * dim, dim, invb[jx]), ia);
+      float key;
+      if (general) {
+        key = exact_key(sa, rb.base + (size_t)prob * rb.prob_stride + (size_t)jx * dim, dim, invb[jx]);
+      } else {
+        const uint4* bw = reinterpret_cast<const uint4*>(u8b + ((size_t)prob * b_alloc + jx) * 128);
+        unsigned dot = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint4 w = bw[q];
+          dot = __dp4a(sa8[4 * q], w.x, dot); dot = __dp4a(sa8[4 * q + 1], w.y, dot);
+          dot = __dp4a(sa8[4 * q + 2], w.z, dot); dot = __dp4a(sa8[4 * q + 3], w.w, dot);
+        }
+        key = __fmul_rn((float)(int)dot, invb[jx]);
+      }
+      const float sc = score_from_key(key, ia);
       if (sc < b1) { b2 = b1; b1 = sc; bj = (uint32_t)jx; }
       else if (sc < b2) b2 = sc;
     }
@@ -1047,9 +1103,12 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   const size_t prep_smem = (size_t)PREP_ROWS * (dim + 1) * sizeof(float);
   const bool exact_sizes = (n_prob == 1 && !A.gather && !B.gather);   // caps are the live sizes
   {
-    ProfScope ps(ctx, st, "match_prep", exact_sizes ? ((double)A.cap + B.cap) * dim * 4.0 : 0.0, 0.0, 2);
-    match_prep_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, kp, 0, opA, u8A, rawA, invA, ctl, nullptr);
-    match_prep_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, kp, 1, opB, u8B, rawB, invB, ctl, invb_max);
+    ProfScope ps(ctx, st, "match_prep", exact_sizes ? ((double)A.cap + B.cap) * (dim * 4.0 + 132.0) : 0.0, 0.0, 4);
+    match_prep_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, u8A, invA, ctl, nullptr);
+    match_prep_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, u8B, invB, ctl, invb_max);
+    // general float descriptors only (both return at once when every value is an integer 0..255)
+    match_prep_split_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, kp, 0, opA, rawA, ctl);
+    match_prep_split_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, kp, 1, opB, rawB, ctl);
   }
   VO_CUDA(cudaGetLastError());
 
@@ -1102,7 +1161,7 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
       B.count_stride, B.cap, ctl, flt, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
   if (B.cap > 0) {
     int scan_grid = ctx->num_sms * 2;
-    match_rowscan_kernel<<<scan_grid, 256, 0, st>>>(scan_list, ctl + 1, ra, rb, dim, invA, a_alloc, invB, b_alloc, B.count,
+    match_rowscan_kernel<<<scan_grid, 256, 0, st>>>(scan_list, ctl + 1, ra, rb, u8A, u8B, a_alloc, b_alloc, ctl, dim, invA, a_alloc, invB, b_alloc, B.count,
                                                     B.count_stride, B.cap, out->j1, out->s1, out->s2, a_alloc);
   }
   VO_CUDA(cudaGetLastError());

@@ -493,6 +493,125 @@ sift_blur_stream_kernel(const float* __restrict__ src, float* __restrict__ dst, 
   }
 }
 
+// Base image, streaming: u8 -> 2x bilinear upsample (cv::resize convention) -> blur(sig_diff), same
+// strip-walking structure as sift_blur_stream_kernel.  The upsample is separable and the contract's
+// value  wya*(wxa*a + wxb*b) + wyb*(wxa*c + wxb*d)  only mixes two SOURCE rows, so the horizontal
+// blends h(r, x) = wxa*img[r][xa] + wxb*img[r][xb] are formed once per source row into a small ring
+// and every upsampled sample is 2 multiplies + 1 add on top of them (identical operations, identical
+// order, bit-identical result).
+template <int R>
+__global__ void __launch_bounds__(256, 3)
+sift_base_stream_kernel(const uint8_t* __restrict__ img8, float* __restrict__ dst, int h, int w, int pitch,
+                        int rows8, int cols8, int seg_rows, const Taps taps) {
+  constexpr int RP = (R + 3) & ~3;
+  constexpr int NWIN = 4 + 2 * RP;
+  constexpr int RING = 64, HRING = 16, HW = ST_W + 2 * RP;
+  static_assert(ST_CH + 2 * R <= RING, "ring too small");
+  __shared__ __align__(16) float ring[RING][ST_W];
+  __shared__ __align__(16) float hring[HRING][HW];
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * ST_W;
+  const int ys = blockIdx.y * seg_rows, ye = min(ys + seg_rows, h);
+  const uint8_t* src = img8 + (size_t)b * rows8 * cols8;
+  float* out = dst + (size_t)b * h * pitch;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+
+  auto src_rows = [&](int y, int& ya, int& yb) {
+    ya = (y & 1) ? (y >> 1) : (y >> 1) - 1; yb = ya + 1;
+    if (ya < 0) ya = 0;
+    if (yb > rows8 - 1) yb = rows8 - 1;
+  };
+  int h_done = -1;   // source rows <= h_done are (or were) in the ring; block-uniform
+  auto ensure_h = [&](int y_lo, int y_hi) {   // h rows needed by upsampled rows [y_lo, y_hi]
+    int lo, hi, t;
+    src_rows(y_lo, lo, t); src_rows(y_hi, t, hi);
+    if (lo <= h_done) lo = h_done + 1;
+    const int nr = hi - lo + 1;
+    for (int idx = tid; idx < nr * HW; idx += 256) {
+      const int rr = idx / HW, q = idx - rr * HW;
+      const int r = lo + rr;
+      const int x = reflect101(x0 - RP + q, w);
+      int xa = (x & 1) ? (x >> 1) : (x >> 1) - 1, xb = xa + 1;
+      const float wxb = (x & 1) ? 0.25f : 0.75f, wxa = 1.0f - wxb;
+      if (xa < 0) xa = 0;
+      if (xb > cols8 - 1) xb = cols8 - 1;
+      const float a = src[(size_t)r * cols8 + xa], c = src[(size_t)r * cols8 + xb];
+      hring[r & (HRING - 1)][q] = wxa * a + wxb * c;
+    }
+    if (hi > h_done) h_done = hi;
+  };
+  auto row_pass = [&](int row) {
+    int ya, yb;
+    src_rows(row, ya, yb);
+    const float wyb = (row & 1) ? 0.25f : 0.75f, wya = 1.0f - wyb;
+    const float4* pa = reinterpret_cast<const float4*>(&hring[ya & (HRING - 1)][4 * lane]);
+    const float4* pb = reinterpret_cast<const float4*>(&hring[yb & (HRING - 1)][4 * lane]);
+    float win[NWIN];
+#pragma unroll
+    for (int q = 0; q < NWIN / 4; ++q) {
+      const float4 va = pa[q], vb = pb[q];
+      win[4 * q] = wya * va.x + wyb * vb.x; win[4 * q + 1] = wya * va.y + wyb * vb.y;
+      win[4 * q + 2] = wya * va.z + wyb * vb.z; win[4 * q + 3] = wya * va.w + wyb * vb.w;
+    }
+    float acc[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) acc[o] = taps.k[0] * win[RP + o];
+#pragma unroll
+    for (int i = 1; i <= R; ++i) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] = fmaf(taps.k[i], win[RP + o - i] + win[RP + o + i], acc[o]);
+    }
+    *reinterpret_cast<float4*>(&ring[row & (RING - 1)][4 * lane]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  };
+
+  {
+    const int lo = max(ys - R, 0), hi = min(ys + R, h);
+    ensure_h(lo, hi - 1);
+    __syncthreads();
+    for (int row = lo + wrp; row < hi; row += 8) row_pass(row);
+  }
+  const int cp = tid & 63, rg = tid >> 6;
+  const int x = x0 + 2 * cp;
+  for (int yc = ys; yc < ye; yc += ST_CH) {
+    const int lo = yc + R, hi = min(yc + ST_CH + R, h);
+    __syncthreads();                       // previous chunk's column pass is done with the rings
+    if (lo < hi) ensure_h(lo, hi - 1);
+    __syncthreads();
+    for (int row = lo + wrp; row < hi; row += 8) row_pass(row);
+    __syncthreads();
+    const int yf = yc + rg * 4;
+    if (yf < ye && x < w) {
+      u64 win[4 + 2 * R];
+      if (yf - R >= 0 && yf + 3 + R < h) {
+#pragma unroll
+        for (int q = 0; q < 4 + 2 * R; ++q)
+          win[q] = *reinterpret_cast<const u64*>(&ring[(yf - R + q) & (RING - 1)][2 * cp]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4 + 2 * R; ++q) {
+          const int ry = reflect101(yf - R + q, h);
+          win[q] = *reinterpret_cast<const u64*>(&ring[ry & (RING - 1)][2 * cp]);
+        }
+      }
+      u64 acc[4];
+      const u64 k0 = f2_bcast(taps.k[0]);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] = f2_mul(k0, win[R + o]);
+#pragma unroll
+      for (int i = 1; i <= R; ++i) {
+        const u64 ki = f2_bcast(taps.k[i]);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o] = f2_fma(ki, f2_add(win[R + o - i], win[R + o + i]), acc[o]);
+      }
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int y = yf + o;
+        if (y < ye) *reinterpret_cast<float2*>(out + (size_t)y * pitch + x) = *reinterpret_cast<const float2*>(&acc[o]);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 sift_downsample_kernel(const float* __restrict__ src, float* __restrict__ dst, int sh, int spitch, int dh, int dw, int dpitch) {
   const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
@@ -1195,7 +1314,16 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
   VO_CUDA(cudaMemsetAsync(p->counters, 0, (size_t)batch * 4 * sizeof(int), st));
   // pyramid
   ProfScope* ps_base = new ProfScope(ctx, st, "sift_base_upsample_blur", (double)batch * ((double)p->rows * p->cols + (double)p->h[0] * p->w[0] * 4.0));
-  if (p->base_taps.r == 5)
+  if (p->base_taps.r == 5 && p->h[0] >= 64) {
+    const int strips = div_up(p->w[0], ST_W);
+    int n_seg = 1;
+    const int target = ctx->num_sms * 8;
+    if (strips * batch < target) n_seg = div_up(target, strips * batch);
+    int seg_rows = div_up(div_up(p->h[0], n_seg), ST_CH) * ST_CH;
+    if (seg_rows < 4 * ST_CH) seg_rows = 4 * ST_CH;
+    n_seg = div_up(p->h[0], seg_rows);
+    sift_base_stream_kernel<5><<<dim3(strips, n_seg, batch), 256, 0, st>>>(p->img, p->G(0, 0), p->h[0], p->w[0], p->pitch[0], p->rows, p->cols, seg_rows, p->base_taps);
+  } else if (p->base_taps.r == 5)
     VO_TRY((launch_blur_t<5, true>(nullptr, p->img, p->G(0, 0), nullptr, p->h[0], p->w[0], p->pitch[0], p->rows, p->cols, batch, p->base_taps, st)));
   else
     VO_TRY((launch_blur_t<0, true>(nullptr, p->img, p->G(0, 0), nullptr, p->h[0], p->w[0], p->pitch[0], p->rows, p->cols, batch, p->base_taps, st)));
