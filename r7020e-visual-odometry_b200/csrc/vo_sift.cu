@@ -360,6 +360,10 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
     if (tid == 0 && c + 4 < n_groups) issue(c + 4);
     const int yf = ys + c * TS_G + rg * 4;
     if (yf < ye && x < w) {
+      // centre pixels of G[l] for the fused DoG: issued first so their latency hides behind the filter
+      float2 cc[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) cc[o] = (yf + o < ye) ? __ldg(reinterpret_cast<const float2*>(img + (size_t)(yf + o) * pitch + x)) : make_float2(0.f, 0.f);
       u64 win[4 + 2 * R];
       const int s0 = (yf - R) & (RING - 1);
       if (yf - R >= 0 && yf + 3 + R < h) {
@@ -393,10 +397,9 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
         const int y = yf + o;
         if (y < ye) {
           const size_t g = (size_t)y * pitch + x;
-          const float2 cc = __ldg(reinterpret_cast<const float2*>(img + g));
           const float2 v = *reinterpret_cast<const float2*>(&acc[o]);
           *reinterpret_cast<float2*>(dst + img_off + g) = v;
-          *reinterpret_cast<float2*>(dog + img_off + g) = make_float2(v.x - cc.x, v.y - cc.y);
+          *reinterpret_cast<float2*>(dog + img_off + g) = make_float2(v.x - cc[o].x, v.y - cc[o].y);
         }
       }
     }
@@ -786,20 +789,40 @@ sift_refine_orient_kernel(const float* __restrict__ gauss, const float* __restri
     const float* gimg = gauss + oi.goff[o] + (size_t)layer * lstride + (size_t)b * rows * pitch;
     for (int k = lane; k < ORI_BINS; k += 32) s_hist[wib][k] = 0;
     __syncwarp();
-    const int side = 2 * radius + 1;
-    for (int idx = lane; idx < side * side; idx += 32) {
-      const int i = idx / side - radius, j = idx % side - radius;
+    const int side = 2 * radius + 1, total = side * side;
+    // two samples per lane in flight (loads first, arithmetic after); (i, j) advance incrementally
+    struct OSamp { float xp, xm, yu, yd; int i, j; bool ok; };
+    auto ofetch = [&](int i, int j, OSamp& sm) {
       const int y = r + i, x = c + j;
-      if (y <= 0 || y >= rows - 1 || x <= 0 || x >= cols - 1) continue;
-      const float dx = gimg[(size_t)y * pitch + x + 1] - gimg[(size_t)y * pitch + x - 1];
-      const float dy = gimg[(size_t)(y - 1) * pitch + x] - gimg[(size_t)(y + 1) * pitch + x];
-      const float wgt = vo_expf((float)(i * i + j * j) * expf_scale);
+      sm.i = i; sm.j = j;
+      sm.ok = !(y <= 0 || y >= rows - 1 || x <= 0 || x >= cols - 1);
+      if (sm.ok) {
+        const float* q = gimg + (size_t)y * pitch + x;
+        sm.xp = __ldg(q + 1); sm.xm = __ldg(q - 1); sm.yu = __ldg(q - pitch); sm.yd = __ldg(q + pitch);
+      }
+    };
+    auto oaccum = [&](const OSamp& sm) {
+      if (!sm.ok) return;
+      const float dx = sm.xp - sm.xm;
+      const float dy = sm.yu - sm.yd;
+      const float wgt = vo_expf((float)(sm.i * sm.i + sm.j * sm.j) * expf_scale);
       const float ang = vo_atan2deg(dy, dx);
       const float mag = __fsqrt_rn(fmaf(dx, dx, dy * dy));
       int bin = __float2int_rn((ORI_BINS / 360.f) * ang);
       if (bin >= ORI_BINS) bin -= ORI_BINS;
       if (bin < 0) bin += ORI_BINS;
       atomicAdd(&s_hist[wib][bin], (uint32_t)__float2int_rn(wgt * mag * SIFT_FIX));
+    };
+    int wi = lane / side - radius, wj = lane % side - radius;
+    for (int idx = lane; idx < total; idx += 64) {
+      OSamp s0, s1;
+      ofetch(wi, wj, s0);
+      wj += 32; while (wj > radius) { wj -= side; ++wi; }
+      s1.ok = false;
+      if (idx + 32 < total) ofetch(wi, wj, s1);
+      wj += 32; while (wj > radius) { wj -= side; ++wi; }
+      oaccum(s0);
+      oaccum(s1);
     }
     __syncwarp();
     float* th = s_sm[wib];   // th[i + 2] = raw bin i, with 2 wrapped entries on each side
@@ -1005,17 +1028,27 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
     for (int k = lane; k < DESC_COPIES * HLEN; k += 32) s_hist[wib][k] = 0;
     __syncwarp();
 
-    auto process = [&](int i, int j) {
-      const float c_rot = j * cos_t - i * sin_t;
-      const float r_rot = j * sin_t + i * cos_t;
-      float rbin = r_rot + D / 2 - 0.5f, cbin = c_rot + D / 2 - 0.5f;
+    // A sample is handled in two steps so that two samples per lane are in flight: fetch() applies the
+    // exact acceptance test of the contract (the row intervals below are only a superset) and issues
+    // the four gradient loads; accumulate() does the arithmetic and the trilinear scatter.
+    struct Samp { float c_rot, r_rot, rbin, cbin, xp, xm, yu, yd; bool ok; };
+    auto fetch = [&](int i, int j, Samp& sm) {
+      sm.c_rot = j * cos_t - i * sin_t;
+      sm.r_rot = j * sin_t + i * cos_t;
+      sm.rbin = sm.r_rot + D / 2 - 0.5f; sm.cbin = sm.c_rot + D / 2 - 0.5f;
       const int r = py + i, c = px + j;
-      // the exact acceptance test of the contract (the row intervals below are only a superset)
-      if (!(rbin > -1 && rbin < D && cbin > -1 && cbin < D && r > 0 && r < rows - 1 && c > 0 && c < cols - 1)) return;
-      const float* q = img + (size_t)r * pitch + c;
-      const float dx = q[1] - q[-1];
-      const float dy = q[-pitch] - q[pitch];
-      const float wgt = vo_expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
+      sm.ok = sm.rbin > -1 && sm.rbin < D && sm.cbin > -1 && sm.cbin < D && r > 0 && r < rows - 1 && c > 0 && c < cols - 1;
+      if (sm.ok) {
+        const float* q = img + (size_t)r * pitch + c;
+        sm.xp = __ldg(q + 1); sm.xm = __ldg(q - 1); sm.yu = __ldg(q - pitch); sm.yd = __ldg(q + pitch);
+      }
+    };
+    auto accumulate = [&](const Samp& sm) {
+      if (!sm.ok) return;
+      float rbin = sm.rbin, cbin = sm.cbin;
+      const float dx = sm.xp - sm.xm;
+      const float dy = sm.yu - sm.yd;
+      const float wgt = vo_expf((sm.c_rot * sm.c_rot + sm.r_rot * sm.r_rot) * exp_scale);
       const float a = vo_atan2deg(dy, dx);
       const float mag = __fsqrt_rn(fmaf(dx, dx, dy * dy)) * wgt;
       float obin = (a - ori) * bins_per_rad;
@@ -1041,6 +1074,7 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
       atomicAdd(hp + (D + 3) * (N + 2), (uint32_t)__float2int_rn(v110 * SIFT_FIX));
       atomicAdd(hp + (D + 3) * (N + 2) + 1, (uint32_t)__float2int_rn(v111 * SIFT_FIX));
     };
+    auto process = [&](int i, int j) { Samp sm; fetch(i, j, sm); accumulate(sm); };
 
     const int side = 2 * radius + 1, total = side * side;
     my_bytes += (unsigned long long)total * 4ull + 512ull;   // patch read + descriptor written
@@ -1083,9 +1117,17 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
       __syncwarp();
       const int ncand = carry;
       int row = 0;
-      for (int k = lane; k < ncand; k += 32) {
+      for (int k = lane; k < ncand; k += 64) {
+        Samp s0, s1;
         while (k >= s_rowoff[wib][row + 1]) ++row;
-        process(row - radius, (int)s_rowj[wib][row] + (k - s_rowoff[wib][row]));
+        fetch(row - radius, (int)s_rowj[wib][row] + (k - s_rowoff[wib][row]), s0);
+        s1.ok = false;
+        if (k + 32 < ncand) {
+          while (k + 32 >= s_rowoff[wib][row + 1]) ++row;
+          fetch(row - radius, (int)s_rowj[wib][row] + (k + 32 - s_rowoff[wib][row]), s1);
+        }
+        accumulate(s0);
+        accumulate(s1);
       }
     } else {
       // very large windows (non-default options): plain scan of the whole window
