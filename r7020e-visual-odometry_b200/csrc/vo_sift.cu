@@ -69,8 +69,9 @@ void sift_plan_destroy(SiftPlan* p) {
 __device__ __forceinline__ float vo_expf(float x) {
   const float t = x * 1.44269504088896341f;
   float n = rintf(t);
-  if (n < -126.f) return 0.f;
+  const bool under = n < -126.f;     // result is 0; evaluated branch-free with n clamped
   if (n > 127.f) n = 127.f;
+  if (under) n = -126.f;
   float r = fmaf(n, -0.693145751953125f, x);
   r = fmaf(n, -1.42860682030941723e-6f, r);
   float p = 1.0f / 720.0f;
@@ -80,7 +81,13 @@ __device__ __forceinline__ float vo_expf(float x) {
   p = fmaf(p, r, 0.5f);
   p = fmaf(p, r, 1.0f);
   p = fmaf(p, r, 1.0f);
-  return __int_as_float(__float_as_int(p) + (((int)n) << 23));
+  return under ? 0.f : __int_as_float(__float_as_int(p) + (((int)n) << 23));
+}
+
+// (uint32_t)__float2int_rn(v * 4096) for 0 <= v * 4096 < 2^22 without the conversion pipe: v * 4096 is
+// exact, so one fused multiply-add onto 1.5 * 2^23 rounds it to nearest-even into the mantissa.
+__device__ __forceinline__ uint32_t sift_fix(float v) {
+  return (uint32_t)__float_as_int(fmaf(v, SIFT_FIX, 12582912.f)) & 0x3FFFFFu;
 }
 
 __device__ __forceinline__ float vo_atan2deg(float y, float x) {
@@ -89,16 +96,12 @@ __device__ __forceinline__ float vo_atan2deg(float y, float x) {
   const float p5 = 0.1555786518463281f * 57.29577951308232f;
   const float p7 = -0.04432655554792128f * 57.29577951308232f;
   const float ax = fabsf(x), ay = fabsf(y);
-  float a, c, c2;
-  if (ax >= ay) {
-    c = __fdiv_rn(ay, ax + 2.220446049250313e-16f);
-    c2 = c * c;
-    a = fmaf(fmaf(fmaf(p7, c2, p5), c2, p3), c2, p1) * c;
-  } else {
-    c = __fdiv_rn(ax, ay + 2.220446049250313e-16f);
-    c2 = c * c;
-    a = 90.f - fmaf(fmaf(fmaf(p7, c2, p5), c2, p3), c2, p1) * c;
-  }
+  // branch-free form of: ax >= ay ? poly(ay / (ax + eps)) : 90 - poly(ax / (ay + eps)) (same operations)
+  const bool xbig = ax >= ay;
+  const float c = __fdiv_rn(xbig ? ay : ax, (xbig ? ax : ay) + 2.220446049250313e-16f);
+  const float c2 = c * c;
+  const float pa = fmaf(fmaf(fmaf(p7, c2, p5), c2, p3), c2, p1) * c;
+  float a = xbig ? pa : 90.f - pa;
   if (x < 0) a = 180.f - a;
   if (y < 0) a = 360.f - a;
   return a;
@@ -1028,9 +1031,10 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
     for (int k = lane; k < DESC_COPIES * HLEN; k += 32) s_hist[wib][k] = 0;
     __syncwarp();
 
-    // A sample is handled in two steps so that two samples per lane are in flight: fetch() applies the
-    // exact acceptance test of the contract (the row intervals below are only a superset) and issues
-    // the four gradient loads; accumulate() does the arithmetic and the trilinear scatter.
+    // fetch() applies the exact acceptance test of the contract (the row intervals below are only a
+    // superset) and issues the four gradient loads; accumulate() does the arithmetic and the trilinear
+    // scatter.  (Keeping two samples per lane in flight was measured slower: the kernel is issue-bound,
+    // and the extra registers cost occupancy.)
     struct Samp { float c_rot, r_rot, rbin, cbin, xp, xm, yu, yd; bool ok; };
     auto fetch = [&](int i, int j, Samp& sm) {
       sm.c_rot = j * cos_t - i * sin_t;
@@ -1065,14 +1069,14 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
       const float v011 = v_rc01 * obin, v010 = v_rc01 - v011;
       const float v001 = v_rc00 * obin, v000 = v_rc00 - v001;
       uint32_t* hp = hist + ((r0 + 1) * (D + 2) + c0 + 1) * (N + 2) + o0;
-      atomicAdd(hp, (uint32_t)__float2int_rn(v000 * SIFT_FIX));
-      atomicAdd(hp + 1, (uint32_t)__float2int_rn(v001 * SIFT_FIX));
-      atomicAdd(hp + (N + 2), (uint32_t)__float2int_rn(v010 * SIFT_FIX));
-      atomicAdd(hp + (N + 3), (uint32_t)__float2int_rn(v011 * SIFT_FIX));
-      atomicAdd(hp + (D + 2) * (N + 2), (uint32_t)__float2int_rn(v100 * SIFT_FIX));
-      atomicAdd(hp + (D + 2) * (N + 2) + 1, (uint32_t)__float2int_rn(v101 * SIFT_FIX));
-      atomicAdd(hp + (D + 3) * (N + 2), (uint32_t)__float2int_rn(v110 * SIFT_FIX));
-      atomicAdd(hp + (D + 3) * (N + 2) + 1, (uint32_t)__float2int_rn(v111 * SIFT_FIX));
+      atomicAdd(hp, sift_fix(v000));
+      atomicAdd(hp + 1, sift_fix(v001));
+      atomicAdd(hp + (N + 2), sift_fix(v010));
+      atomicAdd(hp + (N + 3), sift_fix(v011));
+      atomicAdd(hp + (D + 2) * (N + 2), sift_fix(v100));
+      atomicAdd(hp + (D + 2) * (N + 2) + 1, sift_fix(v101));
+      atomicAdd(hp + (D + 3) * (N + 2), sift_fix(v110));
+      atomicAdd(hp + (D + 3) * (N + 2) + 1, sift_fix(v111));
     };
     auto process = [&](int i, int j) { Samp sm; fetch(i, j, sm); accumulate(sm); };
 
@@ -1117,17 +1121,9 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
       __syncwarp();
       const int ncand = carry;
       int row = 0;
-      for (int k = lane; k < ncand; k += 64) {
-        Samp s0, s1;
+      for (int k = lane; k < ncand; k += 32) {
         while (k >= s_rowoff[wib][row + 1]) ++row;
-        fetch(row - radius, (int)s_rowj[wib][row] + (k - s_rowoff[wib][row]), s0);
-        s1.ok = false;
-        if (k + 32 < ncand) {
-          while (k + 32 >= s_rowoff[wib][row + 1]) ++row;
-          fetch(row - radius, (int)s_rowj[wib][row] + (k + 32 - s_rowoff[wib][row]), s1);
-        }
-        accumulate(s0);
-        accumulate(s1);
+        process(row - radius, (int)s_rowj[wib][row] + (k - s_rowoff[wib][row]));
       }
     } else {
       // very large windows (non-default options): plain scan of the whole window
