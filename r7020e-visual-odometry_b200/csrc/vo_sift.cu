@@ -37,6 +37,7 @@ constexpr float SIFT_INV_FIX = 1.0f / 4096.0f;
 constexpr int TILE_W = 128, TILE_H = 32;
 
 struct Taps { float k[MAX_R + 1]; int r; };
+struct OctInfo { int h[MAX_OCT], w[MAX_OCT], pitch[MAX_OCT]; size_t goff[MAX_OCT], doff[MAX_OCT]; };
 
 struct SiftPlan {
   int rows = 0, cols = 0, batch = 0, nl = 0;
@@ -624,6 +625,65 @@ sift_downsample_kernel(const float* __restrict__ src, float* __restrict__ dst, i
   if (x < dw) dst[(size_t)b * dh * dpitch + (size_t)y * dpitch + x] = __ldg(src + (size_t)b * sh * spitch + (size_t)(2 * y) * spitch + 2 * x);
 }
 
+// ------------------------------------------------------ small octaves: one launch for all of them
+// Octaves too small for the streaming kernels (a few thousand pixels and less) used to cost one
+// launch per layer.  Here one block per image builds ALL of them: layer 0 of each octave is the 2x
+// decimation of the previous octave's layer nl, then each layer is blurred from the previous one
+// entirely in shared memory (row pass, column pass, reflect-101), written to the Gaussian stack and
+// differenced into the DoG stack.  Same operations in the same order as sift_blur_dog_kernel.
+struct TapsAll { Taps t[8]; };
+__global__ void __launch_bounds__(512)
+sift_small_octaves_kernel(float* __restrict__ gauss, float* __restrict__ dog, const OctInfo oi, int first_oct,
+                          int n_oct, int nl, int batch_stride, int cap, const TapsAll taps) {
+  extern __shared__ float ssm[];
+  float* A = ssm; float* B = ssm + cap; float* T = ssm + 2 * cap;
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  for (int o = first_oct; o < n_oct; ++o) {
+    const int h = oi.h[o], w = oi.w[o], pitch = oi.pitch[o];
+    const size_t lstride = (size_t)batch_stride * h * pitch;
+    float* g0 = gauss + oi.goff[o] + (size_t)b * h * pitch;
+    float* d0 = dog + oi.doff[o] + (size_t)b * h * pitch;
+    const int n = h * w;
+    if (o == 0) {
+      for (int idx = tid; idx < n; idx += nt) { const int y = idx / w, x = idx - y * w; A[idx] = g0[(size_t)y * pitch + x]; }
+    } else {
+      const int hp = oi.h[o - 1], pp = oi.pitch[o - 1];
+      const float* src = gauss + oi.goff[o - 1] + (size_t)nl * batch_stride * hp * pp + (size_t)b * hp * pp;
+      for (int idx = tid; idx < n; idx += nt) {
+        const int y = idx / w, x = idx - y * w;
+        const float v = src[(size_t)(2 * y) * pp + 2 * x];
+        A[idx] = v;
+        g0[(size_t)y * pitch + x] = v;
+      }
+    }
+    __syncthreads();
+    for (int i = 1; i < nl + 3; ++i) {
+      const Taps& tp = taps.t[i];
+      const int R = tp.r;
+      for (int idx = tid; idx < n; idx += nt) {
+        const int y = idx / w, x = idx - y * w;
+        const float* row = A + y * w;
+        float acc = tp.k[0] * row[x];
+        for (int j = 1; j <= R; ++j) acc = fmaf(tp.k[j], row[reflect101(x - j, w)] + row[reflect101(x + j, w)], acc);
+        T[idx] = acc;
+      }
+      __syncthreads();
+      float* gi = g0 + (size_t)i * lstride;
+      float* di = d0 + (size_t)(i - 1) * lstride;
+      for (int idx = tid; idx < n; idx += nt) {
+        const int y = idx / w, x = idx - y * w;
+        float acc = tp.k[0] * T[idx];
+        for (int j = 1; j <= R; ++j) acc = fmaf(tp.k[j], T[reflect101(y - j, h) * w + x] + T[reflect101(y + j, h) * w + x], acc);
+        B[idx] = acc;
+        gi[(size_t)y * pitch + x] = acc;
+        di[(size_t)y * pitch + x] = acc - A[idx];
+      }
+      __syncthreads();
+      float* t2 = A; A = B; B = t2;
+    }
+  }
+}
+
 // ----------------------------------------------------------------------- extrema detection
 // 3x3x3 extrema of the DoG stack, separable and barrier-free.  A pixel of layer l is a maximum iff
 // val >= max3x3(l-1), max3x3(l), max3x3(l+1) (its own 3x3 max contains val itself), symmetrically
@@ -653,11 +713,22 @@ sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int batch, int h
   for (int l = 0; l < L; ++l) { hxA[l] = hxB[l] = hxC[l] = hnA[l] = hnB[l] = hnC[l] = cB[l] = cC[l] = 0.f; }
   const bool col_ok = lane >= 1 && lane <= EX_COLS && x >= SIFT_BORDER && x < w - SIFT_BORDER;
   const int y_end = min(y0 + EX_ROWS, h - SIFT_BORDER);    // last row (exclusive) that can hold a keypoint
+  // the next row's values are loaded one iteration ahead, so the shuffles never wait on HBM
+  float nxt[L];
+  {
+    const size_t off = (size_t)min(max(y0 - 1, 0), h - 1) * pitch;
+#pragma unroll
+    for (int l = 0; l < L; ++l) nxt[l] = __ldg(img + (size_t)l * layer_stride + off);
+  }
   for (int r = y0 - 1; r <= y_end; ++r) {
-    const int rc = min(max(r, 0), h - 1);
     float v[L];
 #pragma unroll
-    for (int l = 0; l < L; ++l) v[l] = __ldg(img + (size_t)l * layer_stride + (size_t)rc * pitch);
+    for (int l = 0; l < L; ++l) v[l] = nxt[l];
+    if (r < y_end) {
+      const size_t off = (size_t)min(max(r + 1, 0), h - 1) * pitch;
+#pragma unroll
+      for (int l = 0; l < L; ++l) nxt[l] = __ldg(img + (size_t)l * layer_stride + off);
+    }
 #pragma unroll
     for (int l = 0; l < L; ++l) {
       const float lf = __shfl_up_sync(0xffffffffu, v[l], 1), rt = __shfl_down_sync(0xffffffffu, v[l], 1);
@@ -699,7 +770,6 @@ sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int batch, int h
 }
 
 // --------------------------------------------------------- refinement + orientation (warp/cand)
-struct OctInfo { int h[MAX_OCT], w[MAX_OCT], pitch[MAX_OCT]; size_t goff[MAX_OCT], doff[MAX_OCT]; };
 
 __global__ void __launch_bounds__(128)
 sift_refine_orient_kernel(const float* __restrict__ gauss, const float* __restrict__ dog, const OctInfo oi,
@@ -1367,7 +1437,16 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
     VO_TRY((launch_blur_t<0, true>(nullptr, p->img, p->G(0, 0), nullptr, p->h[0], p->w[0], p->pitch[0], p->rows, p->cols, batch, p->base_taps, st)));
   delete ps_base;
   // note: layer_elems uses p->batch; kernels index images with the plan's batch stride
-  for (int oc = 0; oc < p->n_oct; ++oc) {
+  OctInfo oi;
+  memset(&oi, 0, sizeof(oi));
+  for (int oc = 0; oc < p->n_oct; ++oc) { oi.h[oc] = p->h[oc]; oi.w[oc] = p->w[oc]; oi.pitch[oc] = p->pitch[oc]; oi.goff[oc] = p->goff[oc]; oi.doff[oc] = p->doff[oc]; }
+  // octaves from first_small on go to the fused shared-memory kernel (when one octave fits: 3 buffers)
+  int first_small = p->n_oct;
+  for (int oc = 0; oc < p->n_oct; ++oc)
+    if (!(p->h[oc] >= 64 && p->w[oc] >= 96)) { first_small = oc; break; }
+  const int small_cap = first_small < p->n_oct ? p->h[first_small] * p->w[first_small] : 0;
+  const bool fuse_small = first_small < p->n_oct && (size_t)small_cap * 12 <= 200 * 1024;
+  for (int oc = 0; oc < (fuse_small ? first_small : p->n_oct); ++oc) {
     const double px = (double)batch * p->h[oc] * p->w[oc];
     if (oc > 0) {
       ProfScope ps(ctx, st, "sift_downsample", px * 8.0);
@@ -1380,6 +1459,21 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
       ProfScope ps(ctx, st, nm, px * 12.0);   // read G[l], write G[l+1], write D[l]
       VO_TRY(launch_blur(p->tm_gauss[oc], (i - 1) * p->batch, p->G(oc, i - 1), p->G(oc, i), p->D(oc, i - 1), p->h[oc], p->w[oc], p->pitch[oc], batch, p->taps[i], ctx->num_sms, st));
     }
+  }
+  if (fuse_small) {
+    double px = 0;
+    for (int oc = first_small; oc < p->n_oct; ++oc) px += (double)batch * p->h[oc] * p->w[oc];
+    TapsAll ta;
+    memset(&ta, 0, sizeof(ta));
+    for (int i = 1; i < nl + 3; ++i) ta.t[i] = p->taps[i];
+    const size_t smem = (size_t)small_cap * 12;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+      VO_CUDA(cudaFuncSetAttribute(sift_small_octaves_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem = smem;
+    }
+    ProfScope ps(ctx, st, "sift_blur_dog_small", px * (8.0 + 12.0 * (nl + 2)));
+    sift_small_octaves_kernel<<<batch, 512, smem, st>>>(p->gauss, p->dog, oi, first_small, p->n_oct, nl, p->batch, small_cap, ta);
   }
   VO_CUDA(cudaGetLastError());
   // extrema
@@ -1399,9 +1493,6 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
     }
 #undef VO_EXTREMA
   }
-  OctInfo oi;
-  memset(&oi, 0, sizeof(oi));
-  for (int oc = 0; oc < p->n_oct; ++oc) { oi.h[oc] = p->h[oc]; oi.w[oc] = p->w[oc]; oi.pitch[oc] = p->pitch[oc]; oi.goff[oc] = p->goff[oc]; oi.doff[oc] = p->doff[oc]; }
   {
     dim3 g(ctx->num_sms * 4 / (batch > 4 ? 4 : 1), batch);
     ProfScope ps(ctx, st, "sift_refine_orient");
