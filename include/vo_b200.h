@@ -115,8 +115,17 @@ int vo_match_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, 
 int vo_match_top2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, int n2,
                       int dim, uint32_t* j1_dev, float* s1_dev, float* s2_dev, void* stream);
 
+/* Relocalisation shard (BASELINE config 5): one 16-byte record per query row,
+ * records_dev[n1] = {uint32 j1, float s1, float s2, uint32 keep}.  keep = 1 iff the row passes the
+ * MatchThreshold and MaxRatio tests of `opts` (then j1/s1 are exactly matchFeatures' pair and metric;
+ * rows with keep = 0 carry j1 = UINT32_MAX, and s2 may be a lower bound of the second-nearest score).
+ * Query rows are independent, so a row-sharded run followed by an all-gather of the records equals
+ * the unsharded result. */
+int vo_match_best2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, int n2, int dim,
+                       const vo_match_opts* opts, void* records_dev, void* stream);
+
 /* counters of the last vo_match / vo_match_top2 call on this ctx (after synchronisation):
- * stats[0] = 1 if the exact-integer bf16 path ran (0: split-bf16 general path),
+ * stats[0] = 1 if the exact-integer u8 path ran (0: split-bf16 general path),
  * stats[1] = rows re-evaluated by the exact FP32 row scan, stats[2] = GEMM kernel launches,
  * stats[3] = K extent of the GEMM. */
 int vo_match_stats(vo_ctx* ctx, int stats[4]);

@@ -1019,6 +1019,17 @@ match_scatter_kernel(const uint32_t* __restrict__ j1, const float* __restrict__ 
   }
 }
 
+// 16-byte best-2 record per query row (the unit the relocalisation shards all-gather):
+// {j1, s1, s2, keep} with keep = 1 iff the row passes the threshold and ratio tests.
+__global__ void __launch_bounds__(256)
+match_records_kernel(const uint32_t* __restrict__ j1, const float* __restrict__ s1, const float* __restrict__ s2,
+                     int n1, int n2, float thr, float max_ratio, int index_base, uint4* __restrict__ rec) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n1) return;
+  const bool keep = n2 > 0 && keep_row(s1[i], s2[i], n2, thr, max_ratio);
+  rec[i] = make_uint4(keep ? j1[i] + (uint32_t)index_base : 0xFFFFFFFFu, __float_as_uint(s1[i]), __float_as_uint(s2[i]), keep ? 1u : 0u);
+}
+
 // --------------------------------------------------------------------------- host plumbing
 static int make_operand_map(CUtensorMap* map, const __nv_bfloat16* base, int rows_alloc, int kp, int n_prob, int box_rows) {
   EncodeTiledFn enc = get_encode_tiled();
@@ -1323,6 +1334,25 @@ int vo_match_top2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_
   VO_CUDA(cudaMemcpyAsync(j1_dev, t.j1, (size_t)n1 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   VO_CUDA(cudaMemcpyAsync(s1_dev, t.s1, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   VO_CUDA(cudaMemcpyAsync(s2_dev, t.s2, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return VO_OK;
+}
+
+int vo_match_best2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, int n2, int dim,
+                       const vo_match_opts* opts, void* records_dev, void* stream) {
+  VO_CHECK_ARG(ctx && records_dev, "ctx/records_dev is null");
+  VO_CHECK_ARG(n1 >= 0 && n2 >= 0 && dim > 0, "negative size");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n1 == 0) return VO_OK;
+  vo_match_opts o; fill_match_opts(opts, &o);
+  Single s; VO_TRY(single_operands(ctx, f1_dev, n1, f2_dev, n2, 0, "f", st, &s));
+  MatchTop2 t;
+  const MatchFilter flt = make_match_filter(o);
+  VO_TRY(match_batch_top2(ctx, s.A, s.B, 1, dim, "f", nullptr, st, &t, &flt));
+  match_records_kernel<<<div_up(n1, 256), 256, 0, st>>>(t.j1, t.s1, t.s2, n1, n2, o.match_threshold * 0.04f, o.max_ratio,
+                                                        o.index_base, static_cast<uint4*>(records_dev));
+  ctx->kernel_launches += 1;
+  VO_CUDA(cudaGetLastError());
   return VO_OK;
 }
 

@@ -89,3 +89,40 @@ def match_top2_row_sharded(queries, landmarks, match_top2_fn, rank, world, dist=
         a = t[: h - l].cpu().numpy()
         J.append(a[:, 0].copy().view(np.uint32)); S1.append(a[:, 1].copy()); S2.append(a[:, 2].copy())
     return np.concatenate(J), np.concatenate(S1), np.concatenate(S2)
+
+
+def relocalise_row_sharded_dev(ctx, queries_dev, landmarks_dev, rank, world, dist=None, opts=None):
+    """Device-resident relocalisation match (BASELINE config 5).  queries_dev: this rank's slice
+    [n1_local, 128] float32 CUDA tensor (row_chunks(n1, world)[rank] of the full query set),
+    landmarks_dev: [n2, 128] float32 CUDA tensor, replicated.  Each rank runs the tcgen05 match on its
+    rows (vo_match_best2_dev: one 16-byte record {j1, s1, s2, keep} per row); one NCCL all-gather of the
+    records assembles every row on every rank.  Returns (records [n1_total, 4] int32 CUDA tensor --
+    columns 1, 2 are float32 bit patterns -- and the per-rank row counts)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    n1, n2 = int(queries_dev.shape[0]), int(landmarks_dev.shape[0])
+    rec = torch.empty((max(n1, 1), 4), dtype=torch.int32, device=queries_dev.device)
+    mo = None
+    if opts is not None:
+        mo = _lib.MatchOpts(*opts)
+    _lib.check(_lib.lib().vo_match_best2_dev(ctx.handle, C.c_void_p(queries_dev.data_ptr()), n1,
+                                             C.c_void_p(landmarks_dev.data_ptr()), n2, int(queries_dev.shape[1]),
+                                             C.byref(mo) if mo is not None else None, C.c_void_p(rec.data_ptr()),
+                                             C.c_void_p(ctx.stream)))
+    if world == 1:
+        ctx.sync()
+        return rec[:n1], [n1]
+    # ranks may hold different row counts: gather the counts, pad to the widest slice
+    cnt = torch.tensor([n1], dtype=torch.int64, device=queries_dev.device)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    ctx.sync()                              # the match ran on the library's stream
+    dist.all_gather(cnts, cnt)
+    counts = [int(c.item()) for c in cnts]
+    width = max(counts)
+    if rec.shape[0] < width:
+        pad = torch.zeros((width, 4), dtype=torch.int32, device=rec.device); pad[:n1] = rec[:n1]; rec = pad
+    out = torch.empty((world * width, 4), dtype=torch.int32, device=rec.device)
+    dist.all_gather_into_tensor(out, rec[:width].contiguous())
+    parts = [out[r * width: r * width + counts[r]] for r in range(world)]
+    return torch.cat(parts, 0), counts

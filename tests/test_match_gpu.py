@@ -132,3 +132,26 @@ def test_large_linearity_property(ctx):
     assert np.array_equal(j1, perm.astype(np.uint32))
     assert float(s1.max()) <= 1e-6          # 2 - 2c with c one or two ulps below 1
     assert float(s2.min()) > 0.1
+
+
+def test_best2_records_row_sharded_equals_unsharded(ctx):
+    """BASELINE config 5 in miniature: 16-byte best-2 records of row shards, concatenated (what the
+    all-gather does), equal the unsharded records; kept rows equal matchFeatures' pairs and metric."""
+    import ctypes as C
+    import torch
+    from vo_b200 import _lib, shard
+    f1, f2 = correlated_pair(1500, 2300, seed=41)
+    q = torch.from_numpy(f1).cuda(); l = torch.from_numpy(f2).cuda()
+    full, _ = shard.relocalise_row_sharded_dev(ctx, q, l, 0, 1)
+    parts = []
+    for lo, hi in shard.row_chunks(len(f1), 3):
+        rec, _ = shard.relocalise_row_sharded_dev(ctx, q[lo:hi].contiguous(), l, 0, 1)
+        parts.append(rec.clone())
+    full, cat = full.cpu().numpy(), torch.cat(parts, 0).cpu().numpy()
+    keep = full[:, 3] == 1
+    assert np.array_equal(keep, cat[:, 3] == 1)
+    assert np.array_equal(full[keep], cat[keep])
+    opairs, ometric = oracle.match(f1, f2)
+    assert np.array_equal(np.nonzero(keep)[0].astype(np.uint32), opairs[:, 0])
+    assert np.array_equal(full[keep, 0].view(np.uint32), opairs[:, 1])
+    assert np.array_equal(full[keep, 1].view(np.uint32), ometric.view(np.uint32))
