@@ -34,6 +34,26 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+# The driver parses stdout for ONE JSON line.  Libraries (NCCL prints its version banner) write to
+# file descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON
+# line goes to a private duplicate of the original stdout.
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 H, W = 376, 1241
 METRIC = "kitti_stereo_frames_per_s_end_to_end"
 UNIT = "frames/s"
@@ -172,7 +192,7 @@ def run_reference(args, rank, world):
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
                                   sample=f"{n} frames (+1 halo) per step, one process per core"),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ GPU legs
@@ -381,7 +401,7 @@ def run_ours(args, rank, world, local_rank):
             line["match_gemm"] = dict(error=str(e))
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_oracle_sample()
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -395,6 +415,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -20,6 +20,7 @@
  */
 #ifndef VO_B200_H
 #define VO_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -159,6 +160,15 @@ typedef struct {
 int vo_p3p(vo_ctx* ctx, const double* img, const double* world, int n, int col_major,
            const double K[4], const vo_p3p_opts* opts, double A[16], uint8_t* inliers,
            int* status, int info[3]);
+
+/* ---------------------------------------------------------------------------- input staging */
+/* Replaces imageDatastore / readimage (VO.m:16-17, 71-72) for KITTI odometry frames: 8-bit grayscale,
+ * non-interlaced PNG.  Host code (zlib inflate + PNG row filters); other PNG flavours are rejected.
+ * vo_png_read_batch decodes n files with n_threads workers (<= 0: one per hardware thread) into
+ * out[n][rows][cols] -- typically the pinned batch buffer handed to vo_frames. */
+int vo_png_info(const uint8_t* file, size_t n_bytes, int* rows, int* cols, int* bit_depth, int* color_type);
+int vo_png_decode_gray8(const uint8_t* file, size_t n_bytes, uint8_t* out, int ld, int rows, int cols);
+int vo_png_read_batch(const char* const* paths, int n, int rows, int cols, uint8_t* out, int n_threads);
 
 /* ------------------------------------------------------------------------- frame pipeline */
 typedef struct {

@@ -1,0 +1,107 @@
+"""Input staging for the frame loop: the reference's ``imageDatastore`` /
+``readimage`` (VO.m:16-17, 71-72) for KITTI odometry frames, i.e. 8-bit grayscale PNG files.
+
+``ImageDatastore`` mirrors the two members VO.m uses (``Files``, ``readimage``); ``read_batch`` decodes
+many files with native worker threads (libvo_b200: zlib inflate + PNG row filters) into one
+contiguous -- optionally pinned -- batch buffer, and ``run_sequence`` overlaps decoding batch k+1 on
+the host with vo_frames on batch k."""
+import ctypes as C
+import glob
+import os
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+def png_info(data):
+    """(rows, cols, bit_depth, colour_type) of a PNG held in memory (bytes)."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    r, c, d, t = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    check(_lib.lib().vo_png_info(buf.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_size_t(len(buf)), C.byref(r), C.byref(c),
+                                 C.byref(d), C.byref(t)))
+    return r.value, c.value, d.value, t.value
+
+
+def png_decode(data):
+    """8-bit grayscale PNG (bytes) -> uint8 [rows, cols]."""
+    rows, cols, _, _ = png_info(data)
+    buf = np.frombuffer(data, dtype=np.uint8)
+    out = np.empty((rows, cols), dtype=np.uint8)
+    check(_lib.lib().vo_png_decode_gray8(buf.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_size_t(len(buf)),
+                                         out.ctypes.data_as(C.POINTER(C.c_uint8)), cols, rows, cols))
+    return out
+
+
+def read_batch(paths, rows=None, cols=None, out=None, threads=0):
+    """Decode ``paths`` into out[n, rows, cols] uint8 (allocated when None; pass a pinned buffer's
+    NumPy view to decode straight into page-locked memory).  The GIL is released while decoding."""
+    paths = [os.fspath(p) for p in paths]
+    if rows is None or cols is None:
+        with open(paths[0], "rb") as f:
+            rows, cols, _, _ = png_info(f.read(64))
+    n = len(paths)
+    if out is None:
+        out = np.empty((n, rows, cols), dtype=np.uint8)
+    assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size >= n * rows * cols
+    arr = (C.c_char_p * n)(*[p.encode() for p in paths])
+    check(_lib.lib().vo_png_read_batch(arr, n, rows, cols, out.ctypes.data_as(C.POINTER(C.c_uint8)), threads))
+    return out[:n] if out.ndim == 3 else out
+
+
+class ImageDatastore:
+    """imageDatastore(folder) as VO.m uses it: sorted ``Files`` and ``readimage(i)`` (1-based)."""
+
+    def __init__(self, location, pattern="*.png"):
+        self.Files = sorted(glob.glob(os.path.join(os.fspath(location), pattern)))
+
+    def __len__(self):
+        return len(self.Files)
+
+    def readimage(self, i):
+        with open(self.Files[i - 1], "rb") as f:
+            return png_decode(f.read())
+
+
+def run_sequence(left_files, right_files, P1, P2, batch=32, seed=0, threads=0, ctx=None, pinned=True):
+    """The VO.m loop over a stereo PNG sequence: frames are decoded ``batch`` at a time (plus the
+    one-frame halo) into two alternating batch buffers by a background thread while the GPU runs
+    vo_frames on the other one.  Returns (rel_pose [n,4,4], status [n], counts [n,8])."""
+    from . import vo
+    n = len(left_files)
+    assert len(right_files) == n and n > 0
+    with open(left_files[0], "rb") as f:
+        rows, cols, _, _ = png_info(f.read(64))
+    bufs = []
+    for _ in range(2):
+        if pinned:
+            import torch
+            t = torch.empty((2, batch + 1, rows, cols), dtype=torch.uint8).pin_memory()
+            bufs.append((t, t.numpy()))
+        else:
+            a = np.empty((2, batch + 1, rows, cols), dtype=np.uint8)
+            bufs.append((a, a))
+    chunks = [(max(b0 - 1, 0), min(b0 + batch, n)) for b0 in range(0, n, batch)]   # [lo, hi) with halo
+
+    def load(k, slot):
+        lo, hi = chunks[k]
+        read_batch(left_files[lo:hi], rows, cols, bufs[slot][1][0], threads)
+        read_batch(right_files[lo:hi], rows, cols, bufs[slot][1][1], threads)
+
+    rel = np.tile(np.eye(4), (n, 1, 1)); status = np.zeros(n, dtype=np.int32); counts = np.zeros((n, 8), dtype=np.int32)
+    load(0, 0)
+    for k, (lo, hi) in enumerate(chunks):
+        th = None
+        if k + 1 < len(chunks):
+            th = threading.Thread(target=load, args=(k + 1, (k + 1) & 1))
+            th.start()
+        m = hi - lo
+        a = bufs[k & 1][1]
+        r, s, c = vo.run_frames(a[0, :m], a[1, :m], P1, P2, seed=seed, first_frame=lo, ctx=ctx)
+        first = 0 if lo == 0 else 1          # the halo frame's outputs belong to the previous chunk
+        rel[lo + first:hi] = r[first:]; status[lo + first:hi] = s[first:]; counts[lo + first:hi] = c[first:]
+        if th is not None:
+            th.join()
+    return rel, status, counts
