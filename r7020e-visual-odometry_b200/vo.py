@@ -66,10 +66,47 @@ def find_remaining_points(ops, old, cur):
     return cur, old, lm, rm, (len(lm), len(rm), len(m3), len(m4))
 
 
-class VisualOdometry:
-    """State of the VO.m script: ``features`` (previous stereo-matched set), ``pose``, ``all_poses``."""
+def new_landmark_indices(l_loc, r_loc, old_l_loc, old_r_loc):
+    """VO.m:147-154: indices (0-based) of stereo-matched features that "did not exist in the previous
+    frame".  The reference tests ``isempty(find(old.Location == loc(index,:), 1))`` -- an N x 2 array
+    compared with a 1 x 2 row, so a feature is old as soon as ANY tracked point shares its x OR its y
+    coordinate, in the left or in the right image.  Mirrored literally (vectorised)."""
+    l_loc = np.asarray(l_loc); r_loc = np.asarray(r_loc)
+    old_l = np.asarray(old_l_loc).reshape(-1, 2); old_r = np.asarray(old_r_loc).reshape(-1, 2)
+    seen_l = np.isin(l_loc[:, 0], old_l[:, 0]) | np.isin(l_loc[:, 1], old_l[:, 1])
+    seen_r = np.isin(r_loc[:, 0], old_r[:, 0]) | np.isin(r_loc[:, 1], old_r[:, 1])
+    return np.nonzero(~seen_l & ~seen_r)[0]
 
-    def __init__(self, P1, P2, ops=None):
+
+def create_landmarks_from_features(ops, features_l, features_r, P1, P2, pose, current_landmarks):
+    """CreateLandmarksFromFeatures.m:1-21 with the per-point ``triangulate`` calls of its loop
+    batched into one GPU call.  Every second feature (i = 1:2:n) is triangulated, kept when
+    0 <= z <= 80 and moved to world coordinates with ``pose`` (4 x 4, premultiply convention);
+    skipped rows stay zero exactly like the reference's pre-sized ``zeros`` array
+    (``zeros(size(features_l, 2), 3)`` = 2 rows, grown by indexing)."""
+    features_l = np.asarray(features_l).reshape(-1, 2); features_r = np.asarray(features_r).reshape(-1, 2)
+    n = len(features_l)
+    picks = np.arange(0, n, 2)                                   # i = 1:2:n (1-based)
+    landmarks = np.zeros((2, 3))
+    if n:
+        coords = ops.triangulate(features_l[picks], features_r[picks], P1, P2)    # CreateLandmarksFromFeatures.m:7
+        keep = ~((coords[:, 2] < 0) | (coords[:, 2] > 80))                        # :9-15
+        if keep.any():
+            A = np.asarray(pose, dtype=np.float64)
+            # MATLAB grows the array (zero-filled) up to the last row actually written
+            landmarks = np.zeros((max(2, int(picks[keep][-1]) + 1), 3))
+            landmarks[picks[keep]] = coords[keep] @ A[:3, :3].T + A[:3, 3]        # :17 transformPointsForward
+    cur = np.asarray(current_landmarks, dtype=np.float64).reshape(-1, 3)
+    return np.vstack([cur, landmarks])                            # :20
+
+
+class VisualOdometry:
+    """State of the VO.m script: ``features`` (previous stereo-matched set), ``pose``, ``all_poses``;
+    with ``view_3D`` also the ``landmarks`` map of VO.m:145-161."""
+
+    def __init__(self, P1, P2, ops=None, view_3D=False):
+        self.view_3D = view_3D
+        self.landmarks = np.zeros((0, 3))
         self.p1 = np.asarray(P1, dtype=np.float64).reshape(3, 4)
         self.p2 = np.asarray(P2, dtype=np.float64).reshape(3, 4)
         # VO.m:35-38: intrinsics of the left camera from p1
@@ -100,6 +137,10 @@ class VisualOdometry:
             rel = r["A"]
             self.pose = self.pose @ rel                                        # VO.m:130
             self.all_poses.append(self.pose.copy())                            # VO.m:133
+            if self.view_3D:                                                   # VO.m:145-161
+                ml, mr = l_pos[matched[:, 0]], r_pos[matched[:, 1]]
+                idx = new_landmark_indices(ml, mr, old["l_pos"], old["r_pos"])
+                self.landmarks = create_landmarks_from_features(ops, ml[idx], mr[idx], self.p1, self.p2, self.pose, self.landmarks)
         self.features = dict(l_desc=l_desc[matched[:, 0]], r_desc=r_desc[matched[:, 1]],   # VO.m:141-144 / 207-210
                              l_pos=l_pos[matched[:, 0]], r_pos=r_pos[matched[:, 1]])
         self.log.append(rec)

@@ -110,3 +110,42 @@ def test_vo_loop_with_oracle_recovers_motion():
     assert np.allclose(rel[:3, 3], truth[:3, 3], atol=0.03) and np.allclose(rel[:3, :3], np.eye(3), atol=5e-3)
     assert len(o.all_poses) == 2 and np.allclose(o.all_poses[-1], o.all_poses[0] @ rel)
     assert o.log[-1]["k4"] <= o.log[-1]["k3"] <= min(o.log[-1]["k1"], o.log[-1]["k2"])
+
+
+def test_landmark_map_mirrors_the_reference_loop():
+    """VO.m:147-161 + CreateLandmarksFromFeatures.m, restated literally (scalar loops, MATLAB growth
+    semantics) and compared with the batched mirror in vo.py (oracle triangulation on both sides)."""
+    from vo_b200 import vo, synth
+    from oracle_ops import OracleOps
+    ops = OracleOps(seed=0)
+    rng = np.random.default_rng(3)
+    P1, P2 = np.asarray(synth.KITTI_P0, float).reshape(3, 4), np.asarray(synth.KITTI_P1, float).reshape(3, 4)
+    n = 41
+    X = np.column_stack([rng.uniform(-10, 10, n), rng.uniform(-2, 2, n), rng.uniform(2, 150, n)])
+    X[5, 2] = -4.0                                     # behind the camera
+    def proj(P):
+        h = np.c_[X, np.ones(n)] @ P.T
+        return (h[:, :2] / h[:, 2:]).astype(np.float32)
+    fl, fr = proj(P1), proj(P2)
+    ang = 0.3
+    pose = np.eye(4); pose[:3, :3] = [[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]]; pose[:3, 3] = [1, 2, 3]
+    cur = rng.normal(size=(4, 3))
+    for m in (n, n - 1, 1, 0):
+        got = vo.create_landmarks_from_features(ops, fl[:m], fr[:m], P1, P2, pose, cur)
+        lm = np.zeros((2, 3))                          # zeros(size(features_l, 2), 3)
+        for i in range(1, m + 1, 2):                   # for i = 1:2:size(features_l, 1)
+            c = ops.triangulate(fl[i - 1:i], fr[i - 1:i], P1, P2)[0]
+            if c[2] < 0 or c[2] > 80:
+                continue
+            if i > len(lm):
+                lm = np.vstack([lm, np.zeros((i - len(lm), 3))])
+            lm[i - 1] = pose[:3, :3] @ c + pose[:3, 3]
+        want = np.vstack([cur, lm])
+        assert got.shape == want.shape, (m, got.shape, want.shape)
+        assert np.allclose(got, want, rtol=0, atol=1e-9)
+    # new-landmark selection: "old" as soon as any tracked point shares the x OR the y coordinate
+    l = np.array([[1., 2.], [3., 4.], [5., 6.], [7., 8.]]); r = l + 100
+    old_l = np.array([[3., 99.], [50., 6.]]); old_r = np.array([[107., 0.]])
+    idx = vo.new_landmark_indices(l, r, old_l, old_r)
+    want = [k for k in range(4) if not (old_l == l[k]).any() and not (old_r == r[k]).any()]
+    assert idx.tolist() == want == [0]

@@ -49,3 +49,30 @@ def test_vo_frames_equals_loop(ctx):
     # batching invariance: cutting the sequence with a one-frame halo gives the same poses
     rel2, _, _ = vo.run_frames(left[2:], right[2:], synth.KITTI_P0, synth.KITTI_P1, seed=5, first_frame=2, ctx=ctx)
     assert np.array_equal(rel2[1:], rel[3:])
+
+
+def test_landmark_map_and_png_sequence(ctx, tmp_path):
+    """Rows N1 + N3 of SURVEY 8f: the landmark map of VO.m:145-161 (view_3D) built with the GPU
+    triangulator equals the oracle-operator run; a PNG sequence decoded by the native reader and run
+    through the double-buffered sequence runner equals vo_frames on the in-memory arrays."""
+    import os
+    cv2 = pytest.importorskip("cv2")
+    from vo_b200 import vo, synth, io
+    left, right = _frames(5, seed=13)
+    g = vo.VisualOdometry(synth.KITTI_P0, synth.KITTI_P1, vo.CudaOps(ctx=ctx, seed=5), view_3D=True)
+    o = vo.VisualOdometry(synth.KITTI_P0, synth.KITTI_P1, OracleOps(seed=5), view_3D=True)
+    for i in range(3):
+        g.step(left[i], right[i]); o.step(left[i], right[i])
+    assert g.landmarks.shape == o.landmarks.shape and len(g.landmarks) > 10
+    assert np.allclose(g.landmarks, o.landmarks, rtol=1e-4, atol=1e-6)     # triangulation tolerance of the north star
+    nz = g.landmarks[np.abs(g.landmarks).sum(1) > 0]
+    assert len(nz) > 5 and (nz[:, 2] > 0).all()
+    lf, rf = [], []
+    for i in range(5):
+        for name, arr, lst in (("image_0", left, lf), ("image_1", right, rf)):
+            os.makedirs(os.path.join(tmp_path, name), exist_ok=True)
+            p = os.path.join(tmp_path, name, f"{i:06d}.png")
+            assert cv2.imwrite(p, arr[i]); lst.append(p)
+    rel, status, counts = io.run_sequence(lf, rf, synth.KITTI_P0, synth.KITTI_P1, batch=2, seed=5, ctx=ctx)
+    rel0, status0, counts0 = vo.run_frames(left, right, synth.KITTI_P0, synth.KITTI_P1, seed=5, ctx=ctx)
+    assert np.array_equal(rel, rel0) and np.array_equal(status, status0) and np.array_equal(counts, counts0)
