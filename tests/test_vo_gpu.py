@@ -76,3 +76,29 @@ def test_landmark_map_and_png_sequence(ctx, tmp_path):
     rel, status, counts = io.run_sequence(lf, rf, synth.KITTI_P0, synth.KITTI_P1, batch=2, seed=5, ctx=ctx)
     rel0, status0, counts0 = vo.run_frames(left, right, synth.KITTI_P0, synth.KITTI_P1, seed=5, ctx=ctx)
     assert np.array_equal(rel, rel0) and np.array_equal(status, status0) and np.array_equal(counts, counts0)
+
+
+def test_trajectory_parity_on_kitti_ground_truth_motion(ctx):
+    """North-star trajectory criterion: KITTI t_err / r_err of the CUDA path within 2 % of the oracle
+    path on the same frames.  Frames are rendered (textured planes, exact stereo geometry) along the
+    first poses of the reference's own ground truth kitti/poses/00.txt (golden fixture)."""
+    import os
+    pytest.importorskip("cv2")
+    from vo_b200 import vo, synth, kitti_eval
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "kitti00_reference_data.npz"))
+    n = 6
+    gt = np.tile(np.eye(4), (n, 1, 1)); gt[:, :3, :] = d["poses"][:n]
+    left, right = synth.plane_world(gt, seed=7)
+    rel, status, counts = vo.run_frames(left, right, synth.KITTI_P0, synth.KITTI_P1, seed=9, ctx=ctx)
+    assert (status == 0).all() and (counts[1:, 6] >= 20).all(), (status, counts[:, 6])
+    est_gpu = np.array([np.eye(4)] + vo.chain_poses(rel[1:]))
+    o = vo.VisualOdometry(synth.KITTI_P0, synth.KITTI_P1, OracleOps(seed=9))
+    for i in range(n):
+        o.step(left[i], right[i])
+    est_cpu = np.array([np.eye(4)] + o.all_poses)
+    lengths = (1.0, 2.0, 3.0)
+    tg, rg, ng = kitti_eval.kitti_errors(est_gpu, gt, lengths=lengths, step=1)
+    tc, rc, nc = kitti_eval.kitti_errors(est_cpu, gt, lengths=lengths, step=1)
+    assert ng == nc and ng >= 6
+    assert abs(tg - tc) <= 0.02 * tc + 1e-12 and abs(rg - rc) <= 0.02 * rc + 1e-12, (tg, tc, rg, rc)
+    assert tg < 0.10, tg                               # and the odometry itself is sane: < 10 % drift
