@@ -990,6 +990,63 @@ sift_rank_kernel(const vo_keypoint* __restrict__ raw, int kp_cap, const int* __r
   if (i < n) sorted[(size_t)b * kp_cap + rank] = me;
 }
 
+// Bucketed rank sort, one block per image.  The order is dominated by x, so keypoints are first
+// counted into SORT_BUCKETS buckets of x (monotone in x, hence consistent with the full order), a block
+// scan gives each bucket's first rank, and an element's rank inside its bucket is the number of
+// bucket mates that precede it under kp_before (a handful of comparisons instead of n).
+constexpr int SORT_BUCKETS = 2048;
+__global__ void __launch_bounds__(1024)
+sift_rank_bucket_kernel(const vo_keypoint* __restrict__ raw, int kp_cap, const int* __restrict__ counters,
+                        vo_keypoint* __restrict__ sorted, float x_scale) {
+  extern __shared__ int srt[];                 // start[SORT_BUCKETS + 1], fill[SORT_BUCKETS], perm[kp_cap] (u16 pairs)
+  int* start = srt;
+  int* fill = srt + SORT_BUCKETS + 1;
+  unsigned short* perm = reinterpret_cast<unsigned short*>(fill + SORT_BUCKETS);
+  __shared__ int warp_sums[32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = min(counters[b * 4 + 1], kp_cap);
+  const vo_keypoint* src = raw + (size_t)b * kp_cap;
+  for (int k = tid; k <= SORT_BUCKETS; k += 1024) { start[k] = 0; if (k < SORT_BUCKETS) fill[k] = 0; }
+  __syncthreads();
+  auto bucket_of = [&](float x) { return min(SORT_BUCKETS - 1, max(0, (int)(x * x_scale))); };
+  for (int i = tid; i < n; i += 1024) atomicAdd(&start[bucket_of(src[i].x) + 1], 1);
+  __syncthreads();
+  // inclusive scan of start[1..SORT_BUCKETS] (2 entries per thread)
+  {
+    const int a0 = start[2 * tid + 1], a1 = start[2 * tid + 2];
+    int x = a0 + a1;
+    const int lane = tid & 31, w = tid >> 5;
+    for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+    if (lane == 31) warp_sums[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int v = warp_sums[lane];
+      for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += y; }
+      warp_sums[lane] = v;
+    }
+    __syncthreads();
+    const int incl = x + (w ? warp_sums[w - 1] : 0);
+    start[2 * tid + 1] = incl - a1;
+    start[2 * tid + 2] = incl;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += 1024) {
+    const int bk = bucket_of(src[i].x);
+    perm[start[bk] + atomicAdd(&fill[bk], 1)] = (unsigned short)i;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += 1024) {
+    const vo_keypoint me = src[i];
+    const int bk = bucket_of(me.x);
+    int rank = start[bk];
+    for (int q = start[bk]; q < start[bk + 1]; ++q) {
+      const int j = perm[q];
+      if (j != i) rank += kp_before(src[j], j, me, i) ? 1 : 0;
+    }
+    sorted[(size_t)b * kp_cap + rank] = me;
+  }
+}
+
 // one block per image: drop exact duplicates (x, y, size, angle), compact, apply the first-octave
 // (-1) adjustment: pt *= 0.5, size *= 0.5, octave word - 1
 __global__ void __launch_bounds__(1024)
@@ -1501,7 +1558,18 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
   {
     dim3 g(p->kp_cap / 256, batch);
     ProfScope ps(ctx, st, "sift_sort_dedupe", 0.0, 0.0, 2);
-    sift_rank_kernel<<<g, 256, 0, st>>>(p->raw, p->kp_cap, p->counters, p->sorted);
+    if (p->kp_cap <= 65536 && p->w[0] > 0) {
+      const size_t smem = (size_t)(2 * SORT_BUCKETS + 1) * sizeof(int) + (size_t)p->kp_cap * sizeof(unsigned short);
+      static size_t attr_smem = 0;
+      if (smem > attr_smem) {
+        VO_CUDA(cudaFuncSetAttribute(sift_rank_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+      }
+      // raw keypoint x is in base-image (2x) pixels: [0, w[0])
+      sift_rank_bucket_kernel<<<batch, 1024, smem, st>>>(p->raw, p->kp_cap, p->counters, p->sorted, (float)SORT_BUCKETS / (float)p->w[0]);
+    } else {
+      sift_rank_kernel<<<g, 256, 0, st>>>(p->raw, p->kp_cap, p->counters, p->sorted);
+    }
     sift_dedupe_kernel<<<batch, 1024, 0, st>>>(p->sorted, p->kp_cap, p->counters, p->final_kp, (float)o.index_base);
   }
   {
