@@ -674,6 +674,57 @@ match_prep_kernel(const MatchOperand op, int rows_alloc, int dim, uint8_t* __res
   }
 }
 
+// The common layout (row-major, dim = 128, optionally gathered rows) without shared memory: eight
+// threads own a row, each loads four float4 (coalesced 128-byte segments), reduces its 16 squares and
+// packs its 16 bytes.  Same results as match_prep_kernel.
+__global__ void __launch_bounds__(256)
+match_prep_rows128_kernel(const MatchOperand op, int rows_alloc, uint8_t* __restrict__ out_u8,
+                          float* __restrict__ inv, int* __restrict__ nonint_flag, int* __restrict__ inv_max_bits) {
+  const int prob = blockIdx.y;
+  const int n = min(op.count[prob * op.count_stride], op.cap);
+  const int row = blockIdx.x * PREP_ROWS + (threadIdx.x >> 3), part = threadIdx.x & 7;
+  if (row >= rows_alloc) return;
+  uint32_t* u8_row = reinterpret_cast<uint32_t*>(out_u8 + ((size_t)prob * rows_alloc + row) * 128);
+  if (row >= n) {   // dead rows feed the MMA as zero operands
+    if (part == 0) inv[(size_t)prob * rows_alloc + row] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) u8_row[part + 8 * q] = 0u;
+    return;
+  }
+  const size_t src_row = op.gather ? (size_t)op.gather[(size_t)prob * op.gather_stride + row] : (size_t)row;
+  const float* x = op.base + (size_t)prob * op.prob_stride + src_row * 128;
+  float acc = 0.f;
+  bool isint = true;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + part + 8 * q);
+    const float e[4] = {v.x, v.y, v.z, v.w};
+    uint32_t w = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      acc = fmaf(e[b], e[b], acc);
+      isint = isint && (e[b] == truncf(e[b])) && (e[b] >= 0.f) && (e[b] <= 255.f);
+      w |= (uint32_t)(__float2int_rz(fminf(fmaxf(e[b], 0.f), 255.f)) & 255) << (8 * b);
+    }
+    u8_row[part + 8 * q] = w;
+  }
+#pragma unroll
+  for (int off = 1; off < 8; off <<= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    isint = __shfl_xor_sync(0xffffffffu, (int)isint, off) && isint;
+  }
+  if (part == 0) {
+    if (!isint) {   // general floats: the oracle's sequential fold
+      acc = 0.f;
+      for (int k = 0; k < 128; ++k) acc = fmaf(x[k], x[k], acc);
+      atomicOr(nonint_flag, 1);
+    }
+    const float iv = (acc == 0.f) ? 0.f : __fdiv_rn(1.0f, __fsqrt_rn(acc));
+    inv[(size_t)prob * rows_alloc + row] = iv;
+    if (inv_max_bits != nullptr && iv > 0.f) atomicMax(inv_max_bits + prob, __float_as_int(iv));
+  }
+}
+
 // Runs only when the non-integer flag is set (general float descriptors): bf16 hi/lo split operands
 // out[p][row][3*kp] (A: hi|hi|lo, B: hi|lo|hi) for match_topk_kernel and, for gathered or column-major
 // inputs, the compact row-major fp32 copy the exact re-scoring reads.
@@ -1115,8 +1166,14 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   const bool exact_sizes = (n_prob == 1 && !A.gather && !B.gather);   // caps are the live sizes
   {
     ProfScope ps(ctx, st, "match_prep", exact_sizes ? ((double)A.cap + B.cap) * (dim * 4.0 + 132.0) : 0.0, 0.0, 4);
-    match_prep_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, u8A, invA, ctl, nullptr);
-    match_prep_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, u8B, invB, ctl, invb_max);
+    if (dim == 128 && !A.col_major && (reinterpret_cast<uintptr_t>(A.base) & 15) == 0 && A.prob_stride % 4 == 0)
+      match_prep_rows128_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, 0, st>>>(A, a_alloc, u8A, invA, ctl, nullptr);
+    else
+      match_prep_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, u8A, invA, ctl, nullptr);
+    if (dim == 128 && !B.col_major && (reinterpret_cast<uintptr_t>(B.base) & 15) == 0 && B.prob_stride % 4 == 0)
+      match_prep_rows128_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, 0, st>>>(B, b_alloc, u8B, invB, ctl, invb_max);
+    else
+      match_prep_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, u8B, invB, ctl, invb_max);
     // general float descriptors only (both return at once when every value is an integer 0..255)
     match_prep_split_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, kp, 0, opA, rawA, ctl);
     match_prep_split_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, kp, 1, opB, rawB, ctl);

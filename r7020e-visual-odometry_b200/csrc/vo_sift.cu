@@ -632,7 +632,7 @@ sift_downsample_kernel(const float* __restrict__ src, float* __restrict__ dst, i
 // entirely in shared memory (row pass, column pass, reflect-101), written to the Gaussian stack and
 // differenced into the DoG stack.  Same operations in the same order as sift_blur_dog_kernel.
 struct TapsAll { Taps t[8]; };
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 sift_small_octaves_kernel(float* __restrict__ gauss, float* __restrict__ dog, const OctInfo oi, int first_oct,
                           int n_oct, int nl, int batch_stride, int cap, const TapsAll taps) {
   extern __shared__ float ssm[];
@@ -664,7 +664,11 @@ sift_small_octaves_kernel(float* __restrict__ gauss, float* __restrict__ dog, co
         const int y = idx / w, x = idx - y * w;
         const float* row = A + y * w;
         float acc = tp.k[0] * row[x];
-        for (int j = 1; j <= R; ++j) acc = fmaf(tp.k[j], row[reflect101(x - j, w)] + row[reflect101(x + j, w)], acc);
+        if (x >= R && x + R < w) {
+          for (int j = 1; j <= R; ++j) acc = fmaf(tp.k[j], row[x - j] + row[x + j], acc);
+        } else {
+          for (int j = 1; j <= R; ++j) acc = fmaf(tp.k[j], row[reflect101(x - j, w)] + row[reflect101(x + j, w)], acc);
+        }
         T[idx] = acc;
       }
       __syncthreads();
@@ -673,7 +677,11 @@ sift_small_octaves_kernel(float* __restrict__ gauss, float* __restrict__ dog, co
       for (int idx = tid; idx < n; idx += nt) {
         const int y = idx / w, x = idx - y * w;
         float acc = tp.k[0] * T[idx];
-        for (int j = 1; j <= R; ++j) acc = fmaf(tp.k[j], T[reflect101(y - j, h) * w + x] + T[reflect101(y + j, h) * w + x], acc);
+        if (y >= R && y + R < h) {
+          for (int j = 1; j <= R; ++j) acc = fmaf(tp.k[j], T[idx - j * w] + T[idx + j * w], acc);
+        } else {
+          for (int j = 1; j <= R; ++j) acc = fmaf(tp.k[j], T[reflect101(y - j, h) * w + x] + T[reflect101(y + j, h) * w + x], acc);
+        }
         B[idx] = acc;
         gi[(size_t)y * pitch + x] = acc;
         di[(size_t)y * pitch + x] = acc - A[idx];
@@ -1530,7 +1538,7 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
       attr_smem = smem;
     }
     ProfScope ps(ctx, st, "sift_blur_dog_small", px * (8.0 + 12.0 * (nl + 2)));
-    sift_small_octaves_kernel<<<batch, 512, smem, st>>>(p->gauss, p->dog, oi, first_small, p->n_oct, nl, p->batch, small_cap, ta);
+    sift_small_octaves_kernel<<<batch, 1024, smem, st>>>(p->gauss, p->dog, oi, first_small, p->n_oct, nl, p->batch, small_cap, ta);
   }
   VO_CUDA(cudaGetLastError());
   // extrema
