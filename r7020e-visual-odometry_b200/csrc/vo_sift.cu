@@ -721,13 +721,16 @@ sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int batch, int h
   for (int l = 0; l < L; ++l) { hxA[l] = hxB[l] = hxC[l] = hnA[l] = hnB[l] = hnC[l] = cB[l] = cC[l] = 0.f; }
   const bool col_ok = lane >= 1 && lane <= EX_COLS && x >= SIFT_BORDER && x < w - SIFT_BORDER;
   const int y_end = min(y0 + EX_ROWS, h - SIFT_BORDER);    // last row (exclusive) that can hold a keypoint
-  // the next row's values are loaded one iteration ahead, so the shuffles never wait on HBM
+  // the next row's values are loaded one iteration ahead, so the shuffles never wait on HBM (two rows
+  // ahead was measured slower: more registers, no gain).  Unrolling by 3 lets the compiler rename the
+  // rolling 3-row window instead of moving registers every row.
   float nxt[L];
   {
     const size_t off = (size_t)min(max(y0 - 1, 0), h - 1) * pitch;
 #pragma unroll
     for (int l = 0; l < L; ++l) nxt[l] = __ldg(img + (size_t)l * layer_stride + off);
   }
+#pragma unroll 3
   for (int r = y0 - 1; r <= y_end; ++r) {
     float v[L];
 #pragma unroll
@@ -892,7 +895,7 @@ sift_refine_orient_kernel(const float* __restrict__ gauss, const float* __restri
       int bin = __float2int_rn((ORI_BINS / 360.f) * ang);
       if (bin >= ORI_BINS) bin -= ORI_BINS;
       if (bin < 0) bin += ORI_BINS;
-      atomicAdd(&s_hist[wib][bin], (uint32_t)__float2int_rn(wgt * mag * SIFT_FIX));
+      atomicAdd(&s_hist[wib][bin], sift_fix(wgt * mag));
     };
     int wi = lane / side - radius, wj = lane % side - radius;
     for (int idx = lane; idx < total; idx += 64) {
