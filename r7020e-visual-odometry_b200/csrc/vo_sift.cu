@@ -29,7 +29,7 @@
 namespace vo {
 
 constexpr int MAX_OCT = 16;
-constexpr int MAX_R = 16;
+constexpr int MAX_R = 32;   // generic-radius kernels: NumLayersInOctave >= 2 at Sigma 1.6 needs r = 18
 constexpr int SIFT_BORDER = 5;
 constexpr int ORI_BINS = 36;
 constexpr float SIFT_FIX = 4096.0f;

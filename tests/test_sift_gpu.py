@@ -96,3 +96,34 @@ def test_sift_capacity_error(ctx):
     img = synth.texture(150, 200, seed=9)
     with pytest.raises(vo_b200.VoError):
         vo_b200.detectSIFTFeatures(img, capacity=10, ctx=ctx)
+
+
+@pytest.mark.parametrize("shape", [(24, 40), (40, 24), (33, 130), (47, 155), (64, 97), (129, 257)])
+def test_sift_ragged_and_tiny_shapes_bit_exact(ctx, shape):
+    """Shapes that exercise every pyramid code path: all octaves in the fused small-octave kernel
+    (first octave included), the streaming/TMA kernels with partial strips, odd sizes, octave
+    boundaries at the 64 x 96 switch.  Keypoints and descriptors must equal the oracle bit for bit."""
+    import vo_b200
+    from vo_b200 import synth
+    img = synth.texture(shape[0], shape[1], seed=shape[0] + shape[1])
+    pts = vo_b200.detectSIFTFeatures(img, capacity=8192, ctx=ctx)
+    okp, odesc = oracle.sift(img)
+    assert len(pts) == len(okp)
+    for f in ("x", "y", "size", "angle", "response", "octave"):
+        assert np.array_equal(pts.kps[f], okp[f]), f
+    assert np.array_equal(pts._features, odesc)
+
+
+@pytest.mark.parametrize("opts", [dict(NumLayersInOctave=2), dict(NumLayersInOctave=4), dict(Sigma=1.2),
+                                  dict(ContrastThreshold=0.03, EdgeThreshold=5.0)])
+def test_sift_options_match_oracle(ctx, opts):
+    """Non-default detector options (MATLAB name-value pairs) go through the generic-radius kernels."""
+    import vo_b200
+    from vo_b200 import synth
+    img = synth.texture(150, 220, seed=31)
+    pts = vo_b200.detectSIFTFeatures(img, capacity=16384, ctx=ctx, **opts)
+    nl = opts.get("NumLayersInOctave", 3)
+    okp, odesc = oracle.sift(img, n_octave_layers=nl, contrast_threshold=opts.get("ContrastThreshold", 0.04 / 3) * nl,
+                             edge_threshold=opts.get("EdgeThreshold", 10.0), sigma=opts.get("Sigma", 1.6))
+    assert len(okp) > 20
+    _compare(pts, pts._features, okp, odesc)
