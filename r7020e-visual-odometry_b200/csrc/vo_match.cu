@@ -576,6 +576,272 @@ match_topk_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+// ------------------------------------------- exact-integer path on CTA PAIRS (cta_group::2)
+// tools/ubench_tmem.cu shows that cta_group::1 MMAs are bound by the rate at which the tensor pipe
+// reads its operands from shared memory (108 cycles per M128 x N128 x K32 MMA, 64 ideal).  In
+// cta_group::2 form two SMs of a cluster share one M = 256, N = 256 MMA: each SM holds its own 128 A rows
+// and HALF of the B tile (128 of the 256 columns), so per MMA an SM reads 8 KB for 128 ideal cycles.
+// Layout per CTA: A panel 16 KB (its 128 rows, resident), B ring X_STAGES x 16 KB (its 128 B rows of each
+// 256-column tile), TMEM 2 accumulator stages x 256 columns (its 128 rows x 256 columns per tile).
+// Protocol (the CUTLASS 2-SM pattern): both CTAs issue their TMA loads with .cta_group::2 and signal
+// the LEADER's (cluster rank 0) "full" barrier; the leader's MMA thread issues the MMAs and
+// multicast-commits to the "stage empty" and "accumulator full" barriers of BOTH CTAs; the epilogue
+// warps of both CTAs arrive (remotely for rank 1) on the leader's "accumulator empty" barrier.
+// Epilogue thread = (TMEM lane quarter, 64-column quarter); candidate slot = split * 4 + quarter.
+// XN = tile width in columns (256: two 32-column chunks per epilogue warp and 2 TMEM stages; 128: one chunk
+// and 4 TMEM stages -- the deeper accumulator ring hides the MMA -> epilogue -> MMA signalling latency).
+constexpr int X_RING_BYTES = 8 * U_TILE_BYTES;     // B ring: 128 KB per CTA whatever the tile width
+constexpr int X_SMEM_BYTES = U_TILE_BYTES + X_RING_BYTES + 512 + 128 * 4 + NUM_EPI_WARPS * U_SCRATCH_INTS * 4;
+// shared::cluster address of the leader's (cluster rank 0) copy of a local shared-memory object
+__device__ __forceinline__ uint32_t leader_addr(uint32_t local) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(local)); return r;
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_mc(uint32_t bar) {   // arrive on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive on the leader CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
+}
+
+template <int XN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+match_topk_u8x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const float* __restrict__ invb_base, int invb_stride, const float* __restrict__ inva_base,
+                       int inva_stride, const int* __restrict__ invb_max_bits, const int* __restrict__ n1p,
+                       int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
+                       const int* __restrict__ nonint_flag, int n_splits, uint2* __restrict__ cand_base,
+                       size_t cand_stride, int slots_per_row, float key_floor, float* __restrict__ dbg_c, int dbg_ld,
+                       long long* __restrict__ clk) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // every exit before the cluster barriers below is taken by BOTH CTAs of a pair (same pair index, split, problem)
+  if (*nonint_flag != 0) return;
+  const int prob = blockIdx.z;
+  const int n1 = min(n1p[prob * n1_stride], cap1), n2 = min(n2p[prob * n2_stride], cap2);
+  const uint32_t rank = cluster_ctarank();            // == blockIdx.x & 1 for cluster dims (2,1,1)
+  const int m_pair = (blockIdx.x >> 1) * 256;
+  if (m_pair >= n1) return;
+  const int m0 = m_pair + (int)rank * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NS = 512 / XN;                       // TMEM accumulator stages
+  constexpr int CH = XN / 128;                       // 32-column chunks per epilogue warp and tile
+  constexpr int XB_BYTES = (XN / 2) * 128;           // this CTA's half of a B tile
+  constexpr int X_STAGES = X_RING_BYTES / XB_BYTES;
+  const int tiles_total = (n2 + XN - 1) / XN;
+  const int split = blockIdx.y;
+  const int t_begin = (int)((long long)split * tiles_total / n_splits);
+  const int t_end = (int)((long long)(split + 1) * tiles_total / n_splits);
+  uint2* cand = cand_base + (size_t)prob * cand_stride;
+  const float* invb = invb_base + (size_t)prob * invb_stride;
+
+  if (t_begin >= t_end) {
+    if (warp >= 2) {
+      const int e = warp - 2, quarter = warp & 3, cq = e >> 2;
+      const int row = m0 + quarter * 32 + lane;
+      if (row < n1) {
+        uint2* out = cand + ((size_t)row * slots_per_row + split * 4 + cq) * NCAND;
+        for (int c = 0; c < NCAND; ++c) out[c] = make_uint2(__float_as_uint(-INFINITY), 0xFFFFFFFFu);
+      }
+    }
+    return;
+  }
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) __trap();
+  const uint32_t sA = base;                              // 16 KB
+  const uint32_t sB = sA + U_TILE_BYTES;                 // [X_STAGES] x XB_BYTES
+  const uint32_t bars = sB + X_RING_BYTES;
+  const uint32_t bar_a_full = bars;                      // leader only
+  const uint32_t bar_b_full = bars + 8;                  // leader only [X_STAGES]
+  const uint32_t bar_b_empty = bar_b_full + 8 * X_STAGES;   // both CTAs [X_STAGES]
+  const uint32_t bar_t_full = bar_b_empty + 8 * X_STAGES;   // both CTAs [NS]
+  const uint32_t bar_t_empty = bar_t_full + 8 * NS;         // leader only [NS]
+  const uint32_t tmem_slot = bar_t_empty + 8 * NS;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - base));
+  float* s_thr = reinterpret_cast<float*>(smem_raw + (bars + 512 - base));   // [128]
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    mbar_init(bar_a_full, 1);
+    for (int s = 0; s < X_STAGES; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, 2 * NUM_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 128) {
+    const int r = threadIdx.x - 64;
+    float t0 = -INFINITY;
+    if (key_floor > 0.f && m0 + r < n1) {
+      const float ia = inva_base[(size_t)prob * inva_stride + m0 + r];
+      if (ia > 0.f) t0 = __fdiv_rn(key_floor, ia);
+    }
+    s_thr[r] = t0;
+  }
+  if (warp == 1) {   // the same warp of both CTAs allocates all 512 columns for the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // barriers of both CTAs are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer (both CTAs; all transaction bytes land on the leader's barriers) =====
+      if (rank == 0) mbar_expect_tx(bar_a_full, 2 * U_TILE_BYTES);
+      tma_load_3d_2sm(sA, &tmA, bar_a_full, 0, m0, prob);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+        if (rank == 0) mbar_expect_tx(bar_b_full + 8 * stage, 2 * XB_BYTES);
+        tma_load_3d_2sm(sB + stage * XB_BYTES, &tmB, bar_b_full + 8 * stage, 0, t * XN + (int)rank * (XN / 2), prob);
+        if (++stage == X_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {  // ===== MMA issuer (leader): D=s32, A=B=u8, K-major, M=256 (pair), N=256, K=32 per MMA =====
+      const uint32_t idesc = (2u << 4) | ((uint32_t)(XN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      mbar_wait(bar_a_full, 0);
+      tc_fence_after();
+      // the issuing thread's own instruction stream paces the tile loop, so everything that does not
+      // depend on the tile is hoisted: A descriptors are constants, B descriptors differ by the stage offset
+      const uint64_t ad0 = umma_desc_sw128(sA), bd0 = umma_desc_sw128(sB);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      long long c_te = 0, c_bf = 0; const long long c_start = clock64();
+      for (int t = t_begin; t < t_end; ++t) {
+        if (clk) {   // debug: where does the issuing thread wait?
+          const long long c0 = clock64();
+          mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);
+          const long long c1 = clock64();
+          mbar_wait(bar_b_full + 8 * stage, phase);
+          c_te += c1 - c0; c_bf += clock64() - c1;
+        } else {
+          mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);
+          mbar_wait(bar_b_full + 8 * stage, phase);
+        }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * XN;
+        const uint64_t bds = bd0 + (uint64_t)(stage * (XB_BYTES >> 4));
+        asm volatile(
+            "{\n\t.reg .pred p0, p1;\n\tsetp.ne.b32 p0, 0, 0;\n\tsetp.eq.b32 p1, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %5, %9, p0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %2, %6, %9, p1;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %3, %7, %9, p1;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %4, %8, %9, p1;\n\t}"
+            ::"r"(d_tmem), "l"(ad0), "l"(ad0 + 2), "l"(ad0 + 4), "l"(ad0 + 6), "l"(bds), "l"(bds + 2), "l"(bds + 4), "l"(bds + 6),
+              "r"(idesc)
+            : "memory");
+        tc_commit_2sm_mc(bar_b_empty + 8 * stage);
+        tc_commit_2sm_mc(bar_t_full + 8 * acc);
+        if (++stage == X_STAGES) { stage = 0; phase ^= 1; }
+        if (++acc == NS) { acc = 0; acc_phase ^= 1; }
+      }
+      if (clk) {
+        long long* o = clk + 4 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+        o[0] = clock64() - c_start; o[1] = c_te; o[2] = c_bf; o[3] = t_end - t_begin;
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): same fast / exact paths as match_topk_u8_kernel =====
+    const int e = warp - 2, quarter = warp & 3, cq = e >> 2;
+    const int row_in_cta = quarter * 32 + lane;
+    const int row = m0 + row_in_cta;
+    const float bmax = __int_as_float(invb_max_bits[prob]);
+    const float bnorm = bmax > 0.f ? __fdiv_rn(1.0f, bmax) : 0.f;
+    int* scr = reinterpret_cast<int*>(s_thr + 128) + e * U_SCRATCH_INTS;
+    Top3 top; top.init();
+    float thr = s_thr[row_in_cta];
+    int thr_raw = raw_bound(thr, bnorm);
+    if (row >= n1) { thr = INFINITY; thr_raw = 0x7fffffff; }
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(bar_t_full + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * XN + cq * (XN / 4));
+      uint32_t r0[32], r1[32];
+      tmem_ld32(tbase, r0);
+      if (CH == 2) tmem_ld32(tbase + 32, r1);
+      const float shared_thr = s_thr[row_in_cta];
+      if (shared_thr > thr) { thr = shared_thr; thr_raw = raw_bound(thr, bnorm); }
+      tmem_ld_wait(r0);
+      if (CH == 2) tmem_ld_wait(r1);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(bar_t_empty + 8 * acc);
+#pragma unroll
+      for (int chunk = 0; chunk < CH; ++chunk) {
+        uint32_t (&r)[32] = chunk == 0 ? r0 : r1;
+        const int j0 = t * XN + cq * (XN / 4) + chunk * 32;
+        if (dbg_c != nullptr && row < n1) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (j0 + c < n2) dbg_c[(size_t)row * dbg_ld + j0 + c] = (float)(int)r[c];
+        }
+        int l1[12];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) l1[q] = imax3((int)r[3 * q], (int)r[3 * q + 1], (int)r[3 * q + 2]);
+        l1[10] = (int)r[30]; l1[11] = (int)r[31];
+        const int a0 = imax3(l1[0], l1[1], l1[2]), a1 = imax3(l1[3], l1[4], l1[5]);
+        const int a2 = imax3(l1[6], l1[7], l1[8]), a3 = imax3(l1[9], l1[10], l1[11]);
+        const int m = max(imax3(a0, a1, a2), a3);
+        const unsigned flagged = __ballot_sync(0xffffffffu, m > thr_raw);
+        if (flagged) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) scr[c * 33 + lane] = (int)r[c];
+          const int jc = j0 + lane;
+          const float ib = (jc < n2) ? invb[jc] : 0.f;
+          __syncwarp();
+          unsigned f = flagged;
+          while (f) {
+            const int L = __ffs(f) - 1;
+            f &= f - 1;
+            const float key = __fmul_rn((float)scr[lane * 33 + L], ib);
+            float thr_l = __shfl_sync(0xffffffffu, thr, L);
+            unsigned cm = __ballot_sync(0xffffffffu, jc < n2 && key > thr_l);
+            while (cm) {
+              const int c = __ffs(cm) - 1;
+              const float kk = __shfl_sync(0xffffffffu, key, c);
+              if (lane == L && kk > thr) {
+                top.insert(kk, (uint32_t)(j0 + c));
+                if (top.k3 > thr) { thr = top.k3; thr_raw = raw_bound(thr, bnorm); }
+              }
+              thr_l = __shfl_sync(0xffffffffu, thr, L);
+              cm &= __ballot_sync(0xffffffffu, key > thr_l) & ~((2u << c) - 1u);
+            }
+          }
+          __syncwarp();
+        }
+      }
+      if (top.k3 > shared_thr) s_thr[row_in_cta] = top.k3;
+      if (++acc == NS) { acc = 0; acc_phase ^= 1; }
+    }
+    if (row < n1) {
+      uint2* out = cand + ((size_t)row * slots_per_row + split * 4 + cq) * NCAND;
+      out[0] = make_uint2(__float_as_uint(top.k1), top.i1);
+      out[1] = make_uint2(__float_as_uint(top.k2), top.i2);
+      out[2] = make_uint2(__float_as_uint(top.k3), top.i3);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // no CTA of the pair exits (or frees TMEM) while the other may still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
 __global__ void match_set_counts_kernel(int* counts, int n1, int n2) {
   if (threadIdx.x == 0) { counts[0] = n1; counts[1] = n2; }
 }
@@ -786,7 +1052,7 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
                       int dim, const float* __restrict__ inva_base, int inva_stride,
                       const float* __restrict__ invb_base, int invb_stride, const int* __restrict__ n1p,
                       int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
-                      const int* __restrict__ nonint_flag, MatchFilter flt, uint32_t* __restrict__ j1_out,
+                      const int* __restrict__ nonint_flag, int all_slots, MatchFilter flt, uint32_t* __restrict__ j1_out,
                       float* __restrict__ s1_out, float* __restrict__ s2_out, int row_stride,
                       int* __restrict__ scan_list, int* __restrict__ scan_count) {
   const int prob = blockIdx.y;
@@ -799,7 +1065,7 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
   uint32_t j[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
   // row stride is n_slots (thin kernel: 4 slots per split); the fat kernel fills the first half only
   const uint2* c = cand_base + (size_t)prob * cand_stride + (size_t)i * n_slots * NCAND;
-  const int used = (*nonint_flag) ? n_slots * NCAND : (n_slots / 2) * NCAND;
+  const int used = ((*nonint_flag) || all_slots) ? n_slots * NCAND : (n_slots / 2) * NCAND;
   for (int s = 0; s < used; ++s) {
     const uint2 e = c[s];
     if (e.y >= (uint32_t)n2) continue;
@@ -1098,12 +1364,12 @@ static int make_operand_map(CUtensorMap* map, const __nv_bfloat16* base, int row
 }
 
 // u8 operands [n_prob][rows_alloc][128]: one 128-row x 128-byte box = one 128B-swizzled K block
-static int make_u8_map(CUtensorMap* map, const uint8_t* base, int rows_alloc, int n_prob) {
+static int make_u8_map(CUtensorMap* map, const uint8_t* base, int rows_alloc, int n_prob, int box_rows = 128) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) { set_error("cuTensorMapEncodeTiled driver entry point not available"); return VO_ERR_CUDA; }
   cuuint64_t gdim[3] = {128, (cuuint64_t)rows_alloc, (cuuint64_t)n_prob};
   cuuint64_t gstride[2] = {128, (cuuint64_t)rows_alloc * 128};
-  cuuint32_t box[3] = {128, 128, 1};
+  cuuint32_t box[3] = {128, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1113,6 +1379,7 @@ static int make_u8_map(CUtensorMap* map, const uint8_t* base, int rows_alloc, in
 }
 
 static bool g_attr_set = false;
+constexpr bool MATCH_PAIRS_DEFAULT = false;
 
 MatchFilter make_match_filter(const vo_match_opts& o) {
   MatchFilter f{0.f, 0.f, 0.f};
@@ -1196,6 +1463,14 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
     if ((long long)m_blocks * n_prob >= 4LL * ctx->num_sms) n_splits = 1;
     if (n_splits > b_tiles) n_splits = b_tiles;
   }
+  // CTA-pair (cta_group::2) kernel: VO_MATCH_PAIRS=0/1 overrides the default
+  static const int pairs_env = [] { const char* e = getenv("VO_MATCH_PAIRS"); return e ? atoi(e) : -1; }();
+  const bool use_pairs = pairs_env >= 0 ? pairs_env != 0 : MATCH_PAIRS_DEFAULT;
+  static const int pair_tile = [] { const char* e = getenv("VO_MATCH_PAIR_TILE"); return (e && atoi(e) == 256) ? 256 : 128; }();
+  if (use_pairs) {
+    const int x_tiles = div_up(B.cap > 0 ? B.cap : 1, pair_tile);
+    if (n_splits > x_tiles) n_splits = x_tiles;
+  }
   const int n_slots = n_splits * 4;
   const size_t cand_stride = (size_t)a_alloc * n_slots * NCAND;
   uint2* cand; VO_TRY(dev_buf(ctx, nm("m_cand").c_str(), (size_t)n_prob * cand_stride, &cand));
@@ -1208,6 +1483,8 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
     VO_TRY(make_u8_map(&tmA8, u8A, a_alloc, n_prob));
     VO_TRY(make_u8_map(&tmB8, u8B, b_alloc, n_prob));
     if (!g_attr_set) {
+      VO_CUDA(cudaFuncSetAttribute(match_topk_u8x2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM_BYTES));
+      VO_CUDA(cudaFuncSetAttribute(match_topk_u8x2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM_BYTES));
       VO_CUDA(cudaFuncSetAttribute(match_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       VO_CUDA(cudaFuncSetAttribute(match_topk_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM_BYTES));
       g_attr_set = true;
@@ -1218,15 +1495,50 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
     match_topk_kernel<<<dim3(a_alloc / BM, n_splits, n_prob), NUM_THREADS, SMEM_BYTES, st>>>(
         tmA, tmB, invB, b_alloc, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap, ctl, kp / BK, n_splits, cand,
         cand_stride, dbg_c, B.cap);
-    match_topk_u8_kernel<<<dim3(m_blocks, n_splits, n_prob), NUM_THREADS, U_SMEM_BYTES, st>>>(
-        tmA8, tmB8, invB, b_alloc, invA, a_alloc, invb_max, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap,
-        ctl, n_splits, cand, cand_stride, n_slots, flt.key_floor, dbg_c, B.cap);
+    if (!use_pairs) {
+      match_topk_u8_kernel<<<dim3(m_blocks, n_splits, n_prob), NUM_THREADS, U_SMEM_BYTES, st>>>(
+          tmA8, tmB8, invB, b_alloc, invA, a_alloc, invb_max, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap,
+          ctl, n_splits, cand, cand_stride, n_slots, flt.key_floor, dbg_c, B.cap);
+    } else {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * m_blocks, n_splits, n_prob);   // one CTA pair (cluster of 2) per 256-row panel
+      cfg.blockDim = dim3(NUM_THREADS);
+      cfg.dynamicSmemBytes = X_SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      static const bool clk_on = getenv("VO_MATCH_CLK") != nullptr;
+      long long* clk = nullptr;
+      const size_t n_cta = (size_t)cfg.gridDim.x * cfg.gridDim.y * cfg.gridDim.z;
+      if (clk_on) { VO_TRY(dev_buf(ctx, "m_clk", 4 * n_cta, &clk)); VO_CUDA(cudaMemsetAsync(clk, 0, 32 * n_cta, st)); }
+      if (pair_tile == 128) {
+        CUtensorMap tmB64;
+        VO_TRY(make_u8_map(&tmB64, u8B, b_alloc, n_prob, 64));
+        VO_CUDA(cudaLaunchKernelEx(&cfg, match_topk_u8x2_kernel<128>, tmA8, tmB64, (const float*)invB, b_alloc, (const float*)invA, a_alloc,
+                                   (const int*)invb_max, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap,
+                                   (const int*)ctl, n_splits, cand, cand_stride, n_slots, flt.key_floor, dbg_c, B.cap, clk));
+      } else {
+        VO_CUDA(cudaLaunchKernelEx(&cfg, match_topk_u8x2_kernel<256>, tmA8, tmB8, (const float*)invB, b_alloc, (const float*)invA, a_alloc,
+                                   (const int*)invb_max, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap,
+                                   (const int*)ctl, n_splits, cand, cand_stride, n_slots, flt.key_floor, dbg_c, B.cap, clk));
+      }
+      if (clk_on) {   // debug only: synchronises
+        std::vector<long long> h(4 * n_cta);
+        VO_CUDA(cudaMemcpyAsync(h.data(), clk, 32 * n_cta, cudaMemcpyDeviceToHost, st));
+        VO_CUDA(cudaStreamSynchronize(st));
+        double tot = 0, te = 0, bf = 0, tiles = 0; int n = 0;
+        for (size_t i = 0; i < n_cta; ++i) if (h[4 * i + 3] > 0) { tot += h[4 * i]; te += h[4 * i + 1]; bf += h[4 * i + 2]; tiles += h[4 * i + 3]; ++n; }
+        if (n) fprintf(stderr, "[match clk] %d leader CTAs, %.0f tiles each: %.0f cycles/tile, wait t_empty %.0f, wait b_full %.0f\n", n, tiles / n, tot / tiles, te / tiles, bf / tiles);
+      }
+    }
     VO_CUDA(cudaGetLastError());
     ctx->match_stats[2] = 1;
   }
   match_finalize_kernel<<<dim3(div_up(A.cap, 128), n_prob), 128, 0, st>>>(
       cand, cand_stride, n_slots, ra, rb, dim, invA, a_alloc, invB, b_alloc, A.count, A.count_stride, A.cap, B.count,
-      B.count_stride, B.cap, ctl, flt, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
+      B.count_stride, B.cap, ctl, use_pairs ? 1 : 0, flt, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
   if (B.cap > 0) {
     int scan_grid = ctx->num_sms * 2;
     match_rowscan_kernel<<<scan_grid, 256, 0, st>>>(scan_list, ctl + 1, ra, rb, u8A, u8B, a_alloc, b_alloc, ctl, dim, invA, a_alloc, invB, b_alloc, B.count,

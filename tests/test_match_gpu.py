@@ -155,3 +155,31 @@ def test_best2_records_row_sharded_equals_unsharded(ctx):
     assert np.array_equal(np.nonzero(keep)[0].astype(np.uint32), opairs[:, 0])
     assert np.array_equal(full[keep, 0].view(np.uint32), opairs[:, 1])
     assert np.array_equal(full[keep, 1].view(np.uint32), ometric.view(np.uint32))
+
+
+def test_cta_pair_kernel_bit_exact():
+    """The experimental cta_group::2 variant of the exact-integer kernel (VO_MATCH_PAIRS=1, read once per
+    process, hence the subprocess) must return the same bit-exact results as the default kernel."""
+    import os, subprocess, sys
+    code = r'''
+import sys, os, numpy as np
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import vo_b200, vo_b200.api as api
+from conftest import correlated_pair
+from oracle import oracle
+ctx = vo_b200.Context(0)
+for n1, n2, seed in [(1, 1, 1), (129, 257, 2), (1000, 777, 3), (3000, 3100, 4)]:
+    f1, f2 = correlated_pair(n1, n2, seed=seed)
+    j1, s1, s2 = api.match_top2(f1, f2, ctx=ctx)
+    oj1, os1, os2 = oracle.match_top2(f1, f2)
+    assert np.array_equal(j1, oj1) and np.array_equal(s1.view(np.uint32), os1.view(np.uint32)) and np.array_equal(s2.view(np.uint32), os2.view(np.uint32))
+    p, m = vo_b200.matchFeatures(f1, f2, return_metric=True, ctx=ctx)
+    op, om = oracle.match(f1, f2)
+    assert np.array_equal(p, op) and np.array_equal(m.view(np.uint32), om.view(np.uint32))
+print("pairs ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for tile in ("256", "128"):
+        env = dict(os.environ, VO_MATCH_PAIRS="1", VO_MATCH_PAIR_TILE=tile)
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "pairs ok" in r.stdout, r.stdout + r.stderr
