@@ -39,6 +39,7 @@ constexpr int TILE_W = 128, TILE_H = 32;
 struct Taps { float k[MAX_R + 1]; int r; };
 struct OctInfo { int h[MAX_OCT], w[MAX_OCT], pitch[MAX_OCT]; size_t goff[MAX_OCT], doff[MAX_OCT]; };
 
+struct RefinedKp;
 struct SiftPlan {
   int rows = 0, cols = 0, batch = 0, nl = 0;
   float sigma = 0, contrast = 0, edge = 0;
@@ -53,7 +54,7 @@ struct SiftPlan {
   int cand_cap = 0, kp_cap = 0;
   uint32_t* cand = nullptr; int* counters = nullptr;   // counters[b*4 + {0:cand,1:raw kp,2:final}]
   vo_keypoint* raw = nullptr; vo_keypoint* sorted = nullptr; vo_keypoint* final_kp = nullptr;
-  float* desc = nullptr; float2* trig = nullptr;
+  float* desc = nullptr; float2* trig = nullptr; struct RefinedKp* refined = nullptr;
   size_t layer_elems(int o) const { return (size_t)batch * h[o] * pitch[o]; }
   float* G(int o, int l) const { return gauss + goff[o] + (size_t)l * layer_elems(o); }
   float* D(int o, int l) const { return dog + doff[o] + (size_t)l * layer_elems(o); }
@@ -62,7 +63,7 @@ struct SiftPlan {
 void sift_plan_destroy(SiftPlan* p) {
   if (!p) return;
   cudaFree(p->gauss); cudaFree(p->dog); cudaFree(p->img); cudaFree(p->img_t); cudaFree(p->cand);
-  cudaFree(p->counters); cudaFree(p->raw); cudaFree(p->sorted); cudaFree(p->final_kp); cudaFree(p->desc); cudaFree(p->trig);
+  cudaFree(p->counters); cudaFree(p->raw); cudaFree(p->sorted); cudaFree(p->final_kp); cudaFree(p->desc); cudaFree(p->trig); cudaFree(p->refined);
   delete p;
 }
 
@@ -782,89 +783,124 @@ sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int batch, int h
 
 // --------------------------------------------------------- refinement + orientation (warp/cand)
 
+// Refinement: THREAD per candidate (the sub-pixel fit is scalar work; a warp per candidate executed
+// it 32 times over).  Survivors are appended, warp-aggregated, to a compact list of refined records
+// that the orientation kernel then processes with a warp each.
+struct RefinedKp { float x, y, size, resp; int oct_word; uint32_t where; };   // where = o<<28 | layer<<25 | r<<13 | c
 __global__ void __launch_bounds__(128)
-sift_refine_orient_kernel(const float* __restrict__ gauss, const float* __restrict__ dog, const OctInfo oi,
-                          int batch, int nl, float contrast_thr, float edge_thr, float sigma,
-                          const uint32_t* __restrict__ cand, int cand_cap, int* __restrict__ counters,
-                          vo_keypoint* __restrict__ raw, int kp_cap) {
+sift_refine_kernel(const float* __restrict__ dog, const OctInfo oi, int batch, int nl, float contrast_thr, float edge_thr,
+                   float sigma, const uint32_t* __restrict__ cand, int cand_cap, int* __restrict__ counters,
+                   RefinedKp* __restrict__ refined) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int n_cand = min(counters[b * 4 + 0], cand_cap);
+  const float img_scale = 1.f / 255.f, deriv_scale = img_scale * 0.5f, second_deriv_scale = img_scale,
+              cross_deriv_scale = img_scale * 0.25f;
+  for (int base = blockIdx.x * 128; base < n_cand; base += gridDim.x * 128) {
+    const int ci = base + threadIdx.x;
+    bool ok = ci < n_cand;
+    float kx = 0, ky = 0, ksize = 0, kresp = 0; int koct = 0;
+    uint32_t where = 0;
+    if (ok) {
+      do {
+        const uint32_t word = cand[(size_t)b * cand_cap + ci];
+        const int o = word >> 28;
+        int layer = (word >> 25) & 7, r = (word >> 13) & 4095, c = word & 8191;
+        const int rows = oi.h[o], cols = oi.w[o], pitch = oi.pitch[o];
+        const size_t lstride = (size_t)batch * rows * pitch;
+        const float* dbase = dog + oi.doff[o] + (size_t)b * rows * pitch;
+        float xi = 0, xr = 0, xc = 0;
+        int it = 0;
+        for (; it < 5; ++it) {
+          const float* img = dbase + (size_t)layer * lstride;
+          const float* prv = img - lstride;
+          const float* nxt = img + lstride;
+          const size_t q = (size_t)r * pitch + c;
+          const float dD0 = (img[q + 1] - img[q - 1]) * deriv_scale;
+          const float dD1 = (img[q + pitch] - img[q - pitch]) * deriv_scale;
+          const float dD2 = (nxt[q] - prv[q]) * deriv_scale;
+          const float v2 = img[q] * 2.f;
+          const float dxx = (img[q + 1] + img[q - 1] - v2) * second_deriv_scale;
+          const float dyy = (img[q + pitch] + img[q - pitch] - v2) * second_deriv_scale;
+          const float dss = (nxt[q] + prv[q] - v2) * second_deriv_scale;
+          const float dxy = (img[q + pitch + 1] - img[q + pitch - 1] - img[q - pitch + 1] + img[q - pitch - 1]) * cross_deriv_scale;
+          const float dxs = (nxt[q + 1] - nxt[q - 1] - prv[q + 1] + prv[q - 1]) * cross_deriv_scale;
+          const float dys = (nxt[q + pitch] - nxt[q - pitch] - prv[q + pitch] + prv[q - pitch]) * cross_deriv_scale;
+          const float a00 = dxx, a01 = dxy, a02 = dxs, a11 = dyy, a12 = dys, a22 = dss;
+          const float m0 = a11 * a22 - a12 * a12, m1 = a01 * a22 - a12 * a02, m2 = a01 * a12 - a11 * a02;
+          const float det = a00 * m0 - a01 * m1 + a02 * m2;
+          float X0 = 0, X1 = 0, X2 = 0;
+          if (det != 0.f) {
+            const float d = __fdiv_rn(1.f, det);
+            X0 = d * (dD0 * m0 - a01 * (dD1 * a22 - a12 * dD2) + a02 * (dD1 * a12 - a11 * dD2));
+            X1 = d * (a00 * (dD1 * a22 - a12 * dD2) - dD0 * m1 + a02 * (a01 * dD2 - dD1 * a02));
+            X2 = d * (a00 * (a11 * dD2 - dD1 * a12) - a01 * (a01 * dD2 - dD1 * a02) + dD0 * m2);
+          }
+          xi = -X2; xr = -X1; xc = -X0;
+          if (fabsf(xi) < 0.5f && fabsf(xr) < 0.5f && fabsf(xc) < 0.5f) break;
+          const float big = (float)(INT32_MAX / 3);
+          if (fabsf(xi) > big || fabsf(xr) > big || fabsf(xc) > big) { ok = false; break; }
+          c += __float2int_rn(xc); r += __float2int_rn(xr); layer += __float2int_rn(xi);
+          if (layer < 1 || layer > nl || c < SIFT_BORDER || c >= cols - SIFT_BORDER || r < SIFT_BORDER || r >= rows - SIFT_BORDER) {
+            ok = false; break;
+          }
+        }
+        if (it >= 5) ok = false;
+        if (ok) {
+          const float* img = dbase + (size_t)layer * lstride;
+          const float* prv = img - lstride;
+          const float* nxt = img + lstride;
+          const size_t q = (size_t)r * pitch + c;
+          const float dD0 = (img[q + 1] - img[q - 1]) * deriv_scale;
+          const float dD1 = (img[q + pitch] - img[q - pitch]) * deriv_scale;
+          const float dD2 = (nxt[q] - prv[q]) * deriv_scale;
+          const float t = dD0 * xc + dD1 * xr + dD2 * xi;
+          const float contr = img[q] * img_scale + t * 0.5f;
+          if (fabsf(contr) * nl < contrast_thr) ok = false;
+          const float v2 = img[q] * 2.f;
+          const float dxx = (img[q + 1] + img[q - 1] - v2) * second_deriv_scale;
+          const float dyy = (img[q + pitch] + img[q - pitch] - v2) * second_deriv_scale;
+          const float dxy = (img[q + pitch + 1] - img[q + pitch - 1] - img[q - pitch + 1] + img[q - pitch - 1]) * cross_deriv_scale;
+          const float tr = dxx + dyy, det = dxx * dyy - dxy * dxy;
+          if (det <= 0 || tr * tr * edge_thr >= (edge_thr + 1) * (edge_thr + 1) * det) ok = false;
+          kx = (c + xc) * (float)(1 << o);
+          ky = (r + xr) * (float)(1 << o);
+          koct = o + (layer << 8) + (__float2int_rn((xi + 0.5f) * 255.f) << 16);
+          ksize = sigma * vo_expf(__fdiv_rn((float)layer + xi, (float)nl) * 0.693147180559945f) * (float)(1 << o) * 2.f;
+          kresp = fabsf(contr);
+        }
+        where = ((uint32_t)o << 28) | ((uint32_t)layer << 25) | ((uint32_t)r << 13) | (uint32_t)c;
+      } while (false);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, ok);
+    if (mask) {
+      const int leader = __ffs(mask) - 1;
+      int slot0 = 0;
+      if (lane == leader) slot0 = atomicAdd(&counters[b * 4 + 3], __popc(mask));
+      slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+      if (ok) {
+        RefinedKp rk; rk.x = kx; rk.y = ky; rk.size = ksize; rk.resp = kresp; rk.oct_word = koct; rk.where = where;
+        refined[(size_t)b * cand_cap + slot0 + __popc(mask & ((1u << lane) - 1u))] = rk;
+      }
+    }
+  }
+}
+
+// Orientation: WARP per refined keypoint.
+__global__ void __launch_bounds__(128)
+sift_orient_kernel(const float* __restrict__ gauss, const OctInfo oi, int batch, const RefinedKp* __restrict__ refined,
+                   int cand_cap, int* __restrict__ counters, vo_keypoint* __restrict__ raw, int kp_cap) {
   __shared__ uint32_t s_hist[4][ORI_BINS];
   __shared__ float s_sm[4][ORI_BINS + 4];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int n_cand = min(counters[b * 4 + 0], cand_cap);
-  const float img_scale = 1.f / 255.f, deriv_scale = img_scale * 0.5f, second_deriv_scale = img_scale,
-              cross_deriv_scale = img_scale * 0.25f;
-  for (int ci = blockIdx.x * 4 + wib; ci < n_cand; ci += gridDim.x * 4) {
-    const uint32_t word = cand[(size_t)b * cand_cap + ci];
-    const int o = word >> 28;
-    int layer = (word >> 25) & 7, r = (word >> 13) & 4095, c = word & 8191;
+  const int n_ref = min(counters[b * 4 + 3], cand_cap);
+  for (int ci = blockIdx.x * 4 + wib; ci < n_ref; ci += gridDim.x * 4) {
+    const RefinedKp rk = refined[(size_t)b * cand_cap + ci];
+    const int o = rk.where >> 28, layer = (rk.where >> 25) & 7, r = (rk.where >> 13) & 4095, c = rk.where & 8191;
     const int rows = oi.h[o], cols = oi.w[o], pitch = oi.pitch[o];
     const size_t lstride = (size_t)batch * rows * pitch;
-    const float* dbase = dog + oi.doff[o] + (size_t)b * rows * pitch;
-    float xi = 0, xr = 0, xc = 0;
-    bool ok = true;
-    int it = 0;
-    for (; it < 5; ++it) {
-      const float* img = dbase + (size_t)layer * lstride;
-      const float* prv = img - lstride;
-      const float* nxt = img + lstride;
-      const size_t q = (size_t)r * pitch + c;
-      const float dD0 = (img[q + 1] - img[q - 1]) * deriv_scale;
-      const float dD1 = (img[q + pitch] - img[q - pitch]) * deriv_scale;
-      const float dD2 = (nxt[q] - prv[q]) * deriv_scale;
-      const float v2 = img[q] * 2.f;
-      const float dxx = (img[q + 1] + img[q - 1] - v2) * second_deriv_scale;
-      const float dyy = (img[q + pitch] + img[q - pitch] - v2) * second_deriv_scale;
-      const float dss = (nxt[q] + prv[q] - v2) * second_deriv_scale;
-      const float dxy = (img[q + pitch + 1] - img[q + pitch - 1] - img[q - pitch + 1] + img[q - pitch - 1]) * cross_deriv_scale;
-      const float dxs = (nxt[q + 1] - nxt[q - 1] - prv[q + 1] + prv[q - 1]) * cross_deriv_scale;
-      const float dys = (nxt[q + pitch] - nxt[q - pitch] - prv[q + pitch] + prv[q - pitch]) * cross_deriv_scale;
-      const float a00 = dxx, a01 = dxy, a02 = dxs, a11 = dyy, a12 = dys, a22 = dss;
-      const float m0 = a11 * a22 - a12 * a12, m1 = a01 * a22 - a12 * a02, m2 = a01 * a12 - a11 * a02;
-      const float det = a00 * m0 - a01 * m1 + a02 * m2;
-      float X0 = 0, X1 = 0, X2 = 0;
-      if (det != 0.f) {
-        const float d = __fdiv_rn(1.f, det);
-        X0 = d * (dD0 * m0 - a01 * (dD1 * a22 - a12 * dD2) + a02 * (dD1 * a12 - a11 * dD2));
-        X1 = d * (a00 * (dD1 * a22 - a12 * dD2) - dD0 * m1 + a02 * (a01 * dD2 - dD1 * a02));
-        X2 = d * (a00 * (a11 * dD2 - dD1 * a12) - a01 * (a01 * dD2 - dD1 * a02) + dD0 * m2);
-      }
-      xi = -X2; xr = -X1; xc = -X0;
-      if (fabsf(xi) < 0.5f && fabsf(xr) < 0.5f && fabsf(xc) < 0.5f) break;
-      const float big = (float)(INT32_MAX / 3);
-      if (fabsf(xi) > big || fabsf(xr) > big || fabsf(xc) > big) { ok = false; break; }
-      c += __float2int_rn(xc); r += __float2int_rn(xr); layer += __float2int_rn(xi);
-      if (layer < 1 || layer > nl || c < SIFT_BORDER || c >= cols - SIFT_BORDER || r < SIFT_BORDER || r >= rows - SIFT_BORDER) {
-        ok = false; break;
-      }
-    }
-    if (it >= 5) ok = false;
-    float kx = 0, ky = 0, ksize = 0, kresp = 0; int koct = 0;
-    if (ok) {
-      const float* img = dbase + (size_t)layer * lstride;
-      const float* prv = img - lstride;
-      const float* nxt = img + lstride;
-      const size_t q = (size_t)r * pitch + c;
-      const float dD0 = (img[q + 1] - img[q - 1]) * deriv_scale;
-      const float dD1 = (img[q + pitch] - img[q - pitch]) * deriv_scale;
-      const float dD2 = (nxt[q] - prv[q]) * deriv_scale;
-      const float t = dD0 * xc + dD1 * xr + dD2 * xi;
-      const float contr = img[q] * img_scale + t * 0.5f;
-      if (fabsf(contr) * nl < contrast_thr) ok = false;
-      const float v2 = img[q] * 2.f;
-      const float dxx = (img[q + 1] + img[q - 1] - v2) * second_deriv_scale;
-      const float dyy = (img[q + pitch] + img[q - pitch] - v2) * second_deriv_scale;
-      const float dxy = (img[q + pitch + 1] - img[q + pitch - 1] - img[q - pitch + 1] + img[q - pitch - 1]) * cross_deriv_scale;
-      const float tr = dxx + dyy, det = dxx * dyy - dxy * dxy;
-      if (det <= 0 || tr * tr * edge_thr >= (edge_thr + 1) * (edge_thr + 1) * det) ok = false;
-      kx = (c + xc) * (float)(1 << o);
-      ky = (r + xr) * (float)(1 << o);
-      koct = o + (layer << 8) + (__float2int_rn((xi + 0.5f) * 255.f) << 16);
-      ksize = sigma * vo_expf(__fdiv_rn((float)layer + xi, (float)nl) * 0.693147180559945f) * (float)(1 << o) * 2.f;
-      kresp = fabsf(contr);
-    }
-    if (!ok) continue;   // warp-uniform: every lane computed the same values
-
+    const float kx = rk.x, ky = rk.y, ksize = rk.size, kresp = rk.resp; const int koct = rk.oct_word;
     // ---- orientation histogram over the (2*radius+1)^2 window of gauss[o][layer]
     const float scl_octv = ksize * 0.5f / (float)(1 << o);
     const int radius = __float2int_rn(4.5f * scl_octv);
@@ -1465,6 +1501,7 @@ static int get_plan(vo_ctx* ctx, int rows, int cols, int batch, const vo_sift_op
   A((void**)&p->raw, (size_t)batch * kp_cap * sizeof(vo_keypoint)); A((void**)&p->sorted, (size_t)batch * kp_cap * sizeof(vo_keypoint));
   A((void**)&p->final_kp, (size_t)batch * kp_cap * sizeof(vo_keypoint)); A((void**)&p->desc, (size_t)batch * kp_cap * 128 * sizeof(float));
   A((void**)&p->trig, (size_t)batch * kp_cap * sizeof(float2));
+  A((void**)&p->refined, (size_t)batch * p->cand_cap * 24);
   if (e != cudaSuccess) { set_error("vo_sift: device allocation failed: %s", cudaGetErrorString(e)); sift_plan_destroy(p); return VO_ERR_CUDA; }
   {
     EncodeTiledFn enc = get_encode_tiled();
@@ -1563,8 +1600,9 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
   }
   {
     dim3 g(ctx->num_sms * 4 / (batch > 4 ? 4 : 1), batch);
-    ProfScope ps(ctx, st, "sift_refine_orient");
-    sift_refine_orient_kernel<<<g, 128, 0, st>>>(p->gauss, p->dog, oi, p->batch, nl, contrast_cv, o.edge_threshold, o.sigma, p->cand, p->cand_cap, p->counters, p->raw, p->kp_cap);
+    ProfScope ps(ctx, st, "sift_refine_orient", 0.0, 0.0, 2);
+    sift_refine_kernel<<<dim3(div_up(p->cand_cap / 4, 128), batch), 128, 0, st>>>(p->dog, oi, p->batch, nl, contrast_cv, o.edge_threshold, o.sigma, p->cand, p->cand_cap, p->counters, p->refined);
+    sift_orient_kernel<<<g, 128, 0, st>>>(p->gauss, oi, p->batch, p->refined, p->cand_cap, p->counters, p->raw, p->kp_cap);
   }
   {
     dim3 g(p->kp_cap / 256, batch);
