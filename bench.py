@@ -170,7 +170,9 @@ def run_reference(args, rank, world):
     import multiprocessing as mp
     from vo_b200 import synth
     cores = os.cpu_count() or 1
-    n = cores                      # frames per step: one per core (+1 halo frame)
+    # frames per step: one per core (+1 halo frame); fewer when many steps are asked for, so that the whole
+    # run stays within a few minutes (a step of `cores` frames takes ~7 s of wall time)
+    n = max(2, min(cores, int(cores * 20 / max(args.steps + args.warmup, 1))))
     left, right = synth.shift_stream(n + 1, seed=99, h=H, w=W)
     ctxm = mp.get_context("fork")
     with ctxm.Pool(cores) as pool:
@@ -272,23 +274,28 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ctx = vo_b200.Context(local_rank)
+    # `--inflight` batches are kept in flight: one context (own stream, own device buffers) per batch slot,
+    # each driven by its own host thread (the C calls release the GIL).  While one batch is in its
+    # latency-bound matching / pose tail, or waiting for its H2D copy, another one fills the SMs.
+    n_ctx = max(1, args.inflight)
+    ctxs = [vo_b200.Context(local_rank) for _ in range(n_ctx)]
+    ctx = ctxs[0]
     pk = peaks()
     B = args.batch
     n_batches = min(args.steps + args.warmup, 4)
     left, right = make_frames(n_batches, B, seed=20260 + 7919 * rank)
     dleft, dright = left.cuda(), right.cuda()
-    stream = torch.cuda.ExternalStream(ctx.stream)
+    streams = [torch.cuda.ExternalStream(c.stream) for c in ctxs]
     P0, P1 = synth.KITTI_P0, synth.KITTI_P1
 
-    def step_dev(i):
+    def step_dev(i, c):
         b = i % n_batches
-        return vo.run_frames(None, None, P0, P1, seed=1, first_frame=i * B, ctx=ctx,
+        return vo.run_frames(None, None, P0, P1, seed=1, first_frame=i * B, ctx=c,
                              device_ptrs=(dleft[b].data_ptr(), dright[b].data_ptr(), B + 1, H, W))
 
-    def step_host(i):
+    def step_host(i, c):
         b = i % n_batches
-        return vo.run_frames(left[b].numpy(), right[b].numpy(), P0, P1, seed=1, first_frame=i * B, ctx=ctx)
+        return vo.run_frames(left[b].numpy(), right[b].numpy(), P0, P1, seed=1, first_frame=i * B, ctx=c)
 
     def barrier():
         torch.cuda.synchronize()
@@ -296,22 +303,39 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, profile):
-        for i in range(args.warmup):
-            step_fn(i)
+    def timed(step_fn, profile, use):
+        """Exactly args.steps steps after args.warmup warm-up steps, spread round-robin over the first
+        `use` contexts; device time from CUDA events on the launching streams, max over streams and ranks."""
+        for i in range(args.warmup * use):
+            step_fn(i, ctxs[i % use])
         barrier()
         if profile:
             ctx.profile_enable(True)
-        launches0 = ctx.kernel_launches()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        counts = []
-        for i in range(args.steps):
-            rel, status, cnt = step_fn(args.warmup + i)
-            counts.append(cnt)
-        e1.record(stream)
+        launches0 = sum(c.kernel_launches() for c in ctxs)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(use)]
+        e0.record(streams[0])
+        results = [None] * args.steps
+
+        nxt = iter(range(args.steps))
+        lock = threading.Lock()
+
+        def worker(k):   # batch slots pull the next step from a shared queue
+            while True:
+                with lock:
+                    i = next(nxt, None)
+                if i is None:
+                    break
+                results[i] = step_fn(args.warmup * use + i, ctxs[k])
+            e1[k].record(streams[k])
+        if use == 1:
+            worker(0)
+        else:
+            th = [threading.Thread(target=worker, args=(k,)) for k in range(use)]
+            [t.start() for t in th]
+            [t.join() for t in th]
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms = max(e0.elapsed_time(e) for e in e1)
         prof = ctx.profile() if profile else None
         if profile:
             ctx.profile_enable(False)
@@ -319,13 +343,17 @@ def run_ours(args, rank, world, local_rank):
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, prof, ctx.kernel_launches() - launches0, counts, (rel, status)
+        counts = [r[2] for r in results]
+        return ms, prof, sum(c.kernel_launches() for c in ctxs) - launches0, counts, results[-1][:2]
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_dev, prof, launches, counts, last = timed(step_dev, profile=True)
+    ms_dev, _, launches, counts, last = timed(step_dev, profile=False, use=n_ctx)
     clocks = sampler.stop()
-    ms_host, _, _, _, _ = timed(step_host, profile=False)
+    ms_host, _, _, _, _ = timed(step_host, profile=False, use=n_ctx)
+    # roofline pass: the same steps, one batch at a time on one stream, with the library's per-stage CUDA
+    # events switched on (they cost a few % of a step, and overlapping batches would smear the stages)
+    ms_prof, prof, _, counts, _ = timed(step_dev, profile=True, use=1)
     frames = args.steps * B * world
     value = frames / (ms_dev * 1e-3)
     e2e = frames / (ms_host * 1e-3)
@@ -380,7 +408,8 @@ def run_ours(args, rank, world, local_rank):
     roofline_all = [roof(k) for k in sorted(kern, key=lambda k: -kern[k]["ms"])]
     gemm_ms = prof.get("match_gemm_topk", dict(ms=0))["ms"]
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                ms_per_step=ms_dev / args.steps, ms_per_step_profiled_serial=ms_prof / args.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32 (SIFT) / u8->s32 exact-integer tensor-core GEMM (match) / f64 (triangulate, P3P)",
                 data="synthetic",
                 config=dict(workload="VO.m loop body on synthetic 1241x376 stereo frames (BASELINE.json configs[1]: "
@@ -388,6 +417,11 @@ def run_ours(args, rank, world, local_rank):
                             frames_per_step_per_gpu=B, halo_frames=1, rows=H, cols=W,
                             l2="per-step working set ~%.1f GB of pyramids >> 126 MB L2; %d distinct input batches"
                                % ((B + 1) * 2 * 110e6 / 1e9, n_batches),
+                            batches_in_flight=n_ctx,
+                            timing="value / e2e: exactly `steps` steps with `batches_in_flight` batches in flight (one stream "
+                                   "and host thread per batch slot), CUDA events on the launching streams; roofline / "
+                                   "stage_share / ms_per_step_profiled_serial: the same steps run one batch at a time with "
+                                   "per-stage CUDA events on",
                             parallelism=f"frame-sharded x{world}, no data-path collective"),
                 e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=int((B + 1) * 2 * H * W),
                          d2h_bytes_per_step=int((B + 1) * (16 * 8 + 4 + 4 * 4 + 5 * 4 + 2 * 16)), ms_per_step=ms_host / args.steps),
@@ -409,9 +443,10 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="new frames per step per GPU")
+    ap.add_argument("--inflight", type=int, default=3, help="batches kept in flight per GPU (contexts / streams / host threads)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

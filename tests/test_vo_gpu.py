@@ -102,3 +102,17 @@ def test_trajectory_parity_on_kitti_ground_truth_motion(ctx):
     assert ng == nc and ng >= 6
     assert abs(tg - tc) <= 0.02 * tc + 1e-12 and abs(rg - rc) <= 0.02 * rc + 1e-12, (tg, tc, rg, rc)
     assert tg < 0.10, tg                               # and the odometry itself is sane: < 10 % drift
+
+
+def test_frame_pipeline_equals_serial(ctx):
+    """Batches in flight on several contexts/streams return exactly what one batch at a time returns."""
+    from vo_b200 import vo, synth
+    left, right = _frames(7, seed=21)
+    batches = [(left[0:3], right[0:3], 0), (left[2:5], right[2:5], 2), (left[4:7], right[4:7], 4)]
+    pipe = vo.FramePipeline(depth=3)
+    got = pipe.map(batches, synth.KITTI_P0, synth.KITTI_P1, seed=5)
+    pipe.close()
+    for (l, r, first), g in zip(batches, got):
+        want = vo.run_frames(l, r, synth.KITTI_P0, synth.KITTI_P1, seed=5, first_frame=first, ctx=ctx)
+        for a, b in zip(g, want):
+            assert np.array_equal(a, b)
