@@ -12,7 +12,7 @@ G, P = os.path.join(R, "gpurun_out"), os.path.join(R, "profiles")
 IMAGES = 36.0   # tools/prof_targets.py 8: 2 steps x 9 stereo frames
 
 STAGE_OF = [("sift_descriptor_kernel", "sift_descriptor"), ("sift_trig_kernel", "sift_descriptor"),
-            ("sift_blur_tma_kernel", "sift_blur_tma_kernel"), ("sift_refine_orient_kernel", "sift_refine_orient"),
+            ("sift_blur_tma_kernel", "sift_blur_tma_kernel"), ("sift_refine_kernel", "sift_refine_orient"), ("sift_orient_kernel", "sift_refine_orient"),
             ("sift_extrema_kernel", "sift_extrema"), ("sift_base_stream_kernel", "sift_base_upsample_blur"),
             ("sift_small_octaves_kernel", "sift_blur_dog_small"), ("sift_downsample_kernel", "sift_downsample"),
             ("sift_rank_bucket_kernel", "sift_sort_dedupe"), ("sift_dedupe_kernel", "sift_sort_dedupe")]
