@@ -1196,6 +1196,7 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
     const float scl = size * 0.5f;
     const int px = __float2int_rn(ptx), py = __float2int_rn(pty);
     const float2 cs = trig[(size_t)b * kp_cap + ki];
+    const float* img_c = img + ((ptrdiff_t)py * pitch + px);
     const float bins_per_rad = N / 360.f, exp_scale = -1.f / (D * D * 0.5f);
     const float hist_width = 3.0f * scl;
     int radius = __float2int_rn(hist_width * 1.4142135623730951f * (D + 1) * 0.5f);
@@ -1216,9 +1217,10 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
       sm.rbin = sm.r_rot + D / 2 - 0.5f; sm.cbin = sm.c_rot + D / 2 - 0.5f;
       const int r = py + i, c = px + j;
       sm.ok = sm.rbin > -1 && sm.rbin < D && sm.cbin > -1 && sm.cbin < D && r > 0 && r < rows - 1 && c > 0 && c < cols - 1;
-      if (sm.ok) {
-        const float* q = img + (size_t)r * pitch + c;
-        sm.xp = __ldg(q + 1); sm.xm = __ldg(q - 1); sm.yu = __ldg(q - pitch); sm.yd = __ldg(q + pitch);
+      if (sm.ok) {   // 32-bit offsets from the keypoint's centre pixel (fewer 64-bit address operations)
+        const int off = i * pitch + j;
+        sm.xp = __ldg(img_c + (off + 1)); sm.xm = __ldg(img_c + (off - 1));
+        sm.yu = __ldg(img_c + (off - pitch)); sm.yd = __ldg(img_c + (off + pitch));
       }
     };
     auto accumulate = [&](const Samp& sm) {
