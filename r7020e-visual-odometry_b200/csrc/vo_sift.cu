@@ -411,98 +411,10 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
   }
 }
 
-constexpr int ST_W = 128, ST_CH = 16;
-template <int R>
-__global__ void __launch_bounds__(256, 3)
-sift_blur_stream_kernel(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ dog,
-                        int h, int w, int pitch, int seg_rows, const Taps taps) {
-  constexpr int RP = (R + 3) & ~3;       // halo rounded up to whole float4s
-  constexpr int NWIN = 4 + 2 * RP;
-  constexpr int RING = 64;               // power of two >= ST_CH + 2R (42 at R = 13): slot = row & 63
-  static_assert(ST_CH + 2 * R <= RING, "ring too small");
-  __shared__ __align__(16) float ring[RING][ST_W];
-  const int b = blockIdx.z;
-  const int x0 = blockIdx.x * ST_W;
-  const int ys = blockIdx.y * seg_rows, ye = min(ys + seg_rows, h);
-  const size_t img_off = (size_t)b * h * pitch;
-  const float* img = src + img_off;
-  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-  const bool interior = (x0 - RP >= 0) && (x0 + ST_W + R <= w);
-
-  auto row_pass = [&](int row) {
-    float win[NWIN];
-    if (interior) {
-      const float4* p4 = reinterpret_cast<const float4*>(img + (size_t)row * pitch + x0 + 4 * lane - RP);
-#pragma unroll
-      for (int q = 0; q < NWIN / 4; ++q) {
-        const float4 v = __ldg(p4 + q);
-        win[4 * q] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w;
-      }
-    } else {
-      const float* pr = img + (size_t)row * pitch;
-#pragma unroll
-      for (int q = RP - R; q < NWIN - (RP - R); ++q) win[q] = __ldg(pr + reflect101(x0 + 4 * lane - RP + q, w));
-    }
-    float acc[4];
-#pragma unroll
-    for (int o = 0; o < 4; ++o) acc[o] = taps.k[0] * win[RP + o];
-#pragma unroll
-    for (int i = 1; i <= R; ++i) {
-#pragma unroll
-      for (int o = 0; o < 4; ++o) acc[o] = fmaf(taps.k[i], win[RP + o - i] + win[RP + o + i], acc[o]);
-    }
-    *reinterpret_cast<float4*>(&ring[row & (RING - 1)][4 * lane]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  };
-
-  // prologue: the R rows above the segment and the first R rows of it
-  for (int row = max(ys - R, 0) + wrp; row < min(ys + R, h); row += 8) row_pass(row);
-  const int cp = tid & 63, rg = tid >> 6;    // column pair, 4-row group inside the chunk
-  const int x = x0 + 2 * cp;
-  for (int yc = ys; yc < ye; yc += ST_CH) {
-    for (int row = yc + R + wrp; row < min(yc + ST_CH + R, h); row += 8) row_pass(row);
-    __syncthreads();
-    const int yf = yc + rg * 4;              // first output row of this thread
-    if (yf < ye && x < w) {
-      u64 win[4 + 2 * R];
-      if (yf - R >= 0 && yf + 3 + R < h) {     // no reflection: consecutive ring slots
-#pragma unroll
-        for (int q = 0; q < 4 + 2 * R; ++q)
-          win[q] = *reinterpret_cast<const u64*>(&ring[(yf - R + q) & (RING - 1)][2 * cp]);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4 + 2 * R; ++q) {
-          const int ry = reflect101(yf - R + q, h);
-          win[q] = *reinterpret_cast<const u64*>(&ring[ry & (RING - 1)][2 * cp]);
-        }
-      }
-      u64 acc[4];
-      const u64 k0 = f2_bcast(taps.k[0]);
-#pragma unroll
-      for (int o = 0; o < 4; ++o) acc[o] = f2_mul(k0, win[R + o]);
-#pragma unroll
-      for (int i = 1; i <= R; ++i) {
-        const u64 ki = f2_bcast(taps.k[i]);
-#pragma unroll
-        for (int o = 0; o < 4; ++o) acc[o] = f2_fma(ki, f2_add(win[R + o - i], win[R + o + i]), acc[o]);
-      }
-#pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        const int y = yf + o;
-        if (y < ye) {
-          const size_t g = (size_t)y * pitch + x;
-          const float2 c = __ldg(reinterpret_cast<const float2*>(img + g));
-          const float2 v = *reinterpret_cast<const float2*>(&acc[o]);
-          *reinterpret_cast<float2*>(dst + img_off + g) = v;
-          *reinterpret_cast<float2*>(dog + img_off + g) = make_float2(v.x - c.x, v.y - c.y);
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
+constexpr int ST_W = 128, ST_CH = 16;   // strip width / rows per chunk of the streaming base-image kernel
 
 // Base image, streaming: u8 -> 2x bilinear upsample (cv::resize convention) -> blur(sig_diff), same
-// strip-walking structure as sift_blur_stream_kernel.  The upsample is separable and the contract's
+// strip-walking structure as sift_blur_tma_kernel (without TMA: the source is the small u8 image).  The upsample is separable and the contract's
 // value  wya*(wxa*a + wxb*b) + wyb*(wxa*c + wxb*d)  only mixes two SOURCE rows, so the horizontal
 // blends h(r, x) = wxa*img[r][xa] + wxb*img[r][xb] are formed once per source row into a small ring
 // and every upsampled sample is 2 multiplies + 1 add on top of them (identical operations, identical
@@ -1383,22 +1295,6 @@ static int launch_blur_t(const float* src, const uint8_t* src8, float* dst, floa
   }
   dim3 grid(div_up(w, TILE_W), div_up(h, TILE_H), batch);
   sift_blur_dog_kernel<RT, U8><<<grid, 256, smem, st>>>(src, src8, dst, dog, h, w, pitch, rows8, cols8, t);
-  return VO_OK;
-}
-
-template <int R>
-static int launch_stream_t(const float* src, float* dst, float* dog, int h, int w, int pitch, int batch, const Taps& t,
-                           int num_sms, cudaStream_t st) {
-  const int strips = div_up(w, ST_W);
-  // enough blocks to fill the GPU a few times over; segments are whole chunks
-  int n_seg = 1;
-  const int target = num_sms * 8;
-  if (strips * batch < target) n_seg = div_up(target, strips * batch);
-  int seg_rows = div_up(div_up(h, n_seg), ST_CH) * ST_CH;
-  if (seg_rows < 4 * ST_CH) seg_rows = 4 * ST_CH;
-  n_seg = div_up(h, seg_rows);
-  dim3 grid(strips, n_seg, batch);
-  sift_blur_stream_kernel<R><<<grid, 256, 0, st>>>(src, dst, dog, h, w, pitch, seg_rows, t);
   return VO_OK;
 }
 
