@@ -183,3 +183,30 @@ print("pairs ok")
         env = dict(os.environ, VO_MATCH_PAIRS="1", VO_MATCH_PAIR_TILE=tile)
         r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "pairs ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_match_large_property(ctx):
+    """Above 16384 query rows matchFeatures takes the count/scan/scatter compaction path.  No oracle run
+    at this size: queries are noisy copies of a permutation of the landmarks (plus unrelated rows), so
+    the expected pairs are known by construction; cross-checked against the exact top-2 of the same data."""
+    import vo_b200
+    import vo_b200.api as api
+    n = 20000
+    rng = np.random.default_rng(8)
+    f2 = sift_like_descriptors(n, 4321)
+    perm = rng.permutation(n)
+    f1 = sift_like_descriptors(n, 999)
+    copied = rng.random(n) < 0.6
+    noisy = np.clip(np.rint(f2[perm] + rng.normal(0, 4.0, (n, 128))), 0, 255).astype(np.float32)
+    f1[copied] = noisy[copied]
+    pairs, metric = vo_b200.matchFeatures(f1, f2, return_metric=True, ctx=ctx)
+    assert np.all(np.diff(pairs[:, 0].astype(np.int64)) > 0)                 # ascending, no duplicates
+    assert np.array_equal(pairs[:, 0], np.nonzero(copied)[0].astype(np.uint32))
+    assert np.array_equal(pairs[:, 1], perm[copied].astype(np.uint32))
+    j1, s1, s2 = api.match_top2(f1, f2, ctx=ctx)
+    keep = (s1 <= np.float32(0.04)) & (s1 / np.maximum(s2, np.float32(1e-6)) <= np.float32(0.6))
+    assert np.array_equal(np.nonzero(keep)[0].astype(np.uint32), pairs[:, 0])
+    assert np.array_equal(j1[keep], pairs[:, 1]) and np.array_equal(s1[keep].view(np.uint32), metric.view(np.uint32))
+    # Unique at this size (forward-backward): copies are mutual nearest neighbours, so nothing is lost
+    upairs = vo_b200.matchFeatures(f1, f2, Unique=True, ctx=ctx)
+    assert np.array_equal(upairs, pairs)
