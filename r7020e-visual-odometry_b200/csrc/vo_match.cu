@@ -453,31 +453,43 @@ match_topk_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer: D=s32, A=B=u8, K-major, N=128, M=128 (two panels), K=32 per MMA =====
+    // ===== MMA issuer: D=s32, A=B=u8, K-major, N=128, M=128 (two panels), K=32 per MMA =====
+    // The whole warp runs the loop converged and ONE elected lane issues: every value below is
+    // warp-uniform, so the descriptors live in uniform registers (inside an `if (lane == 0)` region the
+    // compiler rebuilt and re-broadcast them for every MMA, and the issuing thread's own instruction
+    // stream -- about 100 cycles per MMA -- paced the tile loop, not the tensor pipe).
+    {
       const uint32_t idesc = (2u << 4) | ((uint32_t)(UBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(bar_a_full, 0);
       tc_fence_after();
+      const uint64_t ad0 = umma_desc_sw128(sA), ad1 = umma_desc_sw128(sA + U_TILE_BYTES), bd0 = umma_desc_sw128(sB);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);
         mbar_wait(bar_b_full + 8 * stage, phase);
         tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * 256, d1 = d0 + UBN;
+        const uint64_t bds = bd0 + (uint64_t)(stage * (U_TILE_BYTES >> 4));
+        uint32_t elected;
+        asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(elected));
+        if (elected) {
+          asm volatile(
+              "{\n\t.reg .pred p0, p1;\n\tsetp.ne.b32 p0, 0, 0;\n\tsetp.eq.b32 p1, 0, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::i8 [%0], %2, %4, %5, p0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::i8 [%1], %3, %4, %5, p0;\n\t}"
+              ::"r"(d0), "r"(d1), "l"(ad0), "l"(ad1), "l"(bds), "r"(idesc) : "memory");
 #pragma unroll
-        for (int pn = 0; pn < 2; ++pn) {
-          const uint32_t d_tmem = tmem_base + acc * 256 + pn * UBN;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = umma_desc_sw128(sA + pn * U_TILE_BYTES + k * 32);
-            const uint64_t bd = umma_desc_sw128(sB + stage * U_TILE_BYTES + k * 32);
+          for (int k = 1; k < 4; ++k)
             asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-                ::"r"(d_tmem), "l"(ad), "l"(bd), "r"(idesc), "r"((uint32_t)(k != 0))
+                "{\n\t.reg .pred p1;\n\tsetp.eq.b32 p1, 0, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::i8 [%0], %2, %4, %5, p1;\n\t"
+                "tcgen05.mma.cta_group::1.kind::i8 [%1], %3, %4, %5, p1;\n\t}"
+                ::"r"(d0), "r"(d1), "l"(ad0 + (uint64_t)(2 * k)), "l"(ad1 + (uint64_t)(2 * k)), "l"(bds + (uint64_t)(2 * k)), "r"(idesc)
                 : "memory");
-          }
+          tc_commit(bar_b_empty + 8 * stage);
+          tc_commit(bar_t_full + 8 * acc);
         }
-        tc_commit(bar_b_empty + 8 * stage);
-        tc_commit(bar_t_full + 8 * acc);
+        __syncwarp();
         if (++stage == U_STAGES) { stage = 0; phase ^= 1; }
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
@@ -566,6 +578,238 @@ match_topk_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       out[0] = make_uint2(__float_as_uint(top.k1), top.i1);
       out[1] = make_uint2(__float_as_uint(top.k2), top.i2);
       out[2] = make_uint2(__float_as_uint(top.k3), top.i3);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// --------------------------------------------------- exact-integer path, A operand in TMEM
+// tools/ubench_tmem.cu: a cta_group::1 MMA with both operands in shared memory is bound by the rate at
+// which the tensor pipe reads them (about 75 B/cycle/SM).  The A panels of a CTA never change, so here
+// they live in TMEM (written once with tcgen05.st: lane = row, 32 columns = the row's 128 u8) and the
+// MMA takes A from TMEM ("TS" form); shared memory then only feeds B.  TMEM budget: 64 columns for the
+// two A panels leave 448, i.e. two accumulator stages of 2 panels x 96 columns, so tiles are 96 columns
+// wide and there are 24 epilogue warps (panel, TMEM lane quarter, 32-column third), one chunk each.
+constexpr int TN = 96;                           // tile width (columns)
+constexpr int T_TILE_BYTES = TN * 128;           // 12 KB of u8 B rows
+constexpr int T_STAGES = 10;
+constexpr int T_EPI_WARPS = 24;
+constexpr int T_THREADS = (2 + T_EPI_WARPS) * 32;
+constexpr int T_ACOL = 2 * 2 * TN;               // TMEM column of A panel 0 (after the accumulators)
+constexpr int T_SMEM_BYTES = T_STAGES * T_TILE_BYTES + 256 + UBM * 4 + T_EPI_WARPS * U_SCRATCH_INTS * 4;
+
+__global__ void __launch_bounds__(T_THREADS, 1)
+match_topk_u8ts_kernel(const __grid_constant__ CUtensorMap tmB, const uint8_t* __restrict__ u8a, int a_alloc,
+                       const float* __restrict__ invb_base, int invb_stride, const float* __restrict__ inva_base,
+                       int inva_stride, const int* __restrict__ invb_max_bits, const int* __restrict__ n1p,
+                       int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
+                       const int* __restrict__ nonint_flag, int n_splits, uint2* __restrict__ cand_base,
+                       size_t cand_stride, int slots_per_row, float key_floor, float* __restrict__ dbg_c, int dbg_ld) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if (*nonint_flag != 0) return;
+  const int prob = blockIdx.z;
+  const int n1 = min(n1p[prob * n1_stride], cap1), n2 = min(n2p[prob * n2_stride], cap2);
+  const int m0 = blockIdx.x * UBM;
+  if (m0 >= n1) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_total = (n2 + TN - 1) / TN;
+  const int split = blockIdx.y;
+  const int t_begin = (int)((long long)split * tiles_total / n_splits);
+  const int t_end = (int)((long long)(split + 1) * tiles_total / n_splits);
+  uint2* cand = cand_base + (size_t)prob * cand_stride;
+  const float* invb = invb_base + (size_t)prob * invb_stride;
+  // epilogue warp -> (panel, lane quarter, column third); a warp may only touch TMEM lanes 32*(warp%4)..
+  const int e = warp - 2, quarter = warp & 3, group = e >> 2, panel = group / 3, third = group - 3 * panel;
+
+  if (t_begin >= t_end) {
+    if (warp >= 2) {
+      const int row = m0 + panel * 128 + quarter * 32 + lane;
+      if (row < n1) {
+        uint2* out = cand + ((size_t)row * slots_per_row + split * 4 + third) * NCAND;
+        for (int c = 0; c < NCAND * (third == 0 ? 1 : 1); ++c) out[c] = make_uint2(__float_as_uint(-INFINITY), 0xFFFFFFFFu);
+        if (third == 0) for (int c = 0; c < NCAND; ++c) out[3 * NCAND + c] = make_uint2(__float_as_uint(-INFINITY), 0xFFFFFFFFu);
+      }
+    }
+    return;
+  }
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) __trap();
+  const uint32_t sB = base;                                   // [T_STAGES] x 12 KB
+  const uint32_t bars = sB + T_STAGES * T_TILE_BYTES;
+  const uint32_t bar_a_full = bars;
+  const uint32_t bar_b_full = bars + 8;
+  const uint32_t bar_b_empty = bar_b_full + 8 * T_STAGES;
+  const uint32_t bar_t_full = bar_b_empty + 8 * T_STAGES;
+  const uint32_t bar_t_empty = bar_t_full + 16;
+  const uint32_t tmem_slot = bar_t_empty + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - base));
+  float* s_thr = reinterpret_cast<float*>(smem_raw + (bars + 256 - base));   // [UBM]
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    mbar_init(bar_a_full, 8);                                 // the 8 warps that write the A panels
+    for (int s = 0; s < T_STAGES; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, T_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + UBM) {
+    const int r = threadIdx.x - 64;
+    float t0 = -INFINITY;
+    if (key_floor > 0.f && m0 + r < n1) {
+      const float ia = inva_base[(size_t)prob * inva_stride + m0 + r];
+      if (ia > 0.f) t0 = __fdiv_rn(key_floor, ia);
+    }
+    s_thr[r] = t0;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer: B tiles only =====
+      int stage = 0; uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+        mbar_expect_tx(bar_b_full + 8 * stage, T_TILE_BYTES);
+        tma_load_3d(sB + stage * T_TILE_BYTES, &tmB, bar_b_full + 8 * stage, 0, t * TN, prob);
+        if (++stage == T_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer: D=s32 [tmem], A=u8 [tmem], B=u8 smem descriptor, M=128, N=96, K=32 =====
+      const uint32_t idesc = (2u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      mbar_wait(bar_a_full, 0);
+      tc_fence_after();
+      const uint64_t bd0 = umma_desc_sw128(sB);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);
+        mbar_wait(bar_b_full + 8 * stage, phase);
+        tc_fence_after();
+        const uint64_t bds = bd0 + (uint64_t)(stage * (T_TILE_BYTES >> 4));
+#pragma unroll
+        for (int pn = 0; pn < 2; ++pn) {
+          const uint32_t d_tmem = tmem_base + acc * (2 * TN) + pn * TN;
+          const uint32_t a_tmem = tmem_base + T_ACOL + pn * 32;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+                ::"r"(d_tmem), "r"(a_tmem + k * 8), "l"(bds + (uint64_t)(2 * k)), "r"(idesc), "r"((uint32_t)(k != 0))
+                : "memory");
+          }
+        }
+        tc_commit(bar_b_empty + 8 * stage);
+        tc_commit(bar_t_full + 8 * acc);
+        if (++stage == T_STAGES) { stage = 0; phase ^= 1; }
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int row_in_cta = panel * 128 + quarter * 32 + lane;
+    const int row = m0 + row_in_cta;
+    if (third == 0) {   // these 8 warps first put the A panels into TMEM: lane = row, 32 columns = 128 u8
+      uint32_t a[32];
+      const uint4* src = reinterpret_cast<const uint4*>(u8a + ((size_t)prob * a_alloc + row) * 128);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const uint4 v = __ldg(src + q); a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w; }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(T_ACOL + panel * 32);
+      asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+          "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+          "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+          ::"r"(taddr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+            "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]),
+            "r"(a[16]), "r"(a[17]), "r"(a[18]), "r"(a[19]), "r"(a[20]), "r"(a[21]), "r"(a[22]), "r"(a[23]),
+            "r"(a[24]), "r"(a[25]), "r"(a[26]), "r"(a[27]), "r"(a[28]), "r"(a[29]), "r"(a[30]), "r"(a[31])
+          : "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a_full);
+    }
+    const float bmax = __int_as_float(invb_max_bits[prob]);
+    const float bnorm = bmax > 0.f ? __fdiv_rn(1.0f, bmax) : 0.f;
+    int* scr = reinterpret_cast<int*>(s_thr + UBM) + e * U_SCRATCH_INTS;
+    Top3 top; top.init();
+    float thr = s_thr[row_in_cta];
+    int thr_raw = raw_bound(thr, bnorm);
+    if (row >= n1) { thr = INFINITY; thr_raw = 0x7fffffff; }
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(bar_t_full + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * (2 * TN) + panel * TN + third * 32);
+      uint32_t r[32];
+      tmem_ld32(tbase, r);
+      const float shared_thr = s_thr[row_in_cta];
+      if (shared_thr > thr) { thr = shared_thr; thr_raw = raw_bound(thr, bnorm); }
+      tmem_ld_wait(r);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
+      const int j0 = t * TN + third * 32;
+      if (dbg_c != nullptr && row < n1) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (j0 + c < n2) dbg_c[(size_t)row * dbg_ld + j0 + c] = (float)(int)r[c];
+      }
+      int l1[12];
+#pragma unroll
+      for (int q = 0; q < 10; ++q) l1[q] = imax3((int)r[3 * q], (int)r[3 * q + 1], (int)r[3 * q + 2]);
+      l1[10] = (int)r[30]; l1[11] = (int)r[31];
+      const int a0 = imax3(l1[0], l1[1], l1[2]), a1 = imax3(l1[3], l1[4], l1[5]);
+      const int a2 = imax3(l1[6], l1[7], l1[8]), a3 = imax3(l1[9], l1[10], l1[11]);
+      const int m = max(imax3(a0, a1, a2), a3);
+      const unsigned flagged = __ballot_sync(0xffffffffu, m > thr_raw);
+      if (flagged) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) scr[c * 33 + lane] = (int)r[c];
+        const int jc = j0 + lane;
+        const float ib = (jc < n2) ? invb[jc] : 0.f;
+        __syncwarp();
+        unsigned f = flagged;
+        while (f) {
+          const int L = __ffs(f) - 1;
+          f &= f - 1;
+          const float key = __fmul_rn((float)scr[lane * 33 + L], ib);
+          float thr_l = __shfl_sync(0xffffffffu, thr, L);
+          unsigned cm = __ballot_sync(0xffffffffu, jc < n2 && key > thr_l);
+          while (cm) {
+            const int c = __ffs(cm) - 1;
+            const float kk = __shfl_sync(0xffffffffu, key, c);
+            if (lane == L && kk > thr) {
+              top.insert(kk, (uint32_t)(j0 + c));
+              if (top.k3 > thr) { thr = top.k3; thr_raw = raw_bound(thr, bnorm); }
+            }
+            thr_l = __shfl_sync(0xffffffffu, thr, L);
+            cm &= __ballot_sync(0xffffffffu, key > thr_l) & ~((2u << c) - 1u);
+          }
+        }
+        __syncwarp();
+      }
+      if (top.k3 > shared_thr) s_thr[row_in_cta] = top.k3;
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+    if (row < n1) {
+      uint2* out = cand + ((size_t)row * slots_per_row + split * 4 + third) * NCAND;
+      out[0] = make_uint2(__float_as_uint(top.k1), top.i1);
+      out[1] = make_uint2(__float_as_uint(top.k2), top.i2);
+      out[2] = make_uint2(__float_as_uint(top.k3), top.i3);
+      if (third == 0)   // the fourth slot of this split is not used by this kernel
+        for (int c = 0; c < NCAND; ++c) out[3 * NCAND + c] = make_uint2(__float_as_uint(-INFINITY), 0xFFFFFFFFu);
     }
   }
   tc_fence_before();
@@ -1380,6 +1624,7 @@ static int make_u8_map(CUtensorMap* map, const uint8_t* base, int rows_alloc, in
 
 static bool g_attr_set = false;
 constexpr bool MATCH_PAIRS_DEFAULT = false;
+constexpr bool MATCH_TS_DEFAULT = false;
 
 MatchFilter make_match_filter(const vo_match_opts& o) {
   MatchFilter f{0.f, 0.f, 0.f};
@@ -1466,6 +1711,12 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   // CTA-pair (cta_group::2) kernel: VO_MATCH_PAIRS=0/1 overrides the default
   static const int pairs_env = [] { const char* e = getenv("VO_MATCH_PAIRS"); return e ? atoi(e) : -1; }();
   const bool use_pairs = pairs_env >= 0 ? pairs_env != 0 : MATCH_PAIRS_DEFAULT;
+  static const int ts_env = [] { const char* e = getenv("VO_MATCH_TS"); return e ? atoi(e) : -1; }();
+  const bool use_ts = !use_pairs && (ts_env >= 0 ? ts_env != 0 : MATCH_TS_DEFAULT);
+  if (use_ts) {
+    const int t_tiles = div_up(B.cap > 0 ? B.cap : 1, TN);
+    if (n_splits > t_tiles) n_splits = t_tiles;
+  }
   static const int pair_tile = [] { const char* e = getenv("VO_MATCH_PAIR_TILE"); return (e && atoi(e) == 256) ? 256 : 128; }();
   if (use_pairs) {
     const int x_tiles = div_up(B.cap > 0 ? B.cap : 1, pair_tile);
@@ -1483,6 +1734,7 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
     VO_TRY(make_u8_map(&tmA8, u8A, a_alloc, n_prob));
     VO_TRY(make_u8_map(&tmB8, u8B, b_alloc, n_prob));
     if (!g_attr_set) {
+      VO_CUDA(cudaFuncSetAttribute(match_topk_u8ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM_BYTES));
       VO_CUDA(cudaFuncSetAttribute(match_topk_u8x2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM_BYTES));
       VO_CUDA(cudaFuncSetAttribute(match_topk_u8x2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM_BYTES));
       VO_CUDA(cudaFuncSetAttribute(match_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -1495,7 +1747,13 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
     match_topk_kernel<<<dim3(a_alloc / BM, n_splits, n_prob), NUM_THREADS, SMEM_BYTES, st>>>(
         tmA, tmB, invB, b_alloc, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap, ctl, kp / BK, n_splits, cand,
         cand_stride, dbg_c, B.cap);
-    if (!use_pairs) {
+    if (use_ts) {
+      CUtensorMap tmB96;
+      VO_TRY(make_u8_map(&tmB96, u8B, b_alloc, n_prob, TN));
+      match_topk_u8ts_kernel<<<dim3(m_blocks, n_splits, n_prob), T_THREADS, T_SMEM_BYTES, st>>>(
+          tmB96, u8A, a_alloc, invB, b_alloc, invA, a_alloc, invb_max, A.count, A.count_stride, A.cap, B.count, B.count_stride,
+          B.cap, ctl, n_splits, cand, cand_stride, n_slots, flt.key_floor, dbg_c, B.cap);
+    } else if (!use_pairs) {
       match_topk_u8_kernel<<<dim3(m_blocks, n_splits, n_prob), NUM_THREADS, U_SMEM_BYTES, st>>>(
           tmA8, tmB8, invB, b_alloc, invA, a_alloc, invb_max, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap,
           ctl, n_splits, cand, cand_stride, n_slots, flt.key_floor, dbg_c, B.cap);
@@ -1538,7 +1796,7 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   }
   match_finalize_kernel<<<dim3(div_up(A.cap, 128), n_prob), 128, 0, st>>>(
       cand, cand_stride, n_slots, ra, rb, dim, invA, a_alloc, invB, b_alloc, A.count, A.count_stride, A.cap, B.count,
-      B.count_stride, B.cap, ctl, use_pairs ? 1 : 0, flt, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
+      B.count_stride, B.cap, ctl, (use_pairs || use_ts) ? 1 : 0, flt, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
   if (B.cap > 0) {
     int scan_grid = ctx->num_sms * 2;
     match_rowscan_kernel<<<scan_grid, 256, 0, st>>>(scan_list, ctl + 1, ra, rb, u8A, u8B, a_alloc, b_alloc, ctl, dim, invA, a_alloc, invB, b_alloc, B.count,
