@@ -686,32 +686,38 @@ match_topk_u8ts_kernel(const __grid_constant__ CUtensorMap tmB, const uint8_t* _
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer: D=s32 [tmem], A=u8 [tmem], B=u8 smem descriptor, M=128, N=96, K=32 =====
+    {  // ===== MMA issuer (warp-converged, one elected lane): D=s32 [tmem], A=u8 [tmem], B=u8 smem, M=128, N=96, K=32 =====
       const uint32_t idesc = (2u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(bar_a_full, 0);
       tc_fence_after();
       const uint64_t bd0 = umma_desc_sw128(sB);
+      const uint32_t a0 = tmem_base + T_ACOL, a1 = a0 + 32;
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);
         mbar_wait(bar_b_full + 8 * stage, phase);
         tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * (2 * TN), d1 = d0 + TN;
         const uint64_t bds = bd0 + (uint64_t)(stage * (T_TILE_BYTES >> 4));
+        uint32_t elected;
+        asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(elected));
+        if (elected) {
+          asm volatile(
+              "{\n\t.reg .pred p0;\n\tsetp.ne.b32 p0, 0, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::i8 [%0], [%2], %4, %5, p0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::i8 [%1], [%3], %4, %5, p0;\n\t}"
+              ::"r"(d0), "r"(d1), "r"(a0), "r"(a1), "l"(bds), "r"(idesc) : "memory");
 #pragma unroll
-        for (int pn = 0; pn < 2; ++pn) {
-          const uint32_t d_tmem = tmem_base + acc * (2 * TN) + pn * TN;
-          const uint32_t a_tmem = tmem_base + T_ACOL + pn * 32;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 1; k < 4; ++k)
             asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
-                ::"r"(d_tmem), "r"(a_tmem + k * 8), "l"(bds + (uint64_t)(2 * k)), "r"(idesc), "r"((uint32_t)(k != 0))
-                : "memory");
-          }
+                "{\n\t.reg .pred p1;\n\tsetp.eq.b32 p1, 0, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::i8 [%0], [%2], %4, %5, p1;\n\t"
+                "tcgen05.mma.cta_group::1.kind::i8 [%1], [%3], %4, %5, p1;\n\t}"
+                ::"r"(d0), "r"(d1), "r"(a0 + 8 * k), "r"(a1 + 8 * k), "l"(bds + (uint64_t)(2 * k)), "r"(idesc) : "memory");
+          tc_commit(bar_b_empty + 8 * stage);
+          tc_commit(bar_t_full + 8 * acc);
         }
-        tc_commit(bar_b_empty + 8 * stage);
-        tc_commit(bar_t_full + 8 * acc);
+        __syncwarp();
         if (++stage == T_STAGES) { stage = 0; phase ^= 1; }
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
@@ -954,17 +960,15 @@ match_topk_u8x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {  // ===== MMA issuer (leader): D=s32, A=B=u8, K-major, M=256 (pair), N=256, K=32 per MMA =====
+    if (rank == 0) {  // ===== MMA issuer (leader CTA, warp-converged, one elected lane): M=256 (pair), N=XN, K=32 per MMA =====
       const uint32_t idesc = (2u << 4) | ((uint32_t)(XN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       mbar_wait(bar_a_full, 0);
       tc_fence_after();
-      // the issuing thread's own instruction stream paces the tile loop, so everything that does not
-      // depend on the tile is hoisted: A descriptors are constants, B descriptors differ by the stage offset
       const uint64_t ad0 = umma_desc_sw128(sA), bd0 = umma_desc_sw128(sB);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       long long c_te = 0, c_bf = 0; const long long c_start = clock64();
       for (int t = t_begin; t < t_end; ++t) {
-        if (clk) {   // debug: where does the issuing thread wait?
+        if (clk) {   // debug: where does the issuing warp wait?
           const long long c0 = clock64();
           mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);
           const long long c1 = clock64();
@@ -977,21 +981,26 @@ match_topk_u8x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * XN;
         const uint64_t bds = bd0 + (uint64_t)(stage * (XB_BYTES >> 4));
-        asm volatile(
-            "{\n\t.reg .pred p0, p1;\n\tsetp.ne.b32 p0, 0, 0;\n\tsetp.eq.b32 p1, 0, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %5, %9, p0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::i8 [%0], %2, %6, %9, p1;\n\t"
-            "tcgen05.mma.cta_group::2.kind::i8 [%0], %3, %7, %9, p1;\n\t"
-            "tcgen05.mma.cta_group::2.kind::i8 [%0], %4, %8, %9, p1;\n\t}"
-            ::"r"(d_tmem), "l"(ad0), "l"(ad0 + 2), "l"(ad0 + 4), "l"(ad0 + 6), "l"(bds), "l"(bds + 2), "l"(bds + 4), "l"(bds + 6),
-              "r"(idesc)
-            : "memory");
-        tc_commit_2sm_mc(bar_b_empty + 8 * stage);
-        tc_commit_2sm_mc(bar_t_full + 8 * acc);
+        uint32_t elected;
+        asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(elected));
+        if (elected) {
+          asm volatile(
+              "{\n\t.reg .pred p0, p1;\n\tsetp.ne.b32 p0, 0, 0;\n\tsetp.eq.b32 p1, 0, 0;\n\t"
+              "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %5, %9, p0;\n\t"
+              "tcgen05.mma.cta_group::2.kind::i8 [%0], %2, %6, %9, p1;\n\t"
+              "tcgen05.mma.cta_group::2.kind::i8 [%0], %3, %7, %9, p1;\n\t"
+              "tcgen05.mma.cta_group::2.kind::i8 [%0], %4, %8, %9, p1;\n\t}"
+              ::"r"(d_tmem), "l"(ad0), "l"(ad0 + 2), "l"(ad0 + 4), "l"(ad0 + 6), "l"(bds), "l"(bds + 2), "l"(bds + 4), "l"(bds + 6),
+                "r"(idesc)
+              : "memory");
+          tc_commit_2sm_mc(bar_b_empty + 8 * stage);
+          tc_commit_2sm_mc(bar_t_full + 8 * acc);
+        }
+        __syncwarp();
         if (++stage == X_STAGES) { stage = 0; phase ^= 1; }
         if (++acc == NS) { acc = 0; acc_phase ^= 1; }
       }
-      if (clk) {
+      if (clk && lane == 0) {
         long long* o = clk + 4 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
         o[0] = clock64() - c_start; o[1] = c_te; o[2] = c_bf; o[3] = t_end - t_begin;
       }
