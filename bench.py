@@ -428,7 +428,7 @@ def run_ours(args, rank, world, local_rank):
                 gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_all=roofline_all, stage_share=shares,
                 keypoints_per_image=float(cnt[:, :2].mean()), tracked_per_frame=float(cnt[:, 6].mean()),
                 match_gflop_per_step=2.0 * mm * 128 / 1e9 / args.steps, match_gemm_ms_per_step=gemm_ms / args.steps)
-    if world == 1:
+    if world == 1 and not args.no_match_leg:
         try:
             line["match_gemm"] = match_gemm_leg(ctx, torch, pk)
         except Exception as e:  # keep the headline line even if the side leg fails
@@ -449,6 +449,7 @@ def main():
     ap.add_argument("--inflight", type=int, default=3, help="batches kept in flight per GPU (contexts / streams / host threads)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-match-leg", action="store_true", help="skip the stand-alone match GEMM sweep (used for the ncu launch list)")
     args = ap.parse_args()
     _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))

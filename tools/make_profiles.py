@@ -93,9 +93,31 @@ def opmix(rep, rx, out, which="0"):
         open(os.path.join(P, out), "w").write(run(sys.executable, os.path.join(R, "tools", "ncu_opmix.py"), src, rx, "24", which))
 
 
+def bench_launches():
+    """ncu launch list of bench.py itself, compared with the live stage shares of the same command run plain."""
+    src, plain = os.path.join(G, "r1_launches_bench.csv"), os.path.join(G, "bench_ll_plain.json")
+    if not (os.path.exists(src) and os.path.exists(plain)):
+        return
+    shutil.copy(src, os.path.join(P, "r1_launches_bench.csv"))
+    md = run(sys.executable, os.path.join(R, "tools", "launches_summary.py"), src)
+    live = json.load(open(plain))
+    shares = "\n".join(f"| `{k}` | {100 * v:.1f} % |" for k, v in live["stage_share"].items())
+    open(os.path.join(P, "r1_launches_bench.md"), "w").write(
+        "# Round 1 -- ncu launch list of `bench.py` itself\n\n"
+        "`python bench.py --steps 3 --warmup 3 --no-cpu --no-match-leg` (exit 0 plain, then the same command under "
+        "`ncu --metrics gpu__time_duration.sum --clock-control none --csv`): every kernel launch of the warm-up, the "
+        "device-resident pass, the host-buffer (e2e) pass and the profiled serial pass -- 30 frame-loop steps of 33 stereo frames.  "
+        "Times under ncu are cold-cache and serialised; the SHARES are what to compare with the live CUDA-event shares below.\n\n"
+        + md + "\n## Live stage shares of the same command run without ncu (`stage_share` of its JSON line)\n\n"
+        "| stage | share of the step |\n|---|---|\n" + shares + "\n\n"
+        f"Live: {live['value']:.0f} frames/s ({live['ms_per_step']:.2f} ms per step with {live['config']['batches_in_flight']} batches in flight, "
+        f"{live['ms_per_step_profiled_serial']:.2f} ms per step in the serial profiled pass).\n")
+
+
 if __name__ == "__main__":
     os.makedirs(P, exist_ok=True)
     launches()
+    bench_launches()
     full("r1_sift2.ncu-rep", "r1_ncu_full_sift.md", "Round 1 -- ncu `--set full`: SIFT, sort, prep and geometry kernels of one frame-loop step (18 images of 1241x376)",
          'ncu --set full --clock-control none --import-source on -k regex:"sift_descriptor_kernel|sift_refine_orient_kernel|sift_extrema_kernel|sift_blur_tma_kernel|sift_base_stream|sift_small_oct|match_prep_rows|sift_rank_bucket|triangulate_kernel|p3p_" -c 44 python tools/prof_targets.py 8')
     full("r1_match_u8.ncu-rep", "r1_ncu_full_match.md", "Round 1 -- ncu `--set full`: match_topk_u8_kernel, 32768 x 32768 x 128, matchFeatures mode",
