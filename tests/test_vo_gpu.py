@@ -116,3 +116,26 @@ def test_frame_pipeline_equals_serial(ctx):
         want = vo.run_frames(l, r, synth.KITTI_P0, synth.KITTI_P1, seed=5, first_frame=first, ctx=ctx)
         for a, b in zip(g, want):
             assert np.array_equal(a, b)
+
+
+def test_frames_with_empty_and_blank_inputs(ctx):
+    """Edge cases of the batched loop: blank frames (no keypoints -> no matches -> estworldpose status 1,
+    identity pose), a blank frame in the middle of a textured sequence, a single-frame batch."""
+    from vo_b200 import vo, synth
+    blank = np.full((3, 188, 620), 127, dtype=np.uint8)
+    rel, status, counts = vo.run_frames(blank, blank, synth.KITTI_P0, synth.KITTI_P1, seed=1, ctx=ctx)
+    assert (counts[:, :3] == 0).all() and status[0] == 0 and (status[1:] == 1).all()
+    assert np.array_equal(rel, np.tile(np.eye(4), (3, 1, 1)))
+    left, right = _frames(4, seed=31)
+    left = left.copy(); right = right.copy()
+    left[2] = 127; right[2] = 127
+    rel, status, counts = vo.run_frames(left, right, synth.KITTI_P0, synth.KITTI_P1, seed=1, ctx=ctx)
+    assert status[1] == 0 and counts[1, 6] > 30                # frames 0 -> 1 track normally
+    assert status[2] == 1 and status[3] == 1                   # nothing to track into or out of the blank frame
+    assert counts[2, 0] == 0 and counts[3, 0] > 100
+    one = vo.run_frames(left[:1], right[:1], synth.KITTI_P0, synth.KITTI_P1, seed=1, ctx=ctx)
+    assert one[0].shape == (1, 4, 4) and one[1][0] == 0
+    # the loop mirror agrees on the textured pair
+    g = vo.VisualOdometry(synth.KITTI_P0, synth.KITTI_P1, vo.CudaOps(ctx=ctx, seed=1))
+    g.step(left[0], right[0]); a = g.step(left[1], right[1])
+    assert np.array_equal(a, rel[1])
