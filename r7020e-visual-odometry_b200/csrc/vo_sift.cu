@@ -442,21 +442,29 @@ sift_base_stream_kernel(const uint8_t* __restrict__ img8, float* __restrict__ ds
     if (yb > rows8 - 1) yb = rows8 - 1;
   };
   int h_done = -1;   // source rows <= h_done are (or were) in the ring; block-uniform
-  auto ensure_h = [&](int y_lo, int y_hi) {   // h rows needed by upsampled rows [y_lo, y_hi]
+  // each lane owns columns q = lane + 32k of the blend ring: their source columns and weights never change
+  constexpr int HQ = (HW + 31) / 32;
+  int qxa[HQ], qxb[HQ]; float qwb[HQ];
+#pragma unroll
+  for (int k = 0; k < HQ; ++k) {
+    const int x = reflect101(x0 - RP + lane + 32 * k, w);
+    int xa = (x & 1) ? (x >> 1) : (x >> 1) - 1, xb = xa + 1;
+    qwb[k] = (x & 1) ? 0.25f : 0.75f;
+    qxa[k] = xa < 0 ? 0 : xa;
+    qxb[k] = xb > cols8 - 1 ? cols8 - 1 : xb;
+  }
+  auto ensure_h = [&](int y_lo, int y_hi) {   // h rows needed by upsampled rows [y_lo, y_hi]; warp per source row
     int lo, hi, t;
     src_rows(y_lo, lo, t); src_rows(y_hi, t, hi);
     if (lo <= h_done) lo = h_done + 1;
-    const int nr = hi - lo + 1;
-    for (int idx = tid; idx < nr * HW; idx += 256) {
-      const int rr = idx / HW, q = idx - rr * HW;
-      const int r = lo + rr;
-      const int x = reflect101(x0 - RP + q, w);
-      int xa = (x & 1) ? (x >> 1) : (x >> 1) - 1, xb = xa + 1;
-      const float wxb = (x & 1) ? 0.25f : 0.75f, wxa = 1.0f - wxb;
-      if (xa < 0) xa = 0;
-      if (xb > cols8 - 1) xb = cols8 - 1;
-      const float a = src[(size_t)r * cols8 + xa], c = src[(size_t)r * cols8 + xb];
-      hring[r & (HRING - 1)][q] = wxa * a + wxb * c;
+    for (int r = lo + wrp; r <= hi; r += 8) {
+      const uint8_t* rowp = src + (size_t)r * cols8;
+      float a[HQ], c[HQ];
+#pragma unroll
+      for (int k = 0; k < HQ; ++k) { a[k] = rowp[qxa[k]]; c[k] = rowp[qxb[k]]; }
+#pragma unroll
+      for (int k = 0; k < HQ; ++k)
+        if (lane + 32 * k < HW) hring[r & (HRING - 1)][lane + 32 * k] = (1.0f - qwb[k]) * a[k] + qwb[k] * c[k];
     }
     if (hi > h_done) h_done = hi;
   };
@@ -470,8 +478,10 @@ sift_base_stream_kernel(const uint8_t* __restrict__ img8, float* __restrict__ ds
 #pragma unroll
     for (int q = 0; q < NWIN / 4; ++q) {
       const float4 va = pa[q], vb = pb[q];
-      win[4 * q] = wya * va.x + wyb * vb.x; win[4 * q + 1] = wya * va.y + wyb * vb.y;
-      win[4 * q + 2] = wya * va.z + wyb * vb.z; win[4 * q + 3] = wya * va.w + wyb * vb.w;
+      const float ea[4] = {va.x, va.y, va.z, va.w}, eb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)   // only the taps the filter reads: [RP - R, RP + 4 + R)
+        if (4 * q + j >= RP - R && 4 * q + j < RP + 4 + R) win[4 * q + j] = wya * ea[j] + wyb * eb[j];
     }
     float acc[4];
 #pragma unroll
