@@ -158,8 +158,9 @@ def test_best2_records_row_sharded_equals_unsharded(ctx):
 
 
 def test_cta_pair_kernel_bit_exact():
-    """The experimental cta_group::2 variant of the exact-integer kernel (VO_MATCH_PAIRS=1, read once per
-    process, hence the subprocess) must return the same bit-exact results as the default kernel."""
+    """The experimental variants of the exact-integer kernel -- cta_group::2 CTA pairs (VO_MATCH_PAIRS=1) and
+    A operand in TMEM (VO_MATCH_TS=1); switches are read once per process, hence the subprocess -- must
+    return the same bit-exact results as the default kernel."""
     import os, subprocess, sys
     code = r'''
 import sys, os, numpy as np
@@ -179,10 +180,12 @@ for n1, n2, seed in [(1, 1, 1), (129, 257, 2), (1000, 777, 3), (3000, 3100, 4)]:
 print("pairs ok")
 '''
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for tile in ("256", "128"):
-        env = dict(os.environ, VO_MATCH_PAIRS="1", VO_MATCH_PAIR_TILE=tile)
+    variants = [dict(VO_MATCH_PAIRS="1", VO_MATCH_PAIR_TILE="256"), dict(VO_MATCH_PAIRS="1", VO_MATCH_PAIR_TILE="128"),
+                dict(VO_MATCH_TS="1")]            # CTA pairs (two tile widths) and the A-in-TMEM kernel
+    for v in variants:
+        env = dict(os.environ, **v)
         r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
-        assert r.returncode == 0 and "pairs ok" in r.stdout, r.stdout + r.stderr
+        assert r.returncode == 0 and "pairs ok" in r.stdout, str(v) + r.stdout + r.stderr
 
 
 def test_match_large_property(ctx):
