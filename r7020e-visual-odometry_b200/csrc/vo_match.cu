@@ -26,6 +26,7 @@
 #include "vo_ptx.cuh"
 #include <cuda_bf16.h>
 #include <cfloat>
+#include <algorithm>
 
 namespace vo {
 
@@ -367,38 +368,68 @@ __device__ __forceinline__ int raw_bound(float thr, float bnorm) {
   return __float2int_rd(q) - 2;
 }
 
+// One work segment of a CTA: rows [m0, m0 + 256), column tiles [t0, t1), candidate slot pair `slot`.
+struct USeg { int m0, t0, t1, slot; };
+
+// Two launch forms share this kernel.  Grid form (batched problems with device-side counts): grid =
+// (row panels, column splits, problems), one segment per CTA.  Persistent form (sched_L > 0: one problem
+// whose sizes the host knows): grid = number of SMs; the panel x tile space is cut into equal contiguous
+// ranges of sched_L tiles in panel-major order, so every SM gets the same work (128 row panels would
+// occupy 128 of 148 SMs) and a CTA re-loads its A panels only when its range crosses a panel boundary.
+// Segment k of a panel writes candidate slots 2k, 2k+1; match_finalize_kernel merges them.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 match_topk_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const float* __restrict__ invb_base, int invb_stride, const float* __restrict__ inva_base,
                      int inva_stride, const int* __restrict__ invb_max_bits, const int* __restrict__ n1p,
                      int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
                      const int* __restrict__ nonint_flag, int n_splits, uint2* __restrict__ cand_base,
-                     size_t cand_stride, int slots_per_row, float key_floor, float* __restrict__ dbg_c, int dbg_ld) {
+                     size_t cand_stride, int slots_per_row, float key_floor, float* __restrict__ dbg_c, int dbg_ld,
+                     int sched_L, int sched_T, long long sched_total) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if (*nonint_flag != 0) return;   // general floats: match_topk_kernel (split-bf16) handles them
-  const int prob = blockIdx.z;
+  const bool persistent = sched_L > 0;
+  const int prob = persistent ? 0 : blockIdx.z;
   const int n1 = min(n1p[prob * n1_stride], cap1), n2 = min(n2p[prob * n2_stride], cap2);
-  const int m0 = blockIdx.x * UBM;
-  if (m0 >= n1) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_total = (n2 + UBN - 1) / UBN;
-  const int split = blockIdx.y;
-  const int t_begin = (int)((long long)split * tiles_total / n_splits);
-  const int t_end = (int)((long long)(split + 1) * tiles_total / n_splits);
   uint2* cand = cand_base + (size_t)prob * cand_stride;
   const float* invb = invb_base + (size_t)prob * invb_stride;
-
-  if (t_begin >= t_end) {
-    if (warp >= 2) {
-      const int e = warp - 2, quarter = warp & 3, panel = e >> 3, half = (e >> 2) & 1;
-      const int row = m0 + panel * 128 + quarter * 32 + lane;
-      if (row < n1) {
-        uint2* out = cand + ((size_t)row * slots_per_row + split * 2 + half) * NCAND;
-        for (int c = 0; c < NCAND; ++c) out[c] = make_uint2(__float_as_uint(-INFINITY), 0xFFFFFFFFu);
+  // ---- this CTA's segments
+  const long long g_begin = persistent ? (long long)blockIdx.x * sched_L : 0;
+  const long long g_end = persistent ? min(sched_total, g_begin + sched_L) : 1;
+  USeg grid_seg = {0, 0, 0, 0};
+  if (persistent) {
+    if (g_begin >= g_end) return;
+  } else {
+    const int tiles_total = (n2 + UBN - 1) / UBN;
+    grid_seg.m0 = blockIdx.x * UBM;
+    if (grid_seg.m0 >= n1) return;
+    grid_seg.t0 = (int)((long long)blockIdx.y * tiles_total / n_splits);
+    grid_seg.t1 = (int)((long long)(blockIdx.y + 1) * tiles_total / n_splits);
+    grid_seg.slot = blockIdx.y * 2;
+    if (grid_seg.t0 >= grid_seg.t1) {   // nothing to contract: publish empty candidate slots
+      if (warp >= 2) {
+        const int e = warp - 2, quarter = warp & 3, panel = e >> 3, half = (e >> 2) & 1;
+        const int row = grid_seg.m0 + panel * 128 + quarter * 32 + lane;
+        if (row < n1) {
+          uint2* out = cand + ((size_t)row * slots_per_row + grid_seg.slot + half) * NCAND;
+          for (int c = 0; c < NCAND; ++c) out[c] = make_uint2(__float_as_uint(-INFINITY), 0xFFFFFFFFu);
+        }
       }
+      return;
     }
-    return;
   }
+  // cursor g -> next segment (every role walks the same list with its own cursor)
+  auto next_seg = [&](long long& g, USeg& sg) -> bool {
+    if (g >= g_end) return false;
+    if (!persistent) { sg = grid_seg; g = g_end; return true; }
+    const int panel = (int)(g / sched_T), t0 = (int)(g - (long long)panel * sched_T);
+    const int len = (int)min((long long)(sched_T - t0), g_end - g);
+    sg.m0 = panel * UBM; sg.t0 = t0; sg.t1 = t0 + len;
+    sg.slot = 2 * (int)(blockIdx.x - ((long long)panel * sched_T) / sched_L);
+    g += len;
+    return true;
+  };
+
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();
   const uint32_t sA = base;                              // [2 panels] x 16 KB
@@ -409,27 +440,18 @@ match_topk_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t bar_b_empty = bar_b_full + 8 * U_STAGES;
   const uint32_t bar_t_full = bar_b_empty + 8 * U_STAGES;
   const uint32_t bar_t_empty = bar_t_full + 16;
-  const uint32_t tmem_slot = bar_t_empty + 16;
+  const uint32_t bar_a_empty = bar_t_empty + 16;
+  const uint32_t tmem_slot = bar_a_empty + 8;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - base));
   float* s_thr = reinterpret_cast<float*>(smem_raw + (bars + 256 - base));   // [UBM]
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    mbar_init(bar_a_full, 1);
+    mbar_init(bar_a_full, 1); mbar_init(bar_a_empty, 1);
     for (int s = 0; s < U_STAGES; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + UBM) {
-    // initial per-row key bound: the caller's score bound in key units, or -inf
-    const int r = threadIdx.x - 64;
-    float t0 = -INFINITY;
-    if (key_floor > 0.f && m0 + r < n1) {
-      const float ia = inva_base[(size_t)prob * inva_stride + m0 + r];
-      if (ia > 0.f) t0 = __fdiv_rn(key_floor, ia);
-    }
-    s_thr[r] = t0;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
@@ -442,14 +464,19 @@ match_topk_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
-      mbar_expect_tx(bar_a_full, 2 * U_TILE_BYTES);
-      for (int pn = 0; pn < 2; ++pn) tma_load_3d(sA + pn * U_TILE_BYTES, &tmA, bar_a_full, 0, m0 + pn * 128, prob);
+      long long g = g_begin; USeg sg; int seg_i = 0;
       int stage = 0; uint32_t phase = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
-        mbar_expect_tx(bar_b_full + 8 * stage, U_TILE_BYTES);
-        tma_load_3d(sB + stage * U_TILE_BYTES, &tmB, bar_b_full + 8 * stage, 0, t * UBN, prob);
-        if (++stage == U_STAGES) { stage = 0; phase ^= 1; }
+      while (next_seg(g, sg)) {
+        mbar_wait(bar_a_empty, (uint32_t)((seg_i & 1) ^ 1));   // the previous segment's MMAs are done with the A panels
+        mbar_expect_tx(bar_a_full, 2 * U_TILE_BYTES);
+        for (int pn = 0; pn < 2; ++pn) tma_load_3d(sA + pn * U_TILE_BYTES, &tmA, bar_a_full, 0, sg.m0 + pn * 128, prob);
+        for (int t = sg.t0; t < sg.t1; ++t) {
+          mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+          mbar_expect_tx(bar_b_full + 8 * stage, U_TILE_BYTES);
+          tma_load_3d(sB + stage * U_TILE_BYTES, &tmB, bar_b_full + 8 * stage, 0, t * UBN, prob);
+          if (++stage == U_STAGES) { stage = 0; phase ^= 1; }
+        }
+        ++seg_i;
       }
     }
   } else if (warp == 1) {
@@ -460,54 +487,73 @@ match_topk_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // stream -- about 100 cycles per MMA -- paced the tile loop, not the tensor pipe).
     {
       const uint32_t idesc = (2u << 4) | ((uint32_t)(UBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      mbar_wait(bar_a_full, 0);
-      tc_fence_after();
       const uint64_t ad0 = umma_desc_sw128(sA), ad1 = umma_desc_sw128(sA + U_TILE_BYTES), bd0 = umma_desc_sw128(sB);
+      long long g = g_begin; USeg sg; int seg_i = 0;
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);
-        mbar_wait(bar_b_full + 8 * stage, phase);
+      while (next_seg(g, sg)) {
+        mbar_wait(bar_a_full, (uint32_t)(seg_i & 1));
         tc_fence_after();
-        const uint32_t d0 = tmem_base + acc * 256, d1 = d0 + UBN;
-        const uint64_t bds = bd0 + (uint64_t)(stage * (U_TILE_BYTES >> 4));
         uint32_t elected;
-        asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(elected));
-        if (elected) {
-          asm volatile(
-              "{\n\t.reg .pred p0, p1;\n\tsetp.ne.b32 p0, 0, 0;\n\tsetp.eq.b32 p1, 0, 0;\n\t"
-              "tcgen05.mma.cta_group::1.kind::i8 [%0], %2, %4, %5, p0;\n\t"
-              "tcgen05.mma.cta_group::1.kind::i8 [%1], %3, %4, %5, p0;\n\t}"
-              ::"r"(d0), "r"(d1), "l"(ad0), "l"(ad1), "l"(bds), "r"(idesc) : "memory");
-#pragma unroll
-          for (int k = 1; k < 4; ++k)
+        for (int t = sg.t0; t < sg.t1; ++t) {
+          mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);
+          mbar_wait(bar_b_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t d0 = tmem_base + acc * 256, d1 = d0 + UBN;
+          const uint64_t bds = bd0 + (uint64_t)(stage * (U_TILE_BYTES >> 4));
+          asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(elected));
+          if (elected) {
             asm volatile(
-                "{\n\t.reg .pred p1;\n\tsetp.eq.b32 p1, 0, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::i8 [%0], %2, %4, %5, p1;\n\t"
-                "tcgen05.mma.cta_group::1.kind::i8 [%1], %3, %4, %5, p1;\n\t}"
-                ::"r"(d0), "r"(d1), "l"(ad0 + (uint64_t)(2 * k)), "l"(ad1 + (uint64_t)(2 * k)), "l"(bds + (uint64_t)(2 * k)), "r"(idesc)
-                : "memory");
-          tc_commit(bar_b_empty + 8 * stage);
-          tc_commit(bar_t_full + 8 * acc);
+                "{\n\t.reg .pred p0, p1;\n\tsetp.ne.b32 p0, 0, 0;\n\tsetp.eq.b32 p1, 0, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::i8 [%0], %2, %4, %5, p0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::i8 [%1], %3, %4, %5, p0;\n\t}"
+                ::"r"(d0), "r"(d1), "l"(ad0), "l"(ad1), "l"(bds), "r"(idesc) : "memory");
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+              asm volatile(
+                  "{\n\t.reg .pred p1;\n\tsetp.eq.b32 p1, 0, 0;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %2, %4, %5, p1;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::i8 [%1], %3, %4, %5, p1;\n\t}"
+                  ::"r"(d0), "r"(d1), "l"(ad0 + (uint64_t)(2 * k)), "l"(ad1 + (uint64_t)(2 * k)), "l"(bds + (uint64_t)(2 * k)), "r"(idesc)
+                  : "memory");
+            tc_commit(bar_b_empty + 8 * stage);
+            tc_commit(bar_t_full + 8 * acc);
+            if (t + 1 == sg.t1) tc_commit(bar_a_empty);   // last tile of the segment: A panels may be replaced
+          }
+          __syncwarp();
+          if (++stage == U_STAGES) { stage = 0; phase ^= 1; }
+          acc ^= 1; if (acc == 0) acc_phase ^= 1;
         }
-        __syncwarp();
-        if (++stage == U_STAGES) { stage = 0; phase ^= 1; }
-        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        ++seg_i;
       }
     }
   } else {
     // ===== epilogue =====
     const int e = warp - 2, quarter = warp & 3, panel = e >> 3, half = (e >> 2) & 1;
     const int row_in_cta = panel * 128 + quarter * 32 + lane;
-    const int row = m0 + row_in_cta;
     const float bmax = __int_as_float(invb_max_bits[prob]);
     const float bnorm = bmax > 0.f ? __fdiv_rn(1.0f, bmax) : 0.f;
     int* scr = reinterpret_cast<int*>(s_thr + UBM) + e * U_SCRATCH_INTS;
+    long long g = g_begin; USeg sg;
+    int acc = 0; uint32_t acc_phase = 0;
+    while (next_seg(g, sg)) {
+    const int row = sg.m0 + row_in_cta;
+    // per-row key bound of this segment's panel: the caller's score bound in key units, or -inf.  The two
+    // named barriers keep the 16 epilogue warps from re-initialising s_thr while a slower warp still uses it.
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (half == 0) {
+      float t0 = -INFINITY;
+      if (key_floor > 0.f && row < n1) {
+        const float ia = inva_base[(size_t)prob * inva_stride + row];
+        if (ia > 0.f) t0 = __fdiv_rn(key_floor, ia);
+      }
+      s_thr[row_in_cta] = t0;
+    }
+    asm volatile("bar.sync 1, 512;" ::: "memory");
     Top3 top; top.init();
     float thr = s_thr[row_in_cta];
     int thr_raw = raw_bound(thr, bnorm);
     if (row >= n1) { thr = INFINITY; thr_raw = 0x7fffffff; }   // padding rows never take the exact path
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int t = t_begin; t < t_end; ++t) {
+    for (int t = sg.t0; t < sg.t1; ++t) {
       mbar_wait(bar_t_full + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + panel * UBN + half * 64);
@@ -574,11 +620,12 @@ match_topk_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
     if (row < n1) {
-      uint2* out = cand + ((size_t)row * slots_per_row + split * 2 + half) * NCAND;
+      uint2* out = cand + ((size_t)row * slots_per_row + sg.slot + half) * NCAND;
       out[0] = make_uint2(__float_as_uint(top.k1), top.i1);
       out[1] = make_uint2(__float_as_uint(top.k2), top.i2);
       out[2] = make_uint2(__float_as_uint(top.k3), top.i3);
     }
+    }   // segments
   }
   tc_fence_before();
   __syncthreads();
@@ -1305,7 +1352,8 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
                       int dim, const float* __restrict__ inva_base, int inva_stride,
                       const float* __restrict__ invb_base, int invb_stride, const int* __restrict__ n1p,
                       int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
-                      const int* __restrict__ nonint_flag, int all_slots, MatchFilter flt, uint32_t* __restrict__ j1_out,
+                      const int* __restrict__ nonint_flag, int all_slots, int sched_L, int sched_T, MatchFilter flt,
+                      uint32_t* __restrict__ j1_out,
                       float* __restrict__ s1_out, float* __restrict__ s2_out, int row_stride,
                       int* __restrict__ scan_list, int* __restrict__ scan_count) {
   const int prob = blockIdx.y;
@@ -1318,7 +1366,11 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
   uint32_t j[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
   // row stride is n_slots (thin kernel: 4 slots per split); the fat kernel fills the first half only
   const uint2* c = cand_base + (size_t)prob * cand_stride + (size_t)i * n_slots * NCAND;
-  const int used = ((*nonint_flag) || all_slots) ? n_slots * NCAND : (n_slots / 2) * NCAND;
+  int used = ((*nonint_flag) || all_slots) ? n_slots * NCAND : (n_slots / 2) * NCAND;
+  if (sched_L > 0 && !(*nonint_flag)) {   // persistent u8 kernel: the row's panel was cut into n_seg segments, 2 slots each
+    const long long p0 = (long long)(i / UBM) * sched_T;
+    used = (int)((p0 + sched_T - 1) / sched_L - p0 / sched_L + 1) * 2 * NCAND;
+  }
   for (int s = 0; s < used; ++s) {
     const uint2 e = c[s];
     if (e.y >= (uint32_t)n2) continue;
@@ -1731,6 +1783,21 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
     const int x_tiles = div_up(B.cap > 0 ? B.cap : 1, pair_tile);
     if (n_splits > x_tiles) n_splits = x_tiles;
   }
+  // persistent form of the u8 kernel: one problem whose sizes the host knows and enough tiles to share out
+  int sched_L = 0, sched_T = 0; long long sched_total = 0;
+  if (exact_sizes && !use_pairs && !use_ts && B.cap > 0) {
+    const int T = div_up(B.cap, UBN);
+    const long long total = (long long)div_up(A.cap, UBM) * T;
+    // measured: the equal shares pay off once a CTA's share is long enough to amortise the extra segment
+    // start (A reload, threshold reset; without a score bound also a second "everything is a candidate" phase)
+    const long long share = (total + ctx->num_sms - 1) / ctx->num_sms;
+    if (share >= (flt.key_floor > 0.f ? 128 : 512)) {
+      sched_T = T; sched_total = total;
+      sched_L = (int)share;
+      const int s_max = (T + sched_L - 1) / sched_L + 1;          // segments a panel can be cut into
+      n_splits = std::max(n_splits, div_up(2 * s_max, 4));        // candidate row stride (4 slots per split)
+    }
+  }
   const int n_slots = n_splits * 4;
   const size_t cand_stride = (size_t)a_alloc * n_slots * NCAND;
   uint2* cand; VO_TRY(dev_buf(ctx, nm("m_cand").c_str(), (size_t)n_prob * cand_stride, &cand));
@@ -1763,9 +1830,10 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
           tmB96, u8A, a_alloc, invB, b_alloc, invA, a_alloc, invb_max, A.count, A.count_stride, A.cap, B.count, B.count_stride,
           B.cap, ctl, n_splits, cand, cand_stride, n_slots, flt.key_floor, dbg_c, B.cap);
     } else if (!use_pairs) {
-      match_topk_u8_kernel<<<dim3(m_blocks, n_splits, n_prob), NUM_THREADS, U_SMEM_BYTES, st>>>(
+      const dim3 ugrid = sched_L > 0 ? dim3((unsigned)div_up((int)((sched_total + sched_L - 1) / sched_L), 1), 1, 1) : dim3(m_blocks, n_splits, n_prob);
+      match_topk_u8_kernel<<<ugrid, NUM_THREADS, U_SMEM_BYTES, st>>>(
           tmA8, tmB8, invB, b_alloc, invA, a_alloc, invb_max, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap,
-          ctl, n_splits, cand, cand_stride, n_slots, flt.key_floor, dbg_c, B.cap);
+          ctl, n_splits, cand, cand_stride, n_slots, flt.key_floor, dbg_c, B.cap, sched_L, sched_T, sched_total);
     } else {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(2 * m_blocks, n_splits, n_prob);   // one CTA pair (cluster of 2) per 256-row panel
@@ -1805,7 +1873,7 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   }
   match_finalize_kernel<<<dim3(div_up(A.cap, 128), n_prob), 128, 0, st>>>(
       cand, cand_stride, n_slots, ra, rb, dim, invA, a_alloc, invB, b_alloc, A.count, A.count_stride, A.cap, B.count,
-      B.count_stride, B.cap, ctl, (use_pairs || use_ts) ? 1 : 0, flt, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
+      B.count_stride, B.cap, ctl, (use_pairs || use_ts) ? 1 : 0, sched_L, sched_T, flt, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
   if (B.cap > 0) {
     int scan_grid = ctx->num_sms * 2;
     match_rowscan_kernel<<<scan_grid, 256, 0, st>>>(scan_list, ctl + 1, ra, rb, u8A, u8B, a_alloc, b_alloc, ctl, dim, invA, a_alloc, invB, b_alloc, B.count,
