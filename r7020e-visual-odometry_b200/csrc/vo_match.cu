@@ -222,32 +222,39 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer =====
+    {  // ===== MMA issuer (warp-converged; one elected lane issues, operands stay warp-uniform) =====
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       mbar_wait(bar_a_full, 0);
       tc_fence_after();
+      const uint64_t ad0 = umma_desc_sw128(sA), bd0 = umma_desc_sw128(sB);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
-        // the epilogue of tile t-2 has drained this stage: its 1/||b|| slot can be refilled
-        mbar_expect_tx(bar_i_full + 8 * acc, BN * 4);
-        bulk_load_1d(s_invb_addr + acc * BN * 4, invb + (size_t)t * BN, BN * 4, bar_i_full + 8 * acc);
+        uint32_t elected;
+        asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(elected));
+        if (elected) {   // the epilogue of tile t-2 has drained this stage: its 1/||b|| slot can be refilled
+          mbar_expect_tx(bar_i_full + 8 * acc, BN * 4);
+          bulk_load_1d(s_invb_addr + acc * BN * 4, invb + (size_t)t * BN, BN * 4, bar_i_full + 8 * acc);
+        }
+        __syncwarp();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_b_full + 8 * stage, phase);
           tc_fence_after();
+          const uint64_t ads = ad0 + (uint64_t)(kb * (A_KBLOCK_BYTES >> 4)), bds = bd0 + (uint64_t)(stage * (B_STAGE_BYTES >> 4));
+          asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(elected));
+          if (elected) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t ad = umma_desc_sw128(sA + kb * A_KBLOCK_BYTES + k * UMMA_K * 2);
-            const uint64_t bd = umma_desc_sw128(sB + stage * B_STAGE_BYTES + k * UMMA_K * 2);
-            tc_mma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              tc_mma_bf16(d_tmem, ads + (uint64_t)(2 * k), bds + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            tc_commit(bar_b_empty + 8 * stage);
+            if (kb + 1 == kblocks) tc_commit(bar_t_full + 8 * acc);
           }
-          tc_commit(bar_b_empty + 8 * stage);
+          __syncwarp();
           if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(bar_t_full + 8 * acc);
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
     }
