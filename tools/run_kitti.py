@@ -46,8 +46,9 @@ def main():
         gt = kitti_eval.load_poses(a.poses)[:len(poses)]
         t_err, r_err, n = kitti_eval.kitti_errors(poses, gt)
         xz = kitti_eval.xz_error(poses, gt)
-        print(f"KITTI t_err {100 * t_err:.3f} %  r_err {np.degrees(r_err):.5f} deg/m over {n} segments; "
-              f"xz error (PlotOnMap.m:20) max {xz.max():.2f} m, last {xz[-1]:.2f} m")
+        kitti = (f"KITTI t_err {100 * t_err:.3f} %  r_err {np.degrees(r_err):.5f} deg/m over {n} segments" if n
+                 else "KITTI t_err / r_err: n/a (sequence shorter than 100 m)")
+        print(f"{kitti}; xz error (PlotOnMap.m:20) max {xz.max():.2f} m, last {xz[-1]:.2f} m")
 
 
 if __name__ == "__main__":
