@@ -119,7 +119,7 @@ if __name__ == "__main__":
     launches()
     bench_launches()
     full("r1_sift2.ncu-rep", "r1_ncu_full_sift.md", "Round 1 -- ncu `--set full`: SIFT, sort, prep and geometry kernels of one frame-loop step (18 images of 1241x376)",
-         'ncu --set full --clock-control none --import-source on -k regex:"sift_descriptor_kernel|sift_refine_orient_kernel|sift_extrema_kernel|sift_blur_tma_kernel|sift_base_stream|sift_small_oct|match_prep_rows|sift_rank_bucket|triangulate_kernel|p3p_" -c 44 python tools/prof_targets.py 8')
+         'ncu --set full --clock-control none --import-source on -k regex:"sift_descriptor_kernel|sift_refine_kernel|sift_orient_kernel|sift_extrema_kernel|sift_blur_tma_kernel|sift_base_stream|sift_small_oct|sift_rank_bucket" -c 33 python tools/prof_targets.py 8')
     full("r1_match_u8.ncu-rep", "r1_ncu_full_match.md", "Round 1 -- ncu `--set full`: match_topk_u8_kernel, 32768 x 32768 x 128, matchFeatures mode",
          "ncu --set full --clock-control none --import-source on -k regex:match_topk_u8 -s 2 -c 1 python tools/prof_match.py 32768 match")
     full("r1_match_frames.ncu-rep", "r1_ncu_full_match_frames.md", "Round 1 -- ncu `--set full`: match_topk_u8_kernel inside the frame loop (9 problems of ~4100 x 4100)",
