@@ -60,6 +60,7 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
                        int* status, int* counts) {
   VO_CHECK_ARG(ctx && left && right && P1 && P2 && rel_pose && status, "null argument");
   VO_CHECK_ARG(n >= 1 && rows > 0 && cols > 0, "bad size");
+  VO_CHECK_ARG(!(opts && opts->match.unique), "vo_frames: match.unique is not supported by the batched loop (VO.m never sets Unique); use vo_match");
   VO_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   vo_match_opts mo; fill_match_opts(opts ? &opts->match : nullptr, &mo);
