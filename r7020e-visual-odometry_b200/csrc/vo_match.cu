@@ -685,7 +685,7 @@ match_topk_u8ts_kernel(const __grid_constant__ CUtensorMap tmB, const uint8_t* _
       const int row = m0 + panel * 128 + quarter * 32 + lane;
       if (row < n1) {
         uint2* out = cand + ((size_t)row * slots_per_row + split * 4 + third) * NCAND;
-        for (int c = 0; c < NCAND * (third == 0 ? 1 : 1); ++c) out[c] = make_uint2(__float_as_uint(-INFINITY), 0xFFFFFFFFu);
+        for (int c = 0; c < NCAND; ++c) out[c] = make_uint2(__float_as_uint(-INFINITY), 0xFFFFFFFFu);
         if (third == 0) for (int c = 0; c < NCAND; ++c) out[3 * NCAND + c] = make_uint2(__float_as_uint(-INFINITY), 0xFFFFFFFFu);
       }
     }
