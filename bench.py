@@ -10,10 +10,12 @@ synthetic stream of synth.shift_stream (data: "synthetic").  A *step* = one vo_f
 B+1 consecutive frames (one halo frame + B new frames -> B relative poses).
 
 One JSON line on stdout (rank 0):
-  value    frames/s with the images already resident in HBM (vo_frames_dev), CUDA-event timed
+  value    frames/s with the images already resident in HBM (vo_frames_dev), CUDA-event timed;
+           `--inflight` batches (default 3) are kept in flight, one context / stream / host thread each
   e2e      frames/s through the C ABI with HOST (pinned) images: H2D of every frame and D2H of
-           the poses inside the timed region (vo_frames)
-  roofline the dominant kernel stage of the step (live CUDA-event timers inside the library)
+           the poses inside the timed region (vo_frames), same batches in flight
+  roofline the dominant kernel stage of the step (live CUDA-event timers inside the library) from a
+           third pass over the same steps, one batch at a time (ms_per_step_profiled_serial)
   match_gemm  the tcgen05 match GEMM alone at 32768 x 32768 x 128 (second headline of BASELINE.json)
   cpu_baseline  the single-threaded C oracle on a bounded sample of the same frames (rank 0, N=1)
 
