@@ -213,3 +213,17 @@ def test_match_large_property(ctx):
     # Unique at this size (forward-backward): copies are mutual nearest neighbours, so nothing is lost
     upairs = vo_b200.matchFeatures(f1, f2, Unique=True, ctx=ctx)
     assert np.array_equal(upairs, pairs)
+
+
+def test_best2_records_empty_sides(ctx):
+    """Relocalisation records with an empty landmark set (every row: keep = 0, j1 = UINT32_MAX) and with
+    no queries at all."""
+    import torch
+    from vo_b200 import shard
+    q = torch.from_numpy(sift_like_descriptors(300, 5)).cuda()
+    none = torch.empty((0, 128), dtype=torch.float32, device="cuda")
+    rec, counts = shard.relocalise_row_sharded_dev(ctx, q, none, 0, 1)
+    r = rec.cpu().numpy()
+    assert r.shape == (300, 4) and (r[:, 3] == 0).all() and (r[:, 0].view(np.uint32) == 0xFFFFFFFF).all()
+    rec, counts = shard.relocalise_row_sharded_dev(ctx, none, q, 0, 1)
+    assert rec.shape[0] == 0 and counts == [0]
