@@ -149,3 +149,47 @@ def test_landmark_map_mirrors_the_reference_loop():
     idx = vo.new_landmark_indices(l, r, old_l, old_r)
     want = [k for k in range(4) if not (old_l == l[k]).any() and not (old_r == r[k]).any()]
     assert idx.tolist() == want == [0]
+
+
+def test_sequence_runner_and_pipeline_host_logic(tmp_path, monkeypatch):
+    """Host logic of io.run_sequence (batch cutting with a one-frame halo, double-buffered decode) and of
+    vo.FramePipeline (work queue over several contexts, results in input order) with the GPU call replaced
+    by a stand-in that only records what it was given."""
+    cv2 = pytest.importorskip("cv2")
+    from vo_b200 import io, vo
+    n, h, w = 11, 20, 30
+    rng = np.random.default_rng(0)
+    left = rng.integers(0, 256, (n, h, w), dtype=np.uint8); right = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    lf, rf = [], []
+    for i in range(n):
+        for name, arr, lst in (("l", left, lf), ("r", right, rf)):
+            p = os.path.join(tmp_path, f"{name}{i:04d}.png"); assert cv2.imwrite(p, arr[i]); lst.append(p)
+    calls = []
+
+    def fake_run_frames(l, r, P1, P2, seed=0, first_frame=0, max_keypoints=8192, ctx=None, device_ptrs=None):
+        m = len(l)
+        calls.append((first_frame, m))
+        assert np.array_equal(l, left[first_frame:first_frame + m]) and np.array_equal(r, right[first_frame:first_frame + m])
+        rel = np.tile(np.eye(4), (m, 1, 1)); rel[:, 0, 3] = np.arange(first_frame, first_frame + m)   # frame index in tx
+        return rel, np.zeros(m, np.int32), np.full((m, 8), first_frame, np.int32)
+    monkeypatch.setattr(vo, "run_frames", fake_run_frames)
+    rel, status, counts = io.run_sequence(lf, rf, np.eye(3, 4), np.eye(3, 4), batch=4, pinned=False)
+    assert calls == [(0, 4), (3, 5), (7, 4)]                       # [lo, hi) with the one-frame halo
+    assert np.array_equal(rel[:, 0, 3], np.arange(n))              # every frame's pose comes from the batch that owns it
+    assert counts[:4, 0].tolist() == [0] * 4 and counts[4:8, 0].tolist() == [3] * 4 and counts[8:, 0].tolist() == [7] * 3
+
+    class FakeCtx:
+        def close(self):
+            pass
+    monkeypatch.setattr(vo.api, "Context", lambda device=0: FakeCtx())
+    pipe = vo.FramePipeline(depth=3)
+    batches = [(left[i:i + 2], right[i:i + 2], i) for i in range(0, 10, 2)]
+    out = pipe.map(batches, np.eye(3, 4), np.eye(3, 4))
+    assert [int(o[2][0, 0]) for o in out] == [0, 2, 4, 6, 8]       # results in input order
+    pipe.close()
+
+    def boom(*a, **k):
+        raise RuntimeError("device fault")
+    monkeypatch.setattr(vo, "run_frames", boom)
+    with pytest.raises(RuntimeError, match="device fault"):
+        vo.FramePipeline(depth=2).map(batches, np.eye(3, 4), np.eye(3, 4))
