@@ -173,8 +173,8 @@ def run_reference(args, rank, world):
     from vo_b200 import synth
     cores = os.cpu_count() or 1
     # frames per step: one per core (+1 halo frame); fewer when many steps are asked for, so that the whole
-    # run stays within a few minutes (a step of `cores` frames takes ~7 s of wall time)
-    n = max(2, min(cores, int(cores * 20 / max(args.steps + args.warmup, 1))))
+    # run stays within a few minutes (a step of `cores` frames takes ~14 s of wall time on the GPU box's host)
+    n = max(2, min(cores, int(cores * 9 / max(args.steps + args.warmup, 1))))   # ~2 minutes for the whole run
     left, right = synth.shift_stream(n + 1, seed=99, h=H, w=W)
     ctxm = mp.get_context("fork")
     with ctxm.Pool(cores) as pool:
