@@ -1798,7 +1798,9 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
     // measured: the equal shares pay off once a CTA's share is long enough to amortise the extra segment
     // start (A reload, threshold reset; without a score bound also a second "everything is a candidate" phase)
     const long long share = (total + ctx->num_sms - 1) / ctx->num_sms;
-    if (share >= (flt.key_floor > 0.f ? 128 : 512)) {
+    // ... or when the grid form could not even occupy half the SMs (few query rows against a long landmark list)
+    const bool skinny = (long long)m_blocks * 8 < ctx->num_sms / 2 && total >= ctx->num_sms;
+    if (share >= (flt.key_floor > 0.f ? 128 : 512) || skinny) {
       sched_T = T; sched_total = total;
       sched_L = (int)share;
       const int s_max = (T + sched_L - 1) / sched_L + 1;          // segments a panel can be cut into

@@ -227,3 +227,16 @@ def test_best2_records_empty_sides(ctx):
     assert r.shape == (300, 4) and (r[:, 3] == 0).all() and (r[:, 0].view(np.uint32) == 0xFFFFFFFF).all()
     rec, counts = shard.relocalise_row_sharded_dev(ctx, none, q, 0, 1)
     assert rec.shape[0] == 0 and counts == [0]
+
+
+@pytest.mark.parametrize("n1,n2", [(64, 40000), (300, 70000)])
+def test_skinny_problems_use_every_sm_and_stay_exact(ctx, n1, n2):
+    """Few query rows against a long landmark list: the persistent form cuts the single row panel into many
+    column segments (one per SM); candidates of all segments must merge to the oracle's answer."""
+    import vo_b200.api as api
+    f1, f2 = correlated_pair(n1, n2, seed=n1 + 7)
+    j1, s1, s2 = api.match_top2(f1, f2, ctx=ctx)
+    oj1, os1, os2 = oracle.match_top2(f1, f2)
+    assert np.array_equal(j1, oj1)
+    assert np.array_equal(s1.view(np.uint32), os1.view(np.uint32)) and np.array_equal(s2.view(np.uint32), os2.view(np.uint32))
+    _check(ctx, f1, f2)
