@@ -86,6 +86,22 @@ __device__ __forceinline__ float vo_expf(float x) {
   return under ? 0.f : __int_as_float(__float_as_int(p) + (((int)n) << 23));
 }
 
+// vo_expf for arguments whose rounded exponent can neither overflow nor underflow (here: Gaussian
+// window weights, x in [-40, 0]): the same operations without the range handling, same bits.
+__device__ __forceinline__ float vo_expf_window(float x) {
+  const float n = rintf(x * 1.44269504088896341f);
+  float r = fmaf(n, -0.693145751953125f, x);
+  r = fmaf(n, -1.42860682030941723e-6f, r);
+  float p = 1.0f / 720.0f;
+  p = fmaf(p, r, 1.0f / 120.0f);
+  p = fmaf(p, r, 1.0f / 24.0f);
+  p = fmaf(p, r, 1.0f / 6.0f);
+  p = fmaf(p, r, 0.5f);
+  p = fmaf(p, r, 1.0f);
+  p = fmaf(p, r, 1.0f);
+  return __int_as_float(__float_as_int(p) + (((int)n) << 23));
+}
+
 // (uint32_t)__float2int_rn(v * 4096) for 0 <= v * 4096 < 2^22 without the conversion pipe: v * 4096 is
 // exact, so one fused multiply-add onto 1.5 * 2^23 rounds it to nearest-even into the mantissa.
 __device__ __forceinline__ uint32_t sift_fix(float v) {
@@ -847,7 +863,8 @@ sift_orient_kernel(const float* __restrict__ gauss, const OctInfo oi, int batch,
       if (!sm.ok) return;
       const float dx = sm.xp - sm.xm;
       const float dy = sm.yu - sm.yd;
-      const float wgt = vo_expf((float)(sm.i * sm.i + sm.j * sm.j) * expf_scale);
+      // |i|, |j| <= radius = rn(3 * osig): the argument stays above -36 for every scale
+      const float wgt = vo_expf_window((float)(sm.i * sm.i + sm.j * sm.j) * expf_scale);
       const float ang = vo_atan2deg(dy, dx);
       const float mag = __fsqrt_rn(fmaf(dx, dx, dy * dy));
       int bin = __float2int_rn((ORI_BINS / 360.f) * ang);
@@ -1088,15 +1105,14 @@ sift_trig_kernel(const vo_keypoint* __restrict__ kps, int kp_cap, const int* __r
 // result independent of the order and of the copy assignment.
 constexpr int DESC_COPIES = 2;
 constexpr int DESC_MAX_ROWS = 160;   // window rows handled by the interval scan (radius <= 79)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 10)
 sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int batch, int nl,
                        const vo_keypoint* __restrict__ kps, const float2* __restrict__ trig, int kp_cap,
                        const int* __restrict__ counters, float loc_offset, float* __restrict__ desc,
                        unsigned long long* __restrict__ algo_bytes) {
   constexpr int D = 4, N = 8, HLEN = (D + 2) * (D + 2) * (N + 2);
   __shared__ uint32_t s_hist[4][DESC_COPIES * HLEN];
-  __shared__ int s_rowoff[4][DESC_MAX_ROWS + 1];
-  __shared__ short s_rowj[4][DESC_MAX_ROWS];
+  __shared__ unsigned s_row[4][DESC_MAX_ROWS + 3];
   __shared__ float s_vec[4][128];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1133,12 +1149,15 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
     // scatter.  (Keeping two samples per lane in flight was measured slower: the kernel is issue-bound,
     // and the extra registers cost occupancy.)
     struct Samp { float c_rot, r_rot, rbin, cbin, xp, xm, yu, yd; bool ok; };
-    auto fetch = [&](int i, int j, Samp& sm) {
+    auto fetch = [&](int i, int j, Samp& sm, auto clipped) {
       sm.c_rot = j * cos_t - i * sin_t;
       sm.r_rot = j * sin_t + i * cos_t;
       sm.rbin = sm.r_rot + D / 2 - 0.5f; sm.cbin = sm.c_rot + D / 2 - 0.5f;
-      const int r = py + i, c = px + j;
-      sm.ok = sm.rbin > -1 && sm.rbin < D && sm.cbin > -1 && sm.cbin < D && r > 0 && r < rows - 1 && c > 0 && c < cols - 1;
+      sm.ok = sm.rbin > -1 && sm.rbin < D && sm.cbin > -1 && sm.cbin < D;
+      if constexpr (!decltype(clipped)::value) {   // (the row intervals are already clipped to the image)
+        const int r = py + i, c = px + j;
+        sm.ok = sm.ok && r > 0 && r < rows - 1 && c > 0 && c < cols - 1;
+      }
       if (sm.ok) {   // 32-bit offsets from the keypoint's centre pixel (fewer 64-bit address operations)
         const int off = i * pitch + j;
         sm.xp = __ldg(img_c + (off + 1)); sm.xm = __ldg(img_c + (off - 1));
@@ -1150,7 +1169,8 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
       float rbin = sm.rbin, cbin = sm.cbin;
       const float dx = sm.xp - sm.xm;
       const float dy = sm.yu - sm.yd;
-      const float wgt = vo_expf((sm.c_rot * sm.c_rot + sm.r_rot * sm.r_rot) * exp_scale);
+      // accepted samples have |c_rot|, |r_rot| < 2.5: the argument lies in (-1.6, 0]
+      const float wgt = vo_expf_window((sm.c_rot * sm.c_rot + sm.r_rot * sm.r_rot) * exp_scale);
       const float a = vo_atan2deg(dy, dx);
       const float mag = __fsqrt_rn(fmaf(dx, dx, dy * dy)) * wgt;
       float obin = (a - ori) * bins_per_rad;
@@ -1176,7 +1196,8 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
       atomicAdd(hp + (D + 3) * (N + 2), sift_fix(v110));
       atomicAdd(hp + (D + 3) * (N + 2) + 1, sift_fix(v111));
     };
-    auto process = [&](int i, int j) { Samp sm; fetch(i, j, sm); accumulate(sm); };
+    auto process = [&](int i, int j) { Samp sm; fetch(i, j, sm, std::false_type{}); accumulate(sm); };
+    auto process_clipped = [&](int i, int j) { Samp sm; fetch(i, j, sm, std::true_type{}); accumulate(sm); };
 
     const int side = 2 * radius + 1, total = side * side;
     my_bytes += (unsigned long long)total * 4ull + 512ull;   // patch read + descriptor written
@@ -1212,16 +1233,21 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
           const int y = __shfl_up_sync(0xffffffffu, incl, off);
           if (lane >= off) incl += y;
         }
-        if (ri < side) { s_rowoff[wib][ri + 1] = carry + incl; s_rowj[wib][ri] = (short)jlo; }
+        // one word per row: (packed index of its first candidate << 8) | (jlo + 128)
+        if (ri < side) s_row[wib][ri] = ((unsigned)(carry + incl - cntr) << 8) | (unsigned)(jlo + 128);
         carry += __shfl_sync(0xffffffffu, incl, 31);
       }
-      if (lane == 0) s_rowoff[wib][0] = 0;
-      __syncwarp();
       const int ncand = carry;
+      if (lane < 3) s_row[wib][side + lane] = lane == 0 ? ((unsigned)ncand << 8) : 0xffffffffu;
+      __syncwarp();
+      // The row of packed index k is found by walking forward from the previous one; the next two row
+      // words stay in registers so the walk never waits on the shared-memory load it has just issued.
       int row = 0;
+      unsigned cur = s_row[wib][0], nxt = s_row[wib][1], nx2 = s_row[wib][2];
       for (int k = lane; k < ncand; k += 32) {
-        while (k >= s_rowoff[wib][row + 1]) ++row;
-        process(row - radius, (int)s_rowj[wib][row] + (k - s_rowoff[wib][row]));
+        const unsigned kk = ((unsigned)k << 8) | 255u;
+        while (kk >= nxt) { cur = nxt; nxt = nx2; ++row; nx2 = s_row[wib][row + 2]; }
+        process_clipped(row - radius, (int)(cur & 255u) - 128 + (k - (int)(cur >> 8)));
       }
     } else {
       // very large windows (non-default options): plain scan of the whole window
