@@ -845,6 +845,7 @@ sift_orient_kernel(const float* __restrict__ gauss, const OctInfo oi, int batch,
     const float osig = 1.5f * scl_octv;
     const float expf_scale = __fdiv_rn(-1.f, 2.f * osig * osig);
     const float* gimg = gauss + oi.goff[o] + (size_t)layer * lstride + (size_t)b * rows * pitch;
+    asm volatile("" : "+l"(gimg));   // one 64-bit register pair: each address below is a single IMAD.WIDE
     for (int k = lane; k < ORI_BINS; k += 32) s_hist[wib][k] = 0;
     __syncwarp();
     const int side = 2 * radius + 1, total = side * side;
@@ -855,8 +856,10 @@ sift_orient_kernel(const float* __restrict__ gauss, const OctInfo oi, int batch,
       sm.i = i; sm.j = j;
       sm.ok = !(y <= 0 || y >= rows - 1 || x <= 0 || x >= cols - 1);
       if (sm.ok) {
-        const float* q = gimg + (size_t)y * pitch + x;
-        sm.xp = __ldg(q + 1); sm.xm = __ldg(q - 1); sm.yu = __ldg(q - pitch); sm.yd = __ldg(q + pitch);
+        const unsigned ctr = (unsigned)(y * pitch + x);
+        const float* q = gimg + ctr;
+        sm.xp = __ldg(q + 1); sm.xm = __ldg(q - 1);
+        sm.yu = __ldg(gimg + (ctr - (unsigned)pitch)); sm.yd = __ldg(gimg + (ctr + (unsigned)pitch));
       }
     };
     auto oaccum = [&](const OSamp& sm) {
@@ -1130,11 +1133,11 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
     const int po = oc + 1;
     const int rows = oi.h[po], cols = oi.w[po], pitch = oi.pitch[po];
     const float* img = gauss + oi.goff[po] + (size_t)layer * batch * rows * pitch + (size_t)b * rows * pitch;
+    asm volatile("" : "+l"(img));   // keep the layer pointer as one 64-bit register pair (addresses = one IMAD.WIDE each)
     const float ptx = (kp.x - loc_offset) * scale, pty = (kp.y - loc_offset) * scale;
     const float scl = size * 0.5f;
     const int px = __float2int_rn(ptx), py = __float2int_rn(pty);
     const float2 cs = trig[(size_t)b * kp_cap + ki];
-    const float* img_c = img + ((ptrdiff_t)py * pitch + px);
     const float bins_per_rad = N / 360.f, exp_scale = -1.f / (D * D * 0.5f);
     const float hist_width = 3.0f * scl;
     int radius = __float2int_rn(hist_width * 1.4142135623730951f * (D + 1) * 0.5f);
@@ -1158,10 +1161,11 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
         const int r = py + i, c = px + j;
         sm.ok = sm.ok && r > 0 && r < rows - 1 && c > 0 && c < cols - 1;
       }
-      if (sm.ok) {   // 32-bit offsets from the keypoint's centre pixel (fewer 64-bit address operations)
-        const int off = i * pitch + j;
-        sm.xp = __ldg(img_c + (off + 1)); sm.xm = __ldg(img_c + (off - 1));
-        sm.yu = __ldg(img_c + (off - pitch)); sm.yd = __ldg(img_c + (off + pitch));
+      if (sm.ok) {   // unsigned 32-bit element indices into the layer image: one wide multiply-add per address
+        const unsigned ctr = (unsigned)((py + i) * pitch + (px + j));
+        const float* pc = img + ctr;
+        sm.xp = __ldg(pc + 1); sm.xm = __ldg(pc - 1);
+        sm.yu = __ldg(img + (ctr - (unsigned)pitch)); sm.yd = __ldg(img + (ctr + (unsigned)pitch));
       }
     };
     auto accumulate = [&](const Samp& sm) {
