@@ -292,22 +292,30 @@ __device__ __forceinline__ u64 f2_bcast(float k) { const float2 v = make_float2(
 // (64 rows): the column pass of chunk c reads groups c..c+2 while group c+3 is being written, which
 // leaves a single __syncthreads per chunk.
 constexpr int TS_W = 128, TS_G = 16, TS_HALO = 16, TS_BOXW = TS_W + 2 * TS_HALO;   // 160-float box rows
+__host__ __device__ constexpr int TS_MIRROR(int r) { return 3 + 2 * r; }
 template <int R>
 __global__ void __launch_bounds__(256, 3)
 sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* __restrict__ dst,
                      float* __restrict__ dog, const float* __restrict__ src, int h, int w, int pitch,
                      int seg_rows, const Taps taps) {
   static_assert(R <= TS_HALO, "halo too small");
-  constexpr int RING = 64;
+  // ring slots 0..MIRROR-1 are kept a second time at RING + slot, so the 4 + 2R consecutive rows a
+  // column window reads are always contiguous in shared memory (one base address, immediate offsets)
+  constexpr int RING = 64, MIRROR = TS_MIRROR(R);
   extern __shared__ __align__(128) uint8_t tsm[];      // > 48 KB: dynamic shared memory (opt-in)
   float (*stage)[TS_G][TS_BOXW] = reinterpret_cast<float (*)[TS_G][TS_BOXW]>(tsm);                        // [2]
-  float (*ring)[TS_W] = reinterpret_cast<float (*)[TS_W]>(tsm + 2 * TS_G * TS_BOXW * 4);                   // [RING]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(tsm + 2 * TS_G * TS_BOXW * 4 + RING * TS_W * 4);
+  float (*ring)[TS_W] = reinterpret_cast<float (*)[TS_W]>(tsm + 2 * TS_G * TS_BOXW * 4);                   // [RING + MIRROR]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(tsm + 2 * TS_G * TS_BOXW * 4 + (RING + MIRROR) * TS_W * 4);
   const int b = blockIdx.z;
   const int x0 = blockIdx.x * TS_W;
   const int ys = blockIdx.y * seg_rows, ye = min(ys + seg_rows, h);
   const size_t img_off = (size_t)b * h * pitch;
   const float* img = src + img_off;
+  float* dst_i = dst + img_off;
+  float* dog_i = dog + img_off;
+  // the three image pointers stay in registers as 64-bit values; pixel addresses are then one wide
+  // multiply-add of an unsigned 32-bit element index each
+  asm volatile("" : "+l"(img), "+l"(dst_i), "+l"(dog_i));
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const bool edge = (x0 - R < 0) || (x0 + TS_W + R > w);
   const uint32_t bar0 = smem_u32(&bars[0]);
@@ -363,7 +371,10 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
 #pragma unroll
         for (int o = 0; o < 4; ++o) acc[o] = fmaf(taps.k[i], win[C + o - i] + win[C + o + i], acc[o]);
       }
-      *reinterpret_cast<float4*>(&ring[row & (RING - 1)][4 * lane]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      const int slot = row & (RING - 1);
+      const float4 o4 = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(&ring[slot][4 * lane]) = o4;
+      if (slot < MIRROR) *reinterpret_cast<float4*>(&ring[RING + slot][4 * lane]) = o4;   // warp-uniform
     }
   };
 
@@ -384,18 +395,13 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
       // centre pixels of G[l] for the fused DoG: issued first so their latency hides behind the filter
       float2 cc[4];
 #pragma unroll
-      for (int o = 0; o < 4; ++o) cc[o] = (yf + o < ye) ? __ldg(reinterpret_cast<const float2*>(img + (size_t)(yf + o) * pitch + x)) : make_float2(0.f, 0.f);
+      for (int o = 0; o < 4; ++o) cc[o] = (yf + o < ye) ? __ldg(reinterpret_cast<const float2*>(img + (unsigned)((yf + o) * pitch + x))) : make_float2(0.f, 0.f);
       u64 win[4 + 2 * R];
       const int s0 = (yf - R) & (RING - 1);
       if (yf - R >= 0 && yf + 3 + R < h) {
-        if (s0 + 4 + 2 * R <= RING) {          // contiguous slots: one base address, immediate offsets
-          const float* base = &ring[s0][2 * cp];
+        const float* base = &ring[s0][2 * cp];   // s0 + q <= RING - 1 + MIRROR
 #pragma unroll
-          for (int q = 0; q < 4 + 2 * R; ++q) win[q] = *reinterpret_cast<const u64*>(base + q * TS_W);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4 + 2 * R; ++q) win[q] = *reinterpret_cast<const u64*>(&ring[(s0 + q) & (RING - 1)][2 * cp]);
-        }
+        for (int q = 0; q < 4 + 2 * R; ++q) win[q] = *reinterpret_cast<const u64*>(base + q * TS_W);
       } else {
 #pragma unroll
         for (int q = 0; q < 4 + 2 * R; ++q) {
@@ -417,10 +423,10 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
       for (int o = 0; o < 4; ++o) {
         const int y = yf + o;
         if (y < ye) {
-          const size_t g = (size_t)y * pitch + x;
+          const unsigned g = (unsigned)(y * pitch + x);
           const float2 v = *reinterpret_cast<const float2*>(&acc[o]);
-          *reinterpret_cast<float2*>(dst + img_off + g) = v;
-          *reinterpret_cast<float2*>(dog + img_off + g) = make_float2(v.x - cc[o].x, v.y - cc[o].y);
+          *reinterpret_cast<float2*>(dst_i + g) = v;
+          *reinterpret_cast<float2*>(dog_i + g) = make_float2(v.x - cc[o].x, v.y - cc[o].y);
         }
       }
     }
@@ -1349,7 +1355,7 @@ static int launch_tma_t(const CUtensorMap& tm, int z_base, const float* src, flo
   if (seg_rows < 4 * TS_G) seg_rows = 4 * TS_G;
   n_seg = div_up(h, seg_rows);
   dim3 grid(strips, n_seg, batch);
-  constexpr int smem = 2 * TS_G * TS_BOXW * 4 + 64 * TS_W * 4 + 64;
+  constexpr int smem = 2 * TS_G * TS_BOXW * 4 + (64 + TS_MIRROR(R)) * TS_W * 4 + 64;
   static bool attr = false;
   if (!attr) {
     VO_CUDA(cudaFuncSetAttribute(sift_blur_tma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
