@@ -163,12 +163,17 @@ int vo_p3p(vo_ctx* ctx, const double* img, const double* world, int n, int col_m
 
 /* ---------------------------------------------------------------------------- input staging */
 /* Replaces imageDatastore / readimage (VO.m:16-17, 71-72) for KITTI odometry frames: 8-bit grayscale,
- * non-interlaced PNG.  Host code (zlib inflate + PNG row filters); other PNG flavours are rejected.
+ * non-interlaced PNG.  Host code (the library's own inflate and PNG row filters; zlib only adjudicates
+ * streams that decoder rejects); other PNG flavours are rejected.
  * vo_png_read_batch decodes n files with n_threads workers (<= 0: one per hardware thread) into
  * out[n][rows][cols] -- typically the pinned batch buffer handed to vo_frames. */
 int vo_png_info(const uint8_t* file, size_t n_bytes, int* rows, int* cols, int* bit_depth, int* color_type);
 int vo_png_decode_gray8(const uint8_t* file, size_t n_bytes, uint8_t* out, int ld, int rows, int cols);
 int vo_png_read_batch(const char* const* paths, int n, int rows, int cols, uint8_t* out, int n_threads);
+/* The inflate stage of the reader on its own: the zlib stream in[0, n_in) must inflate to exactly n_out
+ * bytes with a matching Adler-32 (this is the library's own decoder, without the zlib second opinion
+ * the PNG reader takes on failure). */
+int vo_inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t n_out);
 
 /* ------------------------------------------------------------------------- frame pipeline */
 typedef struct {

@@ -2,7 +2,7 @@
 ``readimage`` (VO.m:16-17, 71-72) for KITTI odometry frames, i.e. 8-bit grayscale PNG files.
 
 ``ImageDatastore`` mirrors the two members VO.m uses (``Files``, ``readimage``); ``read_batch`` decodes
-many files with native worker threads (libvo_b200: zlib inflate + PNG row filters) into one
+many files with native worker threads (libvo_b200: its own inflate + PNG row filters) into one
 contiguous -- optionally pinned -- batch buffer, and ``run_sequence`` overlaps decoding batch k+1 on
 the host with vo_frames on batch k."""
 import ctypes as C
@@ -33,6 +33,15 @@ def png_decode(data):
     check(_lib.lib().vo_png_decode_gray8(buf.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_size_t(len(buf)),
                                          out.ctypes.data_as(C.POINTER(C.c_uint8)), cols, rows, cols))
     return out
+
+
+def inflate_zlib(data, n_out):
+    """The reader's inflate stage alone: zlib stream (bytes) -> exactly ``n_out`` bytes (Adler-32 checked)."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    out = np.empty(max(n_out, 1), dtype=np.uint8)
+    check(_lib.lib().vo_inflate_zlib(buf.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_size_t(len(buf)),
+                                     out.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_size_t(n_out)))
+    return out[:n_out].tobytes()
 
 
 def read_batch(paths, rows=None, cols=None, out=None, threads=0):
