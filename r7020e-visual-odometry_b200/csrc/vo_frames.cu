@@ -186,6 +186,10 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
     if (nl > kc || nr > kc || hC[(2 * i) * 4 + 1] > kc || hC[(2 * i + 1) * 4 + 1] > kc) {
       set_error("vo_frames: frame %d has more keypoints (%d / %d) than max_keypoints capacity %d", i, nl, nr, kc);
       rc = VO_ERR_CAPACITY;
+    } else if (hC[(2 * i) * 4 + 0] > 8 * kc || hC[(2 * i + 1) * 4 + 0] > 8 * kc) {   // the plan keeps 8 candidates per keypoint slot
+      set_error("vo_frames: frame %d has more extrema candidates (%d / %d) than the plan holds (%d); raise max_keypoints",
+                i, hC[(2 * i) * 4 + 0], hC[(2 * i + 1) * 4 + 0], 8 * kc);
+      rc = VO_ERR_CAPACITY;
     }
     if (counts) {
       int* c = counts + 8 * i;
