@@ -38,6 +38,11 @@ enum vo_status {
 
 int vo_version(void);
 const char* vo_last_error(void);
+/* A context owns one stream and all device buffers of the calls made through it; contexts share
+ * nothing, so several may be used concurrently from different host threads (one thread per context:
+ * the batches-in-flight pattern of INTEGRATION.md).  Process model: one process per GPU -- all
+ * contexts of a process must be created on the same device (kernel attributes are cached per
+ * process, not per device). */
 int vo_ctx_create(int device, vo_ctx** ctx);
 void vo_ctx_destroy(vo_ctx* ctx);
 int vo_ctx_sync(vo_ctx* ctx);

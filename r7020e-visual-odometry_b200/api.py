@@ -22,6 +22,7 @@ KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"),
                      ("response", "f4"), ("octave", "i4")])
 
 _default_ctx = None
+_process_device = None   # libvo_b200 runs one process per GPU: the device of the first context
 
 
 def _p(a, t):
@@ -29,12 +30,17 @@ def _p(a, t):
 
 
 class Context:
-    """Owns the device state of one GPU (vo_ctx)."""
+    """Owns the device state of one GPU (vo_ctx): one stream and all device buffers.  Several
+    contexts on the same device may run concurrently from different host threads; all contexts of
+    a process live on one device (vo_ctx_create refuses a second device)."""
 
     def __init__(self, device=0):
+        global _process_device
         self._h = C.c_void_p()
         check(_lib.lib().vo_ctx_create(int(device), C.byref(self._h)))
         self.device = device
+        if _process_device is None:
+            _process_device = int(device)
 
     def close(self):
         if self._h:
@@ -87,7 +93,7 @@ class Context:
 def default_context():
     global _default_ctx
     if _default_ctx is None:
-        _default_ctx = Context(0)
+        _default_ctx = Context(0 if _process_device is None else _process_device)
     return _default_ctx
 
 

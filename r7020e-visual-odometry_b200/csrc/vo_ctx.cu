@@ -1,5 +1,6 @@
 // vo_ctx.cu -- context lifetime, error string, scratch buffers, driver entry points.
 #include "vo_internal.h"
+#include <atomic>
 
 namespace vo {
 
@@ -131,6 +132,13 @@ int vo_ctx_create(int device, vo_ctx** out) {
     vo::set_error("device %d is sm_%d%d; libvo_b200 is built for sm_100a only", device, prop.major,
                   prop.minor);
     return VO_ERR_CUDA;
+  }
+  // one process per GPU: kernel attributes (opt-in shared memory sizes) are cached per process
+  static std::atomic<int> process_device(-1);
+  int first = -1;
+  if (!process_device.compare_exchange_strong(first, device) && first != device) {
+    vo::set_error("this process already uses device %d; libvo_b200 runs one process per GPU (requested device %d)", first, device);
+    return VO_ERR_STATE;
   }
   vo_ctx* c = new vo_ctx();
   c->device = device;
