@@ -30,6 +30,19 @@ for tag, shape, seed in (("small", (120, 160), 1), ("wide", (188, 620), 2)):
                         octave=np.array([p.octave for p in kps], dtype=np.int32), desc=desc.astype(np.uint8))
     print(tag, len(kps), "keypoints")
 
+# ---- SIFT with non-default options (the MATLAB name-value pairs NumLayersInOctave, Sigma,
+# ContrastThreshold, EdgeThreshold map onto these OpenCV constructor arguments)
+img = synth.texture(150, 210, seed=9)
+opt_sets = {"layers2": dict(nOctaveLayers=2), "layers4": dict(nOctaveLayers=4), "sigma1p2": dict(sigma=1.2),
+            "contrast_edge": dict(contrastThreshold=0.08, edgeThreshold=5)}
+store = {"image": img}
+for tag, kw in opt_sets.items():
+    kps, desc = cv2.SIFT_create(**kw).detectAndCompute(img, None)
+    store[f"kps_{tag}"] = np.array([[p.pt[0], p.pt[1], p.size, p.angle] for p in kps], dtype=np.float32)
+    store[f"desc_{tag}"] = desc.astype(np.uint8)
+    print("options", tag, len(kps), "keypoints")
+np.savez_compressed(os.path.join(HERE, "sift_cv2_options.npz"), **store)
+
 # ---- Gaussian blur + base image (cv::resize + GaussianBlur)
 img = synth.texture(96, 130, seed=5)
 f = img.astype(np.float32)

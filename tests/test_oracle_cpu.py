@@ -40,6 +40,28 @@ def test_sift_oracle_vs_opencv(tag):
     assert np.array_equal(odesc, np.rint(odesc)) and odesc.max() <= 255 and odesc.min() >= 0
 
 
+@pytest.mark.parametrize("tag,kw", [("layers2", dict(n_octave_layers=2)), ("layers4", dict(n_octave_layers=4)),
+                                    ("sigma1p2", dict(sigma=1.2)),
+                                    ("contrast_edge", dict(contrast_threshold=0.08, edge_threshold=5.0))])
+def test_sift_oracle_options_vs_opencv(tag, kw):
+    """The option handling (layers per octave, sigma, contrast / edge thresholds) is pinned too."""
+    from scipy.spatial import cKDTree
+    g = np.load(os.path.join(G, "sift_cv2_options.npz"))
+    ck, cd = g[f"kps_{tag}"], g[f"desc_{tag}"].astype(np.float32)
+    okp, odesc = oracle.sift(g["image"], **kw)
+    assert len(okp) == len(ck)
+    tree = cKDTree(ck[:, :2])
+    hit = exact = 0
+    for i in range(len(okp)):
+        for c in tree.query_ball_point([okp["x"][i], okp["y"][i]], 0.5):
+            da = abs(((okp["angle"][i] - ck[c, 3]) + 180.0) % 360.0 - 180.0)
+            if da < 2.0 and abs(okp["size"][i] - ck[c, 2]) < 0.1 * ck[c, 2]:
+                hit += 1; exact += np.array_equal(odesc[i], cd[c])
+                break
+    assert hit == len(okp)                                     # every keypoint within 0.5 px / 2 deg / 10 % size
+    assert exact / len(okp) >= 0.9                             # descriptors bit-identical to OpenCV's
+
+
 def test_blur_and_base_image_vs_opencv():
     g = np.load(os.path.join(G, "blur_cv2.npz"))
     f = g["image"].astype(np.float32)
