@@ -2,7 +2,7 @@
 cv2 4.13 and /root/reference exist; the GPU box only reads the .npz files).
 
 The reference (MATLAB + closed-source toolbox) ships no tests or golden vectors, so the oracle is
-pinned against independent implementations: OpenCV 4.13 SIFT / GaussianBlur / triangulatePoints,
+pinned against independent implementations: OpenCV 4.13 SIFT / GaussianBlur / triangulatePoints / solveP3P,
 NumPy float64 brute-force matching, the published Philox4x32-10 known answer, and the reference's
 own data files (kitti/00/calib.txt, kitti/poses/00.txt).
 
@@ -74,6 +74,24 @@ proj = lambda P: (lambda h: h[:, :2] / h[:, 2:])(np.c_[X, np.ones(64)] @ P.T)
 x1 = proj(P0) + rng.normal(0, 0.3, (64, 2)); x2 = proj(P1) + rng.normal(0, 0.3, (64, 2))
 c = cv2.triangulatePoints(P0, P1, x1.T, x2.T)
 np.savez_compressed(os.path.join(HERE, "triangulate_cv2.npz"), x1=x1, x2=x2, xyz=(c[:3] / c[3]).T, truth=X)
+
+# ---- P3P: every solution cv2.solveP3P finds for 200 random three-point problems (KITTI intrinsics)
+rng = np.random.default_rng(12)
+K = np.array([[718.856, 0, 607.1928], [0, 718.856, 185.2157], [0, 0, 1.0]])
+p3p_X, p3p_uv, p3p_n, p3p_R, p3p_t = [], [], [], [], []
+for _ in range(200):
+    R = cv2.Rodrigues(rng.normal(0, 0.3, 3))[0]; t = rng.normal(0, 1, 3)
+    Xw = np.c_[rng.uniform(-10, 10, 3), rng.uniform(-3, 3, 3), rng.uniform(5, 40, 3)]
+    Xc = Xw @ R.T + t
+    uv = np.c_[K[0, 0] * Xc[:, 0] / Xc[:, 2] + K[0, 2], K[1, 1] * Xc[:, 1] / Xc[:, 2] + K[1, 2]]
+    n, rv, tv = cv2.solveP3P(Xw.reshape(-1, 1, 3), uv.reshape(-1, 1, 2), K, None, flags=cv2.SOLVEPNP_P3P)
+    Rs = np.zeros((4, 3, 3)); ts = np.zeros((4, 3))
+    for i in range(n):
+        Rs[i] = cv2.Rodrigues(rv[i])[0]; ts[i] = tv[i].ravel()
+    p3p_X.append(Xw); p3p_uv.append(uv); p3p_n.append(n); p3p_R.append(Rs); p3p_t.append(ts)
+np.savez_compressed(os.path.join(HERE, "p3p_cv2.npz"), X=np.array(p3p_X), uv=np.array(p3p_uv), n=np.array(p3p_n),
+                    R=np.array(p3p_R), t=np.array(p3p_t), K=K)
+print("p3p:", int(np.sum(p3p_n)), "solutions")
 
 # ---- reference data files: calibration and the head of the ground-truth poses of sequence 00
 ref = "/root/reference/kitti"

@@ -181,6 +181,23 @@ def test_p3p_and_msac():
     assert same["best_trial"] == r["best_trial"] and np.array_equal(same["A"], r["A"])   # seeded => reproducible
 
 
+def test_p3p_solutions_equal_opencv_solvep3p():
+    """The oracle's P3P (Gao) against OpenCV's solveP3P on 200 three-point problems: the same number of
+    solutions, and each of them equal to 1e-5 (golden vectors: tests/golden/p3p_cv2.npz)."""
+    g = np.load(os.path.join(G, "p3p_cv2.npz"))
+    K = g["K"]
+    total = 0
+    for X, uv, n, Rc, tc in zip(g["X"], g["uv"], g["n"], g["R"], g["t"]):
+        ray = np.c_[(uv[:, 0] - K[0, 2]) / K[0, 0], (uv[:, 1] - K[1, 2]) / K[1, 1], np.ones(3)]
+        f = ray / np.linalg.norm(ray, axis=1, keepdims=True)
+        Rs, ts = oracle.p3p_solve(f, X)
+        assert len(Rs) == n
+        for i in range(n):
+            assert min(np.abs(Rs[j] - Rc[i]).max() + np.abs(ts[j] - tc[i]).max() for j in range(len(Rs))) < 1e-5
+        total += n
+    assert total > 300
+
+
 def test_find_remaining_points_index_chain():
     """VO.m:280-334 semantics on a toy problem where every match is known: the four gathers must
     leave all eight arrays row-aligned."""
