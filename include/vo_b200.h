@@ -40,9 +40,8 @@ int vo_version(void);
 const char* vo_last_error(void);
 /* A context owns one stream and all device buffers of the calls made through it; contexts share
  * nothing, so several may be used concurrently from different host threads (one thread per context:
- * the batches-in-flight pattern of INTEGRATION.md).  Process model: one process per GPU -- all
- * contexts of a process must be created on the same device (kernel attributes are cached per
- * process, not per device). */
+ * the batches-in-flight pattern of INTEGRATION.md).  The
+ * contexts of a process may live on different devices (kernel attributes are tracked per device). */
 int vo_ctx_create(int device, vo_ctx** ctx);
 void vo_ctx_destroy(vo_ctx* ctx);
 int vo_ctx_sync(vo_ctx* ctx);
@@ -101,7 +100,8 @@ typedef struct {
   int index_base;        /* 0 or 1 (MATLAB)                                                   */
 } vo_match_opts;
 
-/* f1: n1 x dim, f2: n2 x dim float32 (dim <= 256).  col_major = 1: MATLAB layout (element (i,k)
+/* f1: n1 x dim, f2: n2 x dim float32 (1 <= dim <= 128: one descriptor is one 128-byte
+ * tensor-core K block; VO_ERR_ARG otherwise).  col_major = 1: MATLAB layout (element (i,k)
  * at f[k*n + i]).  idx1/idx2/metric: capacity n1 entries; rows ascending in idx1.
  * indexPairs(:,1) = idx1, indexPairs(:,2) = idx2, matchMetric = metric (may be NULL). */
 int vo_match(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2, int dim,

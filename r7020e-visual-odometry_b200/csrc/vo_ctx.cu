@@ -1,10 +1,26 @@
 // vo_ctx.cu -- context lifetime, error string, scratch buffers, driver entry points.
 #include "vo_internal.h"
 #include <atomic>
+#include <mutex>
+#include <utility>
 
 namespace vo {
 
 static thread_local char g_err[1024] = "";
+
+int ensure_dyn_smem(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> done;
+  int dev = 0;
+  VO_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> g(mu);
+  size_t& cur = done[std::make_pair(dev, func)];
+  if (bytes > cur) {
+    VO_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+  }
+  return VO_OK;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -132,13 +148,6 @@ int vo_ctx_create(int device, vo_ctx** out) {
     vo::set_error("device %d is sm_%d%d; libvo_b200 is built for sm_100a only", device, prop.major,
                   prop.minor);
     return VO_ERR_CUDA;
-  }
-  // one process per GPU: kernel attributes (opt-in shared memory sizes) are cached per process
-  static std::atomic<int> process_device(-1);
-  int first = -1;
-  if (!process_device.compare_exchange_strong(first, device) && first != device) {
-    vo::set_error("this process already uses device %d; libvo_b200 runs one process per GPU (requested device %d)", first, device);
-    return VO_ERR_STATE;
   }
   vo_ctx* c = new vo_ctx();
   c->device = device;

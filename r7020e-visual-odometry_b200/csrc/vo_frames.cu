@@ -11,7 +11,8 @@
 
 namespace vo {
 
-void frame_plan_destroy(FramePlan*) {}
+struct FramePlan { int unused = 0; };
+void frame_plan_destroy(FramePlan* p) { delete p; }
 
 // out_k[p][k] = src_k[p][idx[p][k]] for k < cnt[p]   (up to two arrays share one index list)
 __global__ void __launch_bounds__(256)

@@ -214,7 +214,8 @@ bool inflate_zlib_fast(const uint8_t* in0, size_t n_in, uint8_t* out0, size_t n_
       const unsigned len = p[0] | (p[1] << 8), nlen = p[2] | (p[3] << 8);
       if ((len ^ 0xFFFFu) != nlen) return false;
       p += 4;
-      if ((size_t)(in_end - p) < len || (size_t)(out_end - out) < len) return false;
+      // a paired literal may have left `out` one byte past out_end: reject before the unsigned difference wraps
+      if (out > out_end || (size_t)(in_end - p) < len || (size_t)(out_end - out) < len) return false;
       memcpy(out, p, len);
       out += len; in = p + len; bitbuf = 0; bitcnt = 0;
       if (last) break;
@@ -291,6 +292,7 @@ bool inflate_zlib_fast(const uint8_t* in0, size_t n_in, uint8_t* out0, size_t n_
       }
       if (e & (E_EOB | E_BAD)) {
         if (e & E_BAD) return false;
+        if (out > out_end) return false;   // end of block after a literal pair that overran the output
         VO_DROP(e & 15u);
         break;
       }

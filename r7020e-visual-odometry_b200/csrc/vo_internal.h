@@ -106,6 +106,12 @@ void frame_plan_destroy(FramePlan*);
 
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
+// Opt-in dynamic shared memory of a kernel, raised (never lowered) once per (device, kernel).  Contexts on
+// different host threads and different devices share kernels, so the record is process-wide and mutex-guarded.
+int ensure_dyn_smem(const void* func, size_t bytes);
+template <typename F>
+inline int ensure_dyn_smem_of(F* func, size_t bytes) { return ensure_dyn_smem(reinterpret_cast<const void*>(func), bytes); }
+
 // RAII bracket around one or more launches of a stage
 struct ProfScope {
   vo_ctx* c; cudaStream_t st; ProfRec rec; bool on;

@@ -1,24 +1,33 @@
 // vo_match.cu -- matchFeatures(f1, f2) on B200 (replaces VO.m:87, 283, 293, 311, 323).
 //
-// Pipeline (all on one stream, no host round trip between kernels):
-//   1. match_prep_kernel (x2)  rows -> 1/||row|| (oracle fmaf order), bf16 hi/lo split operands
-//                              A' = [hi | hi | lo], B' = [hi | lo | hi] (K-major), and a device
-//                              flag "some value is not an integer in 0..255".
-//   2. match_topk_kernel       tcgen05 GEMM C = A' B'^T with fp32 accumulators in TMEM, operands
-//                              staged by TMA (128B swizzle), warp-specialised: 1 TMA warp, 1 MMA
-//                              warp, 8 epilogue warps.  When every value is an integer 0..255 only
-//                              the first K columns are contracted and C is the EXACT dot product;
-//                              otherwise all 3K columns (hi*hi + hi*lo + lo*hi).  The epilogue
-//                              never stores C: it scales by 1/||b_j|| and keeps the per-row top-3
-//                              (key, column) in registers across all column tiles.
-//   3. match_finalize_kernel   merges the per-split candidates, recomputes the oracle's exact FP32
-//                              score for the three candidates, and certifies the row: every
-//                              non-candidate has key <= k3 (+eps on the split path), and the score
-//                              is a monotone function of the key, so if f(k3) > s1 the nearest
-//                              neighbour (lowest index on ties) and s2 are exactly the oracle's.
-//   4. match_rowscan_kernel    rows that could not be certified (3-way ties, near-ties on the
-//                              split path) are re-evaluated by an exact FP32 scan of all columns.
-//   5. select/compact          threshold + ratio (+ Unique) tests, ordered compaction.
+// Pipeline (all on one stream, no host round trip between kernels; DESIGN.md section 4):
+//   1. match_prep_rows128_kernel   rows -> 1/||row|| (oracle fmaf order), the row as 128 u8 (one 128-byte
+//                              row = one 128B-swizzled K block), max_j 1/||b_j|| per problem and a device
+//                              flag "some value is not an integer in 0..255" (match_prep_kernel is the
+//                              dim < 128 / gathered / column-major form of the same thing).
+//      match_prep_split_kernel only when that flag is set: bf16 hi/lo split operands
+//                              A' = [hi | hi | lo], B' = [hi | lo | hi] for the general-float path.
+//   2. match_topk_u8_kernel    THE hot kernel.  tcgen05.mma.kind::i8 (u8 x u8 -> s32: the exact integer
+//                              dot product), one CTA per SM, 18 warps: warp 0 = TMA producer (two resident
+//                              128-row A panels, B tiles through a 7-stage mbarrier ring), warp 1 = MMA
+//                              issuer (elect.sync, operands in uniform registers) + TMEM allocator
+//                              (2 accumulator stages x 2 panels x 128 columns), warps 2-17 = epilogue:
+//                              tcgen05.ld 32x32b.x32, integer max-tree prefilter against the row's bound,
+//                              exact key = dot * 1/||b_j|| only for chunks that can matter, per-row top-3
+//                              (key, column) in registers across all column tiles.  C is never stored.
+//                              Persistent form (one CTA per SM over a contiguous share of panel x tile
+//                              space) for single large problems; variants behind environment switches:
+//                              match_topk_u8x2_kernel (cta_group::2 pairs), match_topk_u8ts_kernel (A in TMEM).
+//      match_topk_kernel       the same structure with kind::f16 on the split-bf16 operands; both kernels
+//                              are launched and one returns at once on the device flag (no host sync).
+//   3. match_finalize_kernel   merges the per-segment candidates, recomputes the oracle's exact FP32 score
+//                              of the candidates and certifies the row from the monotone key -> score map
+//                              (nearest neighbour with lowest index on ties, s2 or a proof that the
+//                              threshold / ratio outcome cannot change).
+//   4. match_rowscan_kernel    rows that could not be certified (3-way ties, near-ties on the split path)
+//                              are re-evaluated by an exact scan of all columns (integer dp4a / FP32).
+//   5. match_select_* / match_records_kernel   threshold + ratio (+ Unique) tests, ordered compaction, or
+//                              the 16-byte best-2 records of the relocalisation shard.
 //
 // Score arithmetic is the contract in oracle/match.c (DESIGN.md "match arithmetic").
 #include "vo_internal.h"
@@ -1690,7 +1699,6 @@ static int make_u8_map(CUtensorMap* map, const uint8_t* base, int rows_alloc, in
   return VO_OK;
 }
 
-static bool g_attr_set = false;
 constexpr bool MATCH_PAIRS_DEFAULT = false;
 constexpr bool MATCH_TS_DEFAULT = false;
 
@@ -1818,14 +1826,11 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
     VO_TRY(make_operand_map(&tmB, opB, b_alloc, kp, n_prob, BN));
     VO_TRY(make_u8_map(&tmA8, u8A, a_alloc, n_prob));
     VO_TRY(make_u8_map(&tmB8, u8B, b_alloc, n_prob));
-    if (!g_attr_set) {
-      VO_CUDA(cudaFuncSetAttribute(match_topk_u8ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM_BYTES));
-      VO_CUDA(cudaFuncSetAttribute(match_topk_u8x2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM_BYTES));
-      VO_CUDA(cudaFuncSetAttribute(match_topk_u8x2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM_BYTES));
-      VO_CUDA(cudaFuncSetAttribute(match_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      VO_CUDA(cudaFuncSetAttribute(match_topk_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM_BYTES));
-      g_attr_set = true;
-    }
+    VO_TRY(ensure_dyn_smem_of(match_topk_u8ts_kernel, T_SMEM_BYTES));
+    VO_TRY(ensure_dyn_smem_of(match_topk_u8x2_kernel<128>, X_SMEM_BYTES));
+    VO_TRY(ensure_dyn_smem_of(match_topk_u8x2_kernel<256>, X_SMEM_BYTES));
+    VO_TRY(ensure_dyn_smem_of(match_topk_kernel, SMEM_BYTES));
+    VO_TRY(ensure_dyn_smem_of(match_topk_u8_kernel, U_SMEM_BYTES));
     // both variants are launched; each reads the device-side "non-integer input" flag and one of them
     // returns at once (no host synchronisation to pick the path)
     ProfScope ps(ctx, st, "match_gemm_topk", 0.0, exact_sizes ? 2.0 * A.cap * B.cap * dim : 0.0, 2);
@@ -1994,7 +1999,8 @@ extern "C" {
 int vo_match(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2, int dim, int col_major,
              const vo_match_opts* opts, uint32_t* idx1, uint32_t* idx2, float* metric, int* n_pairs) {
   VO_CHECK_ARG(ctx && n_pairs, "ctx/n_pairs is null");
-  VO_CHECK_ARG(n1 >= 0 && n2 >= 0 && dim > 0, "negative size");
+  VO_CHECK_ARG(n1 >= 0 && n2 >= 0, "negative size");
+  VO_CHECK_ARG(dim > 0 && dim <= 128, "dim must be in 1..128 (SIFT descriptors are 128-d)");
   VO_CHECK_ARG((n1 == 0 || f1) && (n2 == 0 || f2), "feature pointer is null");
   VO_CHECK_ARG(n1 == 0 || (idx1 && idx2), "output pointer is null");
   VO_CUDA(cudaSetDevice(ctx->device));
@@ -2028,7 +2034,8 @@ int vo_match_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, 
                  const vo_match_opts* opts, uint32_t* idx1_dev, uint32_t* idx2_dev, float* metric_dev,
                  int* n_pairs_dev, void* stream) {
   VO_CHECK_ARG(ctx && n_pairs_dev, "ctx/n_pairs_dev is null");
-  VO_CHECK_ARG(n1 >= 0 && n2 >= 0 && dim > 0, "negative size");
+  VO_CHECK_ARG(n1 >= 0 && n2 >= 0, "negative size");
+  VO_CHECK_ARG(dim > 0 && dim <= 128, "dim must be in 1..128 (SIFT descriptors are 128-d)");
   VO_CUDA(cudaSetDevice(ctx->device));
   return match_device(ctx, f1_dev, n1, f2_dev, n2, dim, 0, opts, idx1_dev, idx2_dev, metric_dev, n_pairs_dev,
                       (cudaStream_t)stream);
@@ -2037,7 +2044,8 @@ int vo_match_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, 
 int vo_match_top2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, int n2, int dim,
                       uint32_t* j1_dev, float* s1_dev, float* s2_dev, void* stream) {
   VO_CHECK_ARG(ctx, "ctx is null");
-  VO_CHECK_ARG(n1 >= 0 && n2 >= 0 && dim > 0, "negative size");
+  VO_CHECK_ARG(n1 >= 0 && n2 >= 0, "negative size");
+  VO_CHECK_ARG(dim > 0 && dim <= 128, "dim must be in 1..128 (SIFT descriptors are 128-d)");
   VO_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (n1 == 0) return VO_OK;
@@ -2053,7 +2061,8 @@ int vo_match_top2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_
 int vo_match_best2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, int n2, int dim,
                        const vo_match_opts* opts, void* records_dev, void* stream) {
   VO_CHECK_ARG(ctx && records_dev, "ctx/records_dev is null");
-  VO_CHECK_ARG(n1 >= 0 && n2 >= 0 && dim > 0, "negative size");
+  VO_CHECK_ARG(n1 >= 0 && n2 >= 0, "negative size");
+  VO_CHECK_ARG(dim > 0 && dim <= 128, "dim must be in 1..128 (SIFT descriptors are 128-d)");
   VO_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (n1 == 0) return VO_OK;
@@ -2072,7 +2081,8 @@ int vo_match_best2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2
 int vo_match_top2(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2, int dim, int col_major,
                   uint32_t* j1_out, float* s1_out, float* s2_out) {
   VO_CHECK_ARG(ctx, "ctx is null");
-  VO_CHECK_ARG(n1 >= 0 && n2 >= 0 && dim > 0, "negative size");
+  VO_CHECK_ARG(n1 >= 0 && n2 >= 0, "negative size");
+  VO_CHECK_ARG(dim > 0 && dim <= 128, "dim must be in 1..128 (SIFT descriptors are 128-d)");
   VO_CHECK_ARG((n1 == 0 || f1) && (n2 == 0 || f2), "feature pointer is null");
   VO_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -2098,7 +2108,8 @@ int vo_match_stats(vo_ctx* ctx, int stats[4]) {
 
 int vo_match_debug_gemm(vo_ctx* ctx, const float* f1, int n1, const float* f2, int n2, int dim, float* c_out) {
   VO_CHECK_ARG(ctx && f1 && f2 && c_out, "null argument");
-  VO_CHECK_ARG(n1 > 0 && n2 > 0 && dim > 0, "empty input");
+  VO_CHECK_ARG(n1 > 0 && n2 > 0, "empty input");
+  VO_CHECK_ARG(dim > 0 && dim <= 128, "dim must be in 1..128 (SIFT descriptors are 128-d)");
   VO_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   float *d1, *d2, *dc;

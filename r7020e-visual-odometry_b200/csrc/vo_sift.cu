@@ -1332,13 +1332,8 @@ static size_t blur_smem(int R) {
 template <int RT, bool U8>
 static int launch_blur_t(const float* src, const uint8_t* src8, float* dst, float* dog, int h, int w, int pitch,
                          int rows8, int cols8, int batch, const Taps& t, cudaStream_t st) {
-  static bool attr = false;
   const size_t smem = blur_smem(t.r);
-  if (!attr) {
-    VO_CUDA(cudaFuncSetAttribute(sift_blur_dog_kernel<RT, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)blur_smem(RT > 0 ? RT : MAX_R)));
-    attr = true;
-  }
+  VO_TRY(ensure_dyn_smem_of(sift_blur_dog_kernel<RT, U8>, blur_smem(RT > 0 ? RT : MAX_R)));
   dim3 grid(div_up(w, TILE_W), div_up(h, TILE_H), batch);
   sift_blur_dog_kernel<RT, U8><<<grid, 256, smem, st>>>(src, src8, dst, dog, h, w, pitch, rows8, cols8, t);
   return VO_OK;
@@ -1356,11 +1351,7 @@ static int launch_tma_t(const CUtensorMap& tm, int z_base, const float* src, flo
   n_seg = div_up(h, seg_rows);
   dim3 grid(strips, n_seg, batch);
   constexpr int smem = 2 * TS_G * TS_BOXW * 4 + (64 + TS_MIRROR(R)) * TS_W * 4 + 64;
-  static bool attr = false;
-  if (!attr) {
-    VO_CUDA(cudaFuncSetAttribute(sift_blur_tma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  VO_TRY(ensure_dyn_smem_of(sift_blur_tma_kernel<R>, smem));
   sift_blur_tma_kernel<R><<<grid, 256, smem, st>>>(tm, z_base, dst, dog, src, h, w, pitch, seg_rows, t);
   return VO_OK;
 }
@@ -1402,6 +1393,9 @@ static void fill_sift_opts(const vo_sift_opts* in, vo_sift_opts* o) {
 static int get_plan(vo_ctx* ctx, int rows, int cols, int batch, const vo_sift_opts& o, int capacity, SiftPlan** out) {
   SiftPlan* p = ctx->sift_plan;
   const int nl = o.num_layers_in_octave;
+  // candidate words pack y in 12 bits and x in 13 bits of the 2x base image: every entry point (vo_sift,
+  // vo_sift_batch, vo_frames*) comes through here, so the limit is enforced once
+  VO_CHECK_ARG(rows > 0 && cols > 0 && rows <= 4095 / 2 && cols <= 8191 / 2, "image too large (max 2047 x 4095)");
   int kp_cap = ((capacity > 4096 ? capacity : 4096) + 1023) / 1024 * 1024;
   if (p && p->rows == rows && p->cols == cols && p->batch >= batch && p->nl == nl && p->sigma == o.sigma && p->kp_cap >= kp_cap) {
     *out = p; return VO_OK;
@@ -1516,11 +1510,7 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
     memset(&ta, 0, sizeof(ta));
     for (int i = 1; i < nl + 3; ++i) ta.t[i] = p->taps[i];
     const size_t smem = (size_t)small_cap * 12;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-      VO_CUDA(cudaFuncSetAttribute(sift_small_octaves_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_smem = smem;
-    }
+    VO_TRY(ensure_dyn_smem_of(sift_small_octaves_kernel, smem));
     ProfScope ps(ctx, st, "sift_blur_dog_small", px * (8.0 + 12.0 * (nl + 2)));
     sift_small_octaves_kernel<<<batch, 1024, smem, st>>>(p->gauss, p->dog, oi, first_small, p->n_oct, nl, p->batch, small_cap, ta);
   }
@@ -1553,11 +1543,7 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
     ProfScope ps(ctx, st, "sift_sort_dedupe", 0.0, 0.0, 2);
     if (p->kp_cap <= 65536 && p->w[0] > 0) {
       const size_t smem = (size_t)(2 * SORT_BUCKETS + 1) * sizeof(int) + (size_t)p->kp_cap * sizeof(unsigned short);
-      static size_t attr_smem = 0;
-      if (smem > attr_smem) {
-        VO_CUDA(cudaFuncSetAttribute(sift_rank_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-      }
+      VO_TRY(ensure_dyn_smem_of(sift_rank_bucket_kernel, smem));
       // raw keypoint x is in base-image (2x) pixels: [0, w[0])
       sift_rank_bucket_kernel<<<batch, 1024, smem, st>>>(p->raw, p->kp_cap, p->counters, p->sorted, (float)SORT_BUCKETS / (float)p->w[0]);
     } else {
@@ -1601,7 +1587,6 @@ static int sift_host(vo_ctx* ctx, const uint8_t* imgs, int n_img, int rows, int 
                      const vo_sift_opts* opts, int capacity, vo_keypoint* kps, float* desc, int* n_out) {
   VO_CHECK_ARG(ctx && imgs && n_out, "null argument");
   VO_CHECK_ARG(n_img > 0 && rows > 0 && cols > 0 && capacity >= 0, "bad size");
-  VO_CHECK_ARG(rows <= 4095 / 2 && cols <= 8191 / 2, "image too large (max 2047 x 4095)");
   VO_CHECK_ARG(capacity == 0 || (kps && desc), "null output");
   VO_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;

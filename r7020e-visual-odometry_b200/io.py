@@ -8,7 +8,7 @@ the host with vo_frames on batch k."""
 import ctypes as C
 import glob
 import os
-import threading
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -101,16 +101,22 @@ def run_sequence(left_files, right_files, P1, P2, batch=32, seed=0, threads=0, c
 
     rel = np.tile(np.eye(4), (n, 1, 1)); status = np.zeros(n, dtype=np.int32); counts = np.zeros((n, 8), dtype=np.int32)
     load(0, 0)
-    for k, (lo, hi) in enumerate(chunks):
-        th = None
-        if k + 1 < len(chunks):
-            th = threading.Thread(target=load, args=(k + 1, (k + 1) & 1))
-            th.start()
-        m = hi - lo
-        a = bufs[k & 1][1]
-        r, s, c = vo.run_frames(a[0, :m], a[1, :m], P1, P2, seed=seed, first_frame=lo, ctx=ctx)
-        first = 0 if lo == 0 else 1          # the halo frame's outputs belong to the previous chunk
-        rel[lo + first:hi] = r[first:]; status[lo + first:hi] = s[first:]; counts[lo + first:hi] = c[first:]
-        if th is not None:
-            th.join()
+    # the decode of batch k+1 runs as a future: a decode error (bad / missing PNG, size mismatch) is re-raised
+    # by .result() BEFORE that buffer is handed to vo_frames, never swallowed by a background thread
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        pending = None
+        for k, (lo, hi) in enumerate(chunks):
+            if pending is not None:
+                pending.result()
+            pending = pool.submit(load, k + 1, (k + 1) & 1) if k + 1 < len(chunks) else None
+            m = hi - lo
+            a = bufs[k & 1][1]
+            try:
+                r, s, c = vo.run_frames(a[0, :m], a[1, :m], P1, P2, seed=seed, first_frame=lo, ctx=ctx)
+            except BaseException:
+                if pending is not None:
+                    pending.cancel()
+                raise
+            first = 0 if lo == 0 else 1          # the halo frame's outputs belong to the previous chunk
+            rel[lo + first:hi] = r[first:]; status[lo + first:hi] = s[first:]; counts[lo + first:hi] = c[first:]
     return rel, status, counts

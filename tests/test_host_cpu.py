@@ -178,6 +178,17 @@ def test_sequence_runner_and_pipeline_host_logic(tmp_path, monkeypatch):
     assert np.array_equal(rel[:, 0, 3], np.arange(n))              # every frame's pose comes from the batch that owns it
     assert counts[:4, 0].tolist() == [0] * 4 and counts[4:8, 0].tolist() == [3] * 4 and counts[8:, 0].tolist() == [7] * 3
 
+    # a PNG that fails to decode in a LATER batch (decoded by the background worker) must raise before that
+    # buffer reaches vo_frames -- never silently return poses computed from a stale buffer
+    from vo_b200 import VoError
+    calls.clear()
+    good = open(lf[9], "rb").read()
+    open(lf[9], "wb").write(good[:len(good) // 2])
+    with pytest.raises(VoError):
+        io.run_sequence(lf, rf, np.eye(3, 4), np.eye(3, 4), batch=4, pinned=False)
+    assert (7, 4) not in calls                                     # the batch holding frame 9 never ran
+    open(lf[9], "wb").write(good)
+
     class FakeCtx:
         def close(self):
             pass

@@ -160,3 +160,77 @@ def test_png_paeth_runs_use_the_wavefront_path():
         img = (np.cumsum(rng.integers(-6, 7, (23, cols)), axis=1) % 256).astype(np.uint8)
         for filters in ([4], [4, 4, 1], [2, 4, 4, 4, 4, 4, 3], [4, 4, 4, 0, 4, 4, 4, 4, 4, 4, 4, 4, 4, 1], [1, 4, 2, 4, 4, 3]):
             assert np.array_equal(io.png_decode(encode_png(img, filters)), img), (cols, filters)
+
+
+class _Bits:
+    """LSB-first DEFLATE bit writer for hand-built streams."""
+    def __init__(self):
+        self.acc, self.n, self.out = 0, 0, bytearray()
+
+    def put(self, v, nbits):
+        self.acc |= v << self.n
+        self.n += nbits
+        while self.n >= 8:
+            self.out.append(self.acc & 255); self.acc >>= 8; self.n -= 8
+
+    def align(self):
+        if self.n:
+            self.out.append(self.acc & 255); self.acc, self.n = 0, 0
+
+
+def _dyn_block_AA(bits, last, n_lit=2):
+    """A dynamic-Huffman block whose alphabet is {'A': 1 bit, end-of-block: 1 bit} (so two literals pair up in
+    the decoder's two-literal table entries), emitting n_lit 'A's."""
+    bits.put(last, 1); bits.put(2, 2)
+    bits.put(0, 5); bits.put(1, 5); bits.put(14, 4)           # 257 literal/length codes, 2 distance codes, 18 pre-code lengths
+    order = [16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15]
+    for s in order[:18]:
+        bits.put(1 if s in (1, 18) else 0, 3)                 # pre-code: symbol 1 -> '0', symbol 18 -> '1'
+
+    def zeros(k):
+        bits.put(1, 1); bits.put(k - 11, 7)
+    zeros(65); bits.put(0, 1)                                  # lengths 0..64 = 0, 'A' = 1
+    zeros(138); zeros(52); bits.put(0, 1)                      # 66..255 = 0, end-of-block = 1
+    bits.put(0, 1); bits.put(0, 1)                             # two distance codes of length 1
+    for _ in range(n_lit):
+        bits.put(0, 1)
+    bits.put(1, 1)
+
+
+def _stored_block(bits, last, payload):
+    bits.put(last, 1); bits.put(0, 2); bits.align()
+    bits.out += len(payload).to_bytes(2, "little") + (len(payload) ^ 0xFFFF).to_bytes(2, "little") + payload
+
+
+def _zlib_wrap(bits, data):
+    bits.align()
+    return b"\x78\x9c" + bytes(bits.out) + zlib.adler32(data).to_bytes(4, "big")
+
+
+def test_inflate_hand_built_multi_block_streams():
+    """Streams no encoder emits: literal pairs at the very end of the output followed by end-of-block and a stored
+    block (the pair's second byte may land one past the end -- every later bound must notice)."""
+    from vo_b200 import io, VoError
+    rng = np.random.default_rng(5)
+    # valid: dynamic 'A'*k + stored tail, for even and odd k
+    for k in (0, 1, 2, 3, 7, 8):
+        tail = rng.integers(0, 256, 1000, dtype=np.uint8).tobytes()
+        b = _Bits(); _dyn_block_AA(b, 0, k); _stored_block(b, 1, tail)
+        data = b"A" * k + tail
+        z = _zlib_wrap(b, data)
+        assert zlib.decompress(z) == data
+        assert io.inflate_zlib(z, len(data)) == data
+        # dynamic block last, stored first
+        b = _Bits(); _stored_block(b, 0, tail); _dyn_block_AA(b, 1, k)
+        z = _zlib_wrap(b, tail + b"A" * k)
+        assert zlib.decompress(z) == tail + b"A" * k
+        assert io.inflate_zlib(z, len(tail) + k) == tail + b"A" * k
+    # the ADVICE proof of concept: 'A','A',end-of-block into a ONE-byte output, then a 60000-byte stored block
+    for n_out in (0, 1):
+        for k in (n_out + 1, n_out + 2):
+            b = _Bits(); _dyn_block_AA(b, 0, k); _stored_block(b, 1, bytes(60000))
+            with pytest.raises(VoError):
+                io.inflate_zlib(_zlib_wrap(b, b""), n_out)
+            b = _Bits(); _dyn_block_AA(b, 0, k); _dyn_block_AA(b, 0, 2); _stored_block(b, 0, b"xy"); _stored_block(b, 1, bytes(65535))
+            with pytest.raises(VoError):
+                io.inflate_zlib(_zlib_wrap(b, b""), n_out)
