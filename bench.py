@@ -5,19 +5,26 @@
 
 Workload (BASELINE.json configs[1]): the per-frame body of VO.m (SIFT x2 -> stereo match ->
 find_remaining_points (4 matches) -> triangulate -> P3P-MSAC) over 1241x376 stereo frames.  KITTI
-images are not shipped with the reference and there is no network, so the frames are the seeded
-synthetic stream of synth.shift_stream (data: "synthetic").  A *step* = one vo_frames call over
-B+1 consecutive frames (one halo frame + B new frames -> B relative poses).
+images are not shipped with the reference and there is no network, so the frames are rendered: a static
+textured 3-D street world seen through kitti/00/calib.txt's P0/P1 along the reference's own ground truth
+kitti/poses/00.txt (synth.StreetWorld; exact stereo / temporal geometry, occlusion, features entering and
+leaving the view -- data: "synthetic").  A *step* = one vo_frames call over B+1 consecutive frames (one
+halo frame + B new frames -> B relative poses).
 
-One JSON line on stdout (rank 0):
-  value    frames/s with the images already resident in HBM (vo_frames_dev), CUDA-event timed;
-           `--inflight` batches (default 3) are kept in flight, one context / stream / host thread each
-  e2e      frames/s through the C ABI with HOST (pinned) images: H2D of every frame and D2H of
-           the poses inside the timed region (vo_frames), same batches in flight
-  roofline the dominant kernel stage of the step (live CUDA-event timers inside the library) from a
-           third pass over the same steps, one batch at a time (ms_per_step_profiled_serial)
-  match_gemm  the tcgen05 match GEMM alone at 32768 x 32768 x 128 (second headline of BASELINE.json)
-  cpu_baseline  the single-threaded C oracle on a bounded sample of the same frames (rank 0, N=1)
+One JSON line on stdout (rank 0).  All five BASELINE.json configs appear in it, each with a parity flag:
+  value / e2e    configs[1]/[2]: frames/s device-resident (vo_frames_dev) and through the C ABI with HOST
+                 pinned frames (vo_frames: H2D of every frame, D2H of the poses inside the timed region)
+  trajectory     configs[0]/[1]: KITTI devkit t_err / r_err and the reference's xz error (PlotOnMap.m:20) of
+                 the GPU poses against the ground truth, and against the CPU oracle run on the same frames
+  throughput_variant   the constant-shift stream of round 1 (synth.shift_stream), same timing
+  roofline       dominant kernel of the step (live CUDA-event timers inside the library)
+  match_gemm     configs[3]: tcgen05 match GEMM sweep 2048..65536 squared, integer / adversarial-tie /
+                 general-float inputs, sampled rows checked bit-exact against the oracle at every size
+  reloc          configs[4]: 131072 query rows per rank x 1M landmarks, row-sharded, all-gather of the
+                 16-byte records, 4096-hypothesis P3P; sampled rows checked against the oracle
+  e2e_dropin     the literal drop-in: the MEX gateways driven through the stand-in MATLAB host
+  e2e_from_png   PNG files -> poses (decode on host threads overlapped with the GPU)
+  cpu_baseline   the C oracle on ALL host cores over the first frames of the same sequence (rank 0, N=1)
 
 --impl reference times the reference's CPU implementation of the path.  MATLAB is not available
 offline, so this is the oracle port run with one process per host core.
@@ -25,7 +32,6 @@ offline, so this is the oracle port run with one process per host 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -56,9 +62,19 @@ def emit(line):
     out.flush()
 
 
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
 H, W = 376, 1241
 METRIC = "kitti_stereo_frames_per_s_end_to_end"
 UNIT = "frames/s"
+SEQ_SEED = 7
+# identical in both arms (the driver compares the arms' configs)
+CONFIG = dict(workload="VO.m loop body (VO.m:64-232) on 1241x376 stereo frames of a rendered street world along "
+                       "kitti/poses/00.txt through kitti/00/calib.txt P0/P1 (BASELINE.json configs[1]; KITTI images "
+                       "absent offline)",
+              rows=H, cols=W, halo_frames=1, sequence="synth.StreetWorld(seed=7), frames 0..n of kitti/poses/00.txt")
 
 
 def peaks():
@@ -70,57 +86,83 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, sampled in-process through NVML every 10 ms
+    (no nvidia-smi child process competing for the host cores)."""
+    BITS = dict(hw_slowdown=0x8, sw_power_cap=0x4, sw_thermal_slowdown=0x20, hw_thermal_slowdown=0x40)
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.mx, self.err = index, [], set(), None, None
+        self._stop = threading.Event()
+        self.t = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.replace(",", "").isdigit() else self.index
+            self.hd = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.hd, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:   # noqa: BLE001
+            self.err = str(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for k, nme in enumerate(names):
-                    if r[2 + k].lower().startswith("active"):
-                        reasons.add(nme)
-            except Exception:
-                pass
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.hd, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.hd))
+                for k, bit in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception as e:   # noqa: BLE001
+                self.err = str(e)
+                return
+            self._stop.wait(0.01)
+
+    def mark(self):
+        return len(self.sm)
+
+    def stop(self, lo=0, hi=None):
+        if self.t is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvml unavailable: %s" % self.err])
+        self._stop.set()
+        self.t.join()
+        sm = self.sm[lo:hi] or self.sm
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=self.mx, reasons=sorted(self.reasons),
+                    samples=len(sm), sampler="nvml in-process, 10 ms")
 
 
-def make_frames(n_batches, batch, seed):
-    """n_batches x (batch+1) consecutive synthetic stereo frames, as one pinned uint8 tensor pair."""
-    import torch
-    from vo_b200 import synth
-    n = batch + 1
-    left = torch.empty((n_batches, n, H, W), dtype=torch.uint8).pin_memory()
-    right = torch.empty((n_batches, n, H, W), dtype=torch.uint8).pin_memory()
-    for b in range(n_batches):
-        l, r = synth.shift_stream(n, seed=seed + 1000 * b, h=H, w=W)
-        left[b] = torch.from_numpy(l); right[b] = torch.from_numpy(r)
-    return left, right
+# ------------------------------------------------------------------------------------ frames
+def gt_poses(n):
+    d = np.load(os.path.join(ROOT, "tests", "golden", "kitti00_reference_data.npz"))
+    n = min(n, len(d["poses"]))
+    gt = np.tile(np.eye(4), (n, 1, 1))
+    gt[:, :3, :] = d["poses"][:n]
+    return gt
+
+
+def street_frames(n, rank=0, barrier=None):
+    """(left, right, gt) of the first n frames of the street sequence.  Rendered once per box (rank 0, all host
+    cores) and cached in the temp dir; the other ranks and the reference arm load the cache."""
+    import tempfile
+    gt = gt_poses(n)
+    n = len(gt)
+    path = os.path.join(tempfile.gettempdir(), f"vo_b200_street_s{SEQ_SEED}_n{n}_{H}x{W}.npy")
+    if rank == 0 and not os.path.exists(path):
+        from vo_b200 import synth
+        t0 = time.time()
+        left, right = synth.street_sequence(gt, seed=SEQ_SEED, h=H, w=W)
+        np.save(path + ".tmp.npy", np.stack([left, right]))
+        os.replace(path + ".tmp.npy", path)
+        log(f"rendered {n} street frames in {time.time() - t0:.1f} s")
+    if barrier is not None:
+        barrier()
+    a = np.load(path)
+    return a[0], a[1], gt
 
 
 # ------------------------------------------------------------------------------------ CPU legs
@@ -136,7 +178,7 @@ def _oracle_frame(args):
 
 
 def _oracle_pair(args):
-    """find_remaining_points + triangulate + P3P for one frame pair with the oracle."""
+    """find_remaining_points + triangulate + P3P for one frame pair with the oracle -> (status, A, K4)."""
     from oracle_ops import OracleOps
     from vo_b200 import vo, synth
     prev, cur, idx = args
@@ -144,125 +186,238 @@ def _oracle_pair(args):
     ld, lp, rd, rp, m = prev
     old = dict(l_desc=ld[m[:, 0]], r_desc=rd[m[:, 1]], l_pos=lp[m[:, 0]], r_pos=rp[m[:, 1]])
     c = dict(l_desc=cur[0], l_pos=cur[1], r_desc=cur[2], r_pos=cur[3])
-    c, o, _, _, _ = vo.find_remaining_points(ops, old, c)
+    c, o, _, _, ks = vo.find_remaining_points(ops, old, c)
     xyz = ops.triangulate(o["l_pos"], o["r_pos"], synth.KITTI_P0, synth.KITTI_P1)
     r = ops.estworldpose(c["l_pos"].astype(np.float64), xyz, synth.KITTI_K4, idx)
-    return r["status"]
+    return r["status"], r["A"], ks[3]
 
 
-def cpu_oracle_sample(n_frames=10, seed=77):
-    """Single-threaded oracle on n_frames consecutive frames (n_frames SIFT pairs + n_frames-1 poses)."""
-    from vo_b200 import synth
-    left, right = synth.shift_stream(n_frames, seed=seed, h=H, w=W)
+def _oracle_top2_chunk(args):
+    """Oracle best-2 of a few query rows against one column chunk of the landmark set."""
+    from oracle import oracle
+    f1, f2, off = args
+    j, s1, s2 = oracle.match_top2(f1, np.asarray(f2, dtype=np.float32))
+    return j.astype(np.int64) + off, s1, s2
+
+
+_POOL = None
+
+
+def pool():
+    """Worker processes for the oracle legs.  "spawn": the parent holds a CUDA context."""
+    global _POOL
+    if _POOL is None:
+        import multiprocessing as mp
+        _POOL = mp.get_context("spawn").Pool(os.cpu_count() or 1)
+    return _POOL
+
+
+def oracle_top2_rows(f1_rows, f2):
+    """oracle.match_top2(f1_rows, f2) with the columns of f2 spread over the worker pool.  The score of a pair
+    does not depend on the chunking, and the merge keeps the oracle's order (score, then lowest column)."""
+    n2 = len(f2)
+    nchunk = max(1, min(os.cpu_count() or 1, n2 // 4096))
+    edges = np.linspace(0, n2, nchunk + 1).astype(int)
+    parts = pool().map(_oracle_top2_chunk, [(f1_rows, f2[a:b], int(a)) for a, b in zip(edges[:-1], edges[1:])])
+    j = np.stack([p[0] for p in parts] * 2, axis=1)                       # candidate columns: each chunk's best twice
+    s = np.stack([p[1] for p in parts] + [p[2] for p in parts], axis=1)   # best of each chunk, then its runner-up
+    n = len(f1_rows)
+    j1 = np.zeros(n, dtype=np.uint32); s1 = np.zeros(n, dtype=np.float32); s2 = np.zeros(n, dtype=np.float32)
+    for i in range(n):
+        best = s[i, :nchunk]
+        k = int(np.argmin(best))                    # first minimum = lowest chunk = lowest column on ties
+        j1[i] = j[i, k]; s1[i] = best[k]
+        rest = np.concatenate([best[:k], best[k + 1:], s[i, nchunk + k: nchunk + k + 1]])
+        s2[i] = rest.min() if len(rest) else np.float32(np.inf)
+    return j1, s1, s2
+
+
+def oracle_keep(s1, s2, n2, match_threshold=1.0, max_ratio=0.6):
+    """The acceptance tests of oracle/match.c (vo_oracle_match) applied to best-2 scores, in float32."""
+    s1 = s1.astype(np.float32); s2 = s2.astype(np.float32)
+    keep = s1 <= np.float32(match_threshold) * np.float32(0.04)
+    if n2 >= 2:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = np.where(s2 < np.float32(1e-6), np.float32(1.0), s1 / s2).astype(np.float32)
+        keep &= ratio <= np.float32(max_ratio)
+    return keep
+
+
+def oracle_sequence(left, right, n):
+    """The oracle over frames 0..n-1 on all host cores: (rel [n,4,4], status [n], seconds, tracked)."""
     t0 = time.perf_counter()
-    fr = [_oracle_frame((left[i], right[i])) for i in range(n_frames)]
-    for i in range(1, n_frames):
-        _oracle_pair((fr[i - 1], fr[i], i))
+    fr = pool().map(_oracle_frame, [(left[i], right[i]) for i in range(n)], chunksize=1)
+    res = pool().map(_oracle_pair, [(fr[i - 1], fr[i], i) for i in range(1, n)], chunksize=1)
     dt = time.perf_counter() - t0
-    return dict(value=n_frames / dt, unit=UNIT, cores=1, kind="port",
-                sample=f"{n_frames} consecutive 1241x376 stereo frames ({2 * n_frames} SIFT, {n_frames} stereo "
-                       f"matches, {n_frames - 1} tracked pairs + P3P) in {dt:.1f} s, single thread, C oracle "
-                       "(MATLAB + Computer Vision Toolbox not installed: BASELINE.md)")
+    rel = np.tile(np.eye(4), (n, 1, 1))
+    status = np.zeros(n, dtype=np.int32)
+    for i, (st, A, _) in enumerate(res, start=1):
+        status[i] = st
+        if st == 0:
+            rel[i] = A
+    return rel, status, dt, [r[2] for r in res]
+
+
+def cv2_info(left, right):
+    """Informational: OpenCV's own SIFT / brute-force matcher on the same frames (SURVEY 8d "CPU path timed
+    beside it (3)") -- the closest stand-in for what the toolbox (believed to wrap OpenCV) costs."""
+    try:
+        import cv2
+    except Exception as e:   # noqa: BLE001
+        return dict(error=str(e))
+    out = dict(version=cv2.__version__)
+    cores = os.cpu_count() or 1
+    for nt, tag in ((1, "1_thread"), (cores, "all_threads")):
+        cv2.setNumThreads(nt)
+        s = cv2.SIFT_create()
+        t0 = time.perf_counter()
+        feats = [s.detectAndCompute(im, None) for im in (left[0], right[0], left[1], right[1])]
+        t_sift = (time.perf_counter() - t0) / 4
+        bf = cv2.BFMatcher(cv2.NORM_L2)
+        t0 = time.perf_counter()
+        bf.knnMatch(feats[0][1], feats[1][1], k=2)
+        t_match = time.perf_counter() - t0
+        # VO.m body: 2 SIFT + 5 matches (the 4 temporal ones are smaller: counted as 2 full ones)
+        out[tag] = dict(threads=nt, sift_ms_per_image=1e3 * t_sift, bf_knn_match_ms=1e3 * t_match,
+                        keypoints=len(feats[0][0]), est_frames_per_s=1.0 / (2 * t_sift + 3 * t_match))
+    cv2.setNumThreads(cores)
+    return out
+
+
+def trajectory_errors(rel, gt, n):
+    """KITTI devkit errors (Appendix A.5) and the reference's xz error (PlotOnMap.m:20) of chained poses."""
+    from vo_b200 import vo, kitti_eval
+    est = np.array([np.eye(4)] + vo.chain_poses(rel[1:n]))
+    est = gt[0] @ est
+    t, r, k = kitti_eval.kitti_errors(est, gt[:n])
+    xz = kitti_eval.xz_error(est, gt[:n])
+    return dict(frames=int(n), t_err_pct=100.0 * t, r_err_deg_per_m=float(np.degrees(r)), segments=int(k),
+                lengths_m=[L for L in kitti_eval.LENGTHS if L < kitti_eval._distances(gt[:n])[-1]],
+                xz_err_final_m=float(xz[-1]), xz_err_max_m=float(xz.max()))
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the oracle port on all host cores (one process per core), rank 0 only."""
+    """--impl reference: the oracle port on all host cores (one process per core), rank 0 only.  Every step
+    processes at least one frame per core, so the pool is fully subscribed."""
     if rank != 0:
         return
-    import multiprocessing as mp
-    from vo_b200 import synth
     cores = os.cpu_count() or 1
-    # frames per step: one per core (+1 halo frame); fewer when many steps are asked for, so that the whole
-    # run stays within a few minutes (a step of `cores` frames takes ~14 s of wall time on the GPU box's host)
-    n = max(2, min(cores, int(cores * 9 / max(args.steps + args.warmup, 1))))   # ~2 minutes for the whole run
-    left, right = synth.shift_stream(n + 1, seed=99, h=H, w=W)
-    ctxm = mp.get_context("fork")
-    with ctxm.Pool(cores) as pool:
-        def step():
-            fr = pool.map(_oracle_frame, [(left[i], right[i]) for i in range(n + 1)])
-            pool.map(_oracle_pair, [(fr[i - 1], fr[i], i) for i in range(1, n + 1)])
-        for _ in range(args.warmup):
-            step()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step()
-        dt = time.perf_counter() - t0
+    # frames per step: a multiple of the core count (incl. the halo frame) sized so that the whole run stays
+    # within a few minutes (one round of `cores` frames takes ~4.5 s of wall time)
+    rounds = max(1, int(150.0 / (4.5 * max(args.steps + args.warmup, 1))))
+    n = min(cores * rounds, 385) - 1
+    left, right, gt = street_frames(n + 1)
+    log(f"reference arm: {n} frames (+1 halo) per step on {cores} processes")
+
+    def step():
+        return oracle_sequence(left, right, n + 1)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rel, status, _, _ = step()
+    dt = time.perf_counter() - t0
     v = args.steps * n / dt
     line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak",
-                vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="VO.m loop body on synthetic 1241x376 stereo frames (BASELINE.json configs[1])",
-                            frames_per_step=n, note="reference = CPU oracle port; MATLAB not installed (BASELINE.md)"),
+                vs_baseline=None, dtype="f32 (SIFT, match) / f64 (triangulate, P3P)", data="synthetic", config=CONFIG,
+                frames_per_step=n, status_ok=int((status[1:] == 0).sum()),
+                note="reference = CPU oracle port (oracle/*.c), one process per core; MATLAB + Computer Vision Toolbox "
+                     "not installed (BASELINE.md)",
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
-                                  sample=f"{n} frames (+1 halo) per step, one process per core"),
+                                  sample=f"{n} frames (+1 halo) per step, one process per core, {cores} cores"),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
 
 
 # ------------------------------------------------------------------------------------ GPU legs
-def match_gemm_leg(ctx, torch, pk, sizes=(8192, 16384, 32768, 65536)):
-    """tcgen05 match GEMM alone (BASELINE.json config 4 sweep) on n x n x 128 SIFT-like integer descriptors
-    resident in HBM, half of the query rows being noisy copies of landmark rows (so matches exist).
-    Two consumers of the same kernel are timed: "match" = matchFeatures (vo_match_dev, default options:
-    the score bound MatchThreshold/MaxRatio seeds each row's key bound) and "top2" = exact best-2 of every
-    row (vo_match_top2_dev).  time = the GEMM + top-3 kernel (CUDA events inside the library)."""
+def match_gemm_leg(ctx, torch, pk, check=True):
+    """BASELINE.json configs[3]: n x n x 128 for n = 2048..65536 on descriptors resident in HBM.
+    Three input kinds (synth.descriptor_sets): "integer" at every size, "ties" and "float" at three sizes.
+    Two consumers of the same kernel are timed: "match" = matchFeatures (vo_match_dev, default options) and
+    "top2" = exact best-2 of every row (vo_match_top2_dev).  time = the GEMM + top-k kernel (CUDA events inside
+    the library).  Parity: 256 sampled query rows of each run are compared bit for bit (index, score bits, kept
+    pairs) with the oracle."""
     import ctypes as C
-    from vo_b200 import _lib
-    from conftest import correlated_pair
+    from vo_b200 import _lib, synth
     L = _lib.lib()
     stream = torch.cuda.ExternalStream(ctx.stream)
     out = []
-    for n in sizes:
-        a, b = correlated_pair(n, n, seed=1234)
-        f1 = torch.from_numpy(a).cuda(); f2 = torch.from_numpy(b).cuda()
-        j1 = torch.empty(n, dtype=torch.int32, device="cuda"); s1 = torch.empty(n, device="cuda"); s2 = torch.empty(n, device="cuda")
-        i2 = torch.empty(n, dtype=torch.int32, device="cuda"); npairs = torch.zeros(1, dtype=torch.int32, device="cuda")
+    plan = [("integer", (2048, 4096, 8192, 16384, 32768, 65536)), ("ties", (2048, 16384, 65536)),
+            ("float", (2048, 16384, 32768))]
+    all_ok = True
+    for kind, sizes in plan:
+        for n in sizes:
+            a, b = synth.descriptor_sets(kind, n, n, seed=1234)
+            f1 = torch.from_numpy(a).cuda(); f2 = torch.from_numpy(b).cuda()
+            j1 = torch.empty(n, dtype=torch.int32, device="cuda"); s1 = torch.empty(n, device="cuda"); s2 = torch.empty(n, device="cuda")
+            i1 = torch.empty(n, dtype=torch.int32, device="cuda"); i2 = torch.empty(n, dtype=torch.int32, device="cuda")
+            mt = torch.empty(n, device="cuda"); npairs = torch.zeros(1, dtype=torch.int32, device="cuda")
 
-        def call_top2():
-            _lib.check(L.vo_match_top2_dev(ctx.handle, C.c_void_p(f1.data_ptr()), n, C.c_void_p(f2.data_ptr()), n, 128,
-                                           C.c_void_p(j1.data_ptr()), C.c_void_p(s1.data_ptr()), C.c_void_p(s2.data_ptr()),
-                                           C.c_void_p(ctx.stream)))
+            def call_top2():
+                _lib.check(L.vo_match_top2_dev(ctx.handle, C.c_void_p(f1.data_ptr()), n, C.c_void_p(f2.data_ptr()), n, 128,
+                                               C.c_void_p(j1.data_ptr()), C.c_void_p(s1.data_ptr()), C.c_void_p(s2.data_ptr()),
+                                               C.c_void_p(ctx.stream)))
 
-        def call_match():
-            _lib.check(L.vo_match_dev(ctx.handle, C.c_void_p(f1.data_ptr()), n, C.c_void_p(f2.data_ptr()), n, 128, None,
-                                      C.c_void_p(j1.data_ptr()), C.c_void_p(i2.data_ptr()), C.c_void_p(s1.data_ptr()),
-                                      C.c_void_p(npairs.data_ptr()), C.c_void_p(ctx.stream)))
-        rec = dict(n1=n, n2=n, dim=128)
-        for mode, call in (("match", call_match), ("top2", call_top2)):
-            torch.cuda.synchronize()
-            for _ in range(3):
-                call()
-            ctx.sync()
-            ctx.profile_enable(True)
-            reps = 10
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(reps):
-                call()
-            e1.record(stream)
-            ctx.sync()
-            prof = ctx.profile()
-            ctx.profile_enable(False)
-            g = prof["match_gemm_topk"]
-            flops = 2.0 * n * n * 128
-            t_kernel = g["ms"] / g["launches"] * 1e-3
-            tf = flops / t_kernel / 1e12
-            d = dict(kernel_ms=1e3 * t_kernel, call_ms=e0.elapsed_time(e1) / reps, tflops=tf,
-                     frac_of_burst_peak=tf / pk["tf_burst"], frac_of_sustained_peak=tf / pk["tf_sust"],
-                     frac_of_2x_burst_peak=tf / (2 * pk["tf_burst"]))
-            if mode == "match":
-                d["pairs"] = int(npairs.item())
-                rec.update(d)
-            rec[mode] = d
-        out.append(rec)
-        del f1, f2
-    best = max(out, key=lambda d: d["tflops"])
-    head = [d for d in out if d["n1"] == 32768][0] if any(d["n1"] == 32768 for d in out) else best
-    return dict(head, sweep=out, best_tflops=best["tflops"], best_frac_of_burst_peak=best["frac_of_burst_peak"],
-                peak_tflops_burst=pk["tf_burst"], peak_tflops_sustained=pk["tf_sust"], peak_source=pk["src"],
-                path="u8 x u8 -> s32 tcgen05.mma.kind::i8 (exact integer dot, K = 128), fused integer-prefilter top-3 "
-                     "epilogue, no C written; ops counted as 2*N1*N2*128; peaks are the measured bf16 cuBLAS figures "
-                     "(the int8 pipe's nominal peak is 2x bf16: frac_of_2x_burst_peak)")
+            def call_match():
+                _lib.check(L.vo_match_dev(ctx.handle, C.c_void_p(f1.data_ptr()), n, C.c_void_p(f2.data_ptr()), n, 128, None,
+                                          C.c_void_p(i1.data_ptr()), C.c_void_p(i2.data_ptr()), C.c_void_p(mt.data_ptr()),
+                                          C.c_void_p(npairs.data_ptr()), C.c_void_p(ctx.stream)))
+            rec = dict(kind=kind, n1=n, n2=n, dim=128)
+            for mode, call in (("match", call_match), ("top2", call_top2)):
+                torch.cuda.synchronize()
+                for _ in range(3):
+                    call()
+                ctx.sync()
+                ctx.profile_enable(True)
+                reps = 10
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(reps):
+                    call()
+                e1.record(stream)
+                ctx.sync()
+                prof = ctx.profile()
+                ctx.profile_enable(False)
+                g = prof["match_gemm_topk"]
+                flops = 2.0 * n * n * 128
+                t_kernel = g["ms"] / g["launches"] * 1e-3
+                tf = flops / t_kernel / 1e12
+                t_call = e0.elapsed_time(e1) / reps
+                d = dict(kernel_ms=1e3 * t_kernel, call_ms=t_call, tflops=tf, call_tflops=flops / (t_call * 1e-3) / 1e12,
+                         frac_of_burst_peak=tf / pk["tf_burst"], frac_of_sustained_peak=tf / pk["tf_sust"],
+                         frac_of_2x_burst_peak=tf / (2 * pk["tf_burst"]))
+                if mode == "match":
+                    d["pairs"] = int(npairs.item())
+                    rec.update(d)
+                rec[mode] = d
+            if check:
+                rows = np.sort(np.random.default_rng(n).permutation(n)[:256])
+                oj, os1, os2 = oracle_top2_rows(a[rows], b)
+                gj, gs1, gs2 = j1.cpu().numpy().view(np.uint32)[rows], s1.cpu().numpy()[rows], s2.cpu().numpy()[rows]
+                top2_ok = bool(np.array_equal(gj, oj) and np.array_equal(gs1.view(np.uint32), os1.view(np.uint32))
+                               and np.array_equal(gs2.view(np.uint32), os2.view(np.uint32)))
+                keep = oracle_keep(os1, os2, n)
+                p = int(npairs.item())
+                gi1 = i1.cpu().numpy().view(np.uint32)[:p]; gi2 = i2.cpu().numpy().view(np.uint32)[:p]; gm = mt.cpu().numpy()[:p]
+                sel = np.isin(gi1, rows)
+                match_ok = bool(np.array_equal(gi1[sel], rows[keep].astype(np.uint32)) and np.array_equal(gi2[sel], oj[keep])
+                                and np.array_equal(gm[sel].view(np.uint32), os1[keep].view(np.uint32)))
+                rec["parity"] = dict(rows_checked=len(rows), top2_bit_exact=top2_ok, match_bit_exact=match_ok,
+                                     kept_in_sample=int(keep.sum()))
+                all_ok = all_ok and top2_ok and match_ok
+            out.append(rec)
+            del f1, f2
+    ints = [d for d in out if d["kind"] == "integer"]
+    best = max(ints, key=lambda d: d["tflops"])
+    head = [d for d in ints if d["n1"] == 32768][0]
+    return dict(head, sweep=out, parity_all_bit_exact=all_ok if check else None, best_tflops=best["tflops"],
+                best_frac_of_burst_peak=best["frac_of_burst_peak"], peak_tflops_burst=pk["tf_burst"],
+                peak_tflops_sustained=pk["tf_sust"], peak_source=pk["src"],
+                path="integer / ties: u8 x u8 -> s32 tcgen05.mma.kind::i8 (exact integer dot, K = 128), fused integer-prefilter "
+                     "top-3 epilogue, no C written; float: split-bf16 kind::f16 GEMM + exact FP32 re-rank; ops counted as "
+                     "2*N1*N2*128; peaks are the measured bf16 cuBLAS figures (the int8 pipe's nominal peak is 2x bf16: "
+                     "frac_of_2x_burst_peak)")
 
 
 def run_ours(args, rank, world, local_rank):
@@ -284,20 +439,7 @@ def run_ours(args, rank, world, local_rank):
     ctx = ctxs[0]
     pk = peaks()
     B = args.batch
-    n_batches = min(args.steps + args.warmup, 4)
-    left, right = make_frames(n_batches, B, seed=20260 + 7919 * rank)
-    dleft, dright = left.cuda(), right.cuda()
-    streams = [torch.cuda.ExternalStream(c.stream) for c in ctxs]
     P0, P1 = synth.KITTI_P0, synth.KITTI_P1
-
-    def step_dev(i, c):
-        b = i % n_batches
-        return vo.run_frames(None, None, P0, P1, seed=1, first_frame=i * B, ctx=c,
-                             device_ptrs=(dleft[b].data_ptr(), dright[b].data_ptr(), B + 1, H, W))
-
-    def step_host(i, c):
-        b = i % n_batches
-        return vo.run_frames(left[b].numpy(), right[b].numpy(), P0, P1, seed=1, first_frame=i * B, ctx=c)
 
     def barrier():
         torch.cuda.synchronize()
@@ -305,7 +447,35 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, profile, use):
+    n_batches = max(1, min(12, 399 // B))
+    n_seq = n_batches * B + 1
+    sleft, sright, gt = street_frames(n_seq, rank, barrier if dist is not None else None)
+
+    def batches_of(left, right, nb):
+        """[nb, B+1, H, W] pinned views: batch b = frames b*B .. b*B+B (one-frame halo)."""
+        L = torch.empty((nb, B + 1, H, W), dtype=torch.uint8).pin_memory()
+        R = torch.empty((nb, B + 1, H, W), dtype=torch.uint8).pin_memory()
+        for b in range(nb):
+            L[b] = torch.from_numpy(left[b * B: b * B + B + 1]); R[b] = torch.from_numpy(right[b * B: b * B + B + 1])
+        return L, R
+    left, right = batches_of(sleft, sright, n_batches)
+    dleft, dright = left.cuda(), right.cuda()
+    streams = [torch.cuda.ExternalStream(c.stream) for c in ctxs]
+    rot = rank % n_batches      # ranks start at different batches of the sequence
+
+    def make_steps(left, right, dleft, dright, nb):
+        def step_dev(i, c):
+            b = (i + rot) % nb
+            return vo.run_frames(None, None, P0, P1, seed=1, first_frame=b * B, ctx=c,
+                                 device_ptrs=(dleft[b].data_ptr(), dright[b].data_ptr(), B + 1, H, W))
+
+        def step_host(i, c):
+            b = (i + rot) % nb
+            return vo.run_frames(left[b].numpy(), right[b].numpy(), P0, P1, seed=1, first_frame=b * B, ctx=c)
+        return step_dev, step_host
+    step_dev, step_host = make_steps(left, right, dleft, dright, n_batches)
+
+    def timed(step_fn, profile, use, sampler=None):
         """Exactly args.steps steps after args.warmup warm-up steps, spread round-robin over the first
         `use` contexts; device time from CUDA events on the launching streams, max over streams and ranks."""
         for i in range(args.warmup * use):
@@ -316,6 +486,8 @@ def run_ours(args, rank, world, local_rank):
         launches0 = sum(c.kernel_launches() for c in ctxs)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = [torch.cuda.Event(enable_timing=True) for _ in range(use)]
+        cpu0 = time.process_time(); wall0 = time.perf_counter()
+        m0 = sampler.mark() if sampler else 0
         e0.record(streams[0])
         results = [None] * args.steps
 
@@ -337,30 +509,73 @@ def run_ours(args, rank, world, local_rank):
             [t.start() for t in th]
             [t.join() for t in th]
         barrier()
+        m1 = sampler.mark() if sampler else 0
+        host = dict(cpu_s=time.process_time() - cpu0, wall_s=time.perf_counter() - wall0)
         ms = max(e0.elapsed_time(e) for e in e1)
         prof = ctx.profile() if profile else None
         if profile:
             ctx.profile_enable(False)
+        per_rank = [ms]
         if dist is not None:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            t = torch.tensor([ms, host["cpu_s"]], device="cuda", dtype=torch.float64)
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            per_rank = [float(x[0]) for x in allt]
+            host["cpu_s_per_rank"] = [round(float(x[1]), 4) for x in allt]
+            ms = max(per_rank)
         counts = [r[2] for r in results]
-        return ms, prof, sum(c.kernel_launches() for c in ctxs) - launches0, counts, results[-1][:2]
+        return dict(ms=ms, prof=prof, launches=sum(c.kernel_launches() for c in ctxs) - launches0, counts=counts,
+                    per_rank_ms=per_rank, host=host, marks=(m0, m1))
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_dev, _, launches, counts, last = timed(step_dev, profile=False, use=n_ctx)
-    clocks = sampler.stop()
-    ms_host, _, _, _, _ = timed(step_host, profile=False, use=n_ctx)
+    t_dev = timed(step_dev, profile=False, use=n_ctx, sampler=sampler)
+    clocks = sampler.stop(*t_dev["marks"])
+    t_host = timed(step_host, profile=False, use=n_ctx)
     # roofline pass: the same steps, one batch at a time on one stream, with the library's per-stage CUDA
     # events switched on (they cost a few % of a step, and overlapping batches would smear the stages)
-    ms_prof, prof, _, counts, _ = timed(step_dev, profile=True, use=1)
+    t_prof = timed(step_dev, profile=True, use=1)
+    prof, counts = t_prof["prof"], t_prof["counts"]
     frames = args.steps * B * world
-    value = frames / (ms_dev * 1e-3)
-    e2e = frames / (ms_host * 1e-3)
+    value = frames / (t_dev["ms"] * 1e-3)
+    e2e = frames / (t_host["ms"] * 1e-3)
+
+    # throughput variant of round 1: constant-shift stream (every keypoint tracks, ~100 % inliers), same timing
+    tv = None
+    if not args.quick:
+        nb2 = 4
+        l2 = np.empty((nb2 * B + 1, H, W), dtype=np.uint8); r2 = np.empty_like(l2)
+        for b in range(nb2):
+            l, r = synth.shift_stream(B + 1, seed=20260 + 7919 * rank + 1000 * b, h=H, w=W)
+            l2[b * B: b * B + B + 1] = l; r2[b * B: b * B + B + 1] = r
+        left2, right2 = batches_of(l2, r2, nb2)
+        dl2, dr2 = left2.cuda(), right2.cuda()
+        sd2, sh2 = make_steps(left2, right2, dl2, dr2, nb2)
+        a = timed(sd2, profile=False, use=n_ctx)
+        b_ = timed(sh2, profile=False, use=n_ctx)
+        cnt2 = np.concatenate(a["counts"], axis=0).astype(np.float64)
+        tv = dict(workload="synth.shift_stream: one texture, constant 12 px disparity, 3 px/frame shift (round-1 headline)",
+                  value=frames / (a["ms"] * 1e-3), e2e=frames / (b_["ms"] * 1e-3), unit=UNIT, ms_per_step=a["ms"] / args.steps,
+                  keypoints_per_image=float(cnt2[:, :2].mean()), tracked_per_frame=float(cnt2[:, 6].mean()))
+        del dl2, dr2, left2, right2
+
+    # trajectory of the whole rendered sequence through the batched loop (rank 0 reports it)
+    rel_all = np.tile(np.eye(4), (n_seq, 1, 1)); status_all = np.zeros(n_seq, dtype=np.int32)
+    cnt_all = np.zeros((n_seq, 8), dtype=np.int32)
+    for b in range(n_batches):
+        r_, s_, c_ = vo.run_frames(None, None, P0, P1, seed=1, first_frame=b * B, ctx=ctx,
+                                   device_ptrs=(dleft[b].data_ptr(), dright[b].data_ptr(), B + 1, H, W))
+        rel_all[b * B + 1: b * B + B + 1] = r_[1:]; status_all[b * B + 1: b * B + B + 1] = s_[1:]
+        cnt_all[b * B + 1: b * B + B + 1] = c_[1:]
     if rank != 0:
+        if dist is not None:
+            reloc_leg(args, torch, dist, ctx, rank, world, pk)
+            dist.destroy_process_group()
         return
+    trajectory = dict(gpu=trajectory_errors(rel_all, gt, n_seq), status_ok=int((status_all[1:] == 0).sum()),
+                      tracked_min=int(cnt_all[1:, 6].min()), tracked_median=float(np.median(cnt_all[1:, 6])),
+                      inliers_median=float(np.median(cnt_all[1:, 7])))
+
     # dominant kernel of the step and its roofline.  Launches of the same kernel are merged (the TMA blur
     # kernel runs once per octave and layer), so "dominant" is by kernel, not by launch site.
     cnt = np.concatenate(counts, axis=0).astype(np.float64)
@@ -381,9 +596,11 @@ def run_ours(args, rank, world, local_rank):
     if "match_gemm_topk" in kern:
         kern["match_gemm_topk"]["flops"] = 2.0 * mm * 128
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_image", {})
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_image", {})
+            break
 
     def roof(name):
         d = kern[name]
@@ -404,42 +621,137 @@ def run_ours(args, rank, world, local_rank):
         return r
     dom = max(kern, key=lambda k: kern[k]["ms"])
     roofline = roof(dom)
-    if dom == "sift_descriptor":
-        roofline["note"] = ("algorithmic bytes per SURVEY 8(d): (2r+1)^2*4 B read + 512 B written per keypoint, measured on the "
-                            "device; the patches are L1/L2 resident, the kernel is issue-bound (ncu: profiles/)")
     roofline_all = [roof(k) for k in sorted(kern, key=lambda k: -kern[k]["ms"])]
+    # the pyramid stage as a whole against its COMPULSORY traffic (109.95 MB per 1241x376 image)
+    pyr = [k for k in kern if k.startswith(("sift_base", "sift_blur", "sift_downsample", "sift_extrema", "sift_pyramid"))]
+    pyr_ms = sum(kern[k]["ms"] for k in pyr)
+    if pyr_ms > 0:
+        S = sum((2 * H >> o) * (2 * W >> o) for o in range(9))
+        comp = (H * W + 11 * S * 4) * (B + 1) * 2 * args.steps
+        pyramid = dict(kernels=sorted(pyr), ms_per_step=pyr_ms / args.steps, compulsory_bytes_per_image=H * W + 11 * S * 4,
+                       achieved_gbs=comp / (pyr_ms * 1e-3) / 1e9, frac_of_hbm_peak=comp / (pyr_ms * 1e-3) / 1e9 / pk["hbm"])
+    else:
+        pyramid = None
     gemm_ms = prof.get("match_gemm_topk", dict(ms=0))["ms"]
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms_dev / args.steps, ms_per_step_profiled_serial=ms_prof / args.steps,
+                ms_per_step=t_dev["ms"] / args.steps, ms_per_step_profiled_serial=t_prof["ms"] / args.steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32 (SIFT) / u8->s32 exact-integer tensor-core GEMM (match) / f64 (triangulate, P3P)",
-                data="synthetic",
-                config=dict(workload="VO.m loop body on synthetic 1241x376 stereo frames (BASELINE.json configs[1]: "
-                                     "kitti/00-shaped stream; KITTI images absent offline)",
-                            frames_per_step_per_gpu=B, halo_frames=1, rows=H, cols=W,
-                            l2="per-step working set ~%.1f GB of pyramids >> 126 MB L2; %d distinct input batches"
-                               % ((B + 1) * 2 * 110e6 / 1e9, n_batches),
-                            batches_in_flight=n_ctx,
-                            timing="value / e2e: exactly `steps` steps with `batches_in_flight` batches in flight (one stream "
-                                   "and host thread per batch slot), CUDA events on the launching streams; roofline / "
-                                   "stage_share / ms_per_step_profiled_serial: the same steps run one batch at a time with "
-                                   "per-stage CUDA events on",
-                            parallelism=f"frame-sharded x{world}, no data-path collective"),
+                data="synthetic", config=CONFIG,
+                run=dict(frames_per_step_per_gpu=B, distinct_batches=n_batches, sequence_frames=n_seq,
+                         l2="per-step working set ~%.1f GB of pyramids >> 126 MB L2; %d distinct input batches"
+                            % ((B + 1) * 2 * 110e6 / 1e9, n_batches),
+                         batches_in_flight=n_ctx,
+                         timing="value / e2e: exactly `steps` steps with `batches_in_flight` batches in flight (one stream "
+                                "and host thread per batch slot), CUDA events on the launching streams, max over ranks; "
+                                "roofline / stage_share / ms_per_step_profiled_serial: the same steps run one batch at a time "
+                                "with per-stage CUDA events on",
+                         parallelism=f"frame-sharded x{world}, no data-path collective"),
                 e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=int((B + 1) * 2 * H * W),
-                         d2h_bytes_per_step=int((B + 1) * (16 * 8 + 4 + 4 * 4 + 5 * 4 + 2 * 16)), ms_per_step=ms_host / args.steps),
-                gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_all=roofline_all, stage_share=shares,
+                         d2h_bytes_per_step=int((B + 1) * (16 * 8 + 4 + 8 * 4)), ms_per_step=t_host["ms"] / args.steps),
+                gpu_launches=int(t_dev["launches"]), clocks=clocks, roofline=roofline, roofline_all=roofline_all,
+                pyramid_stage=pyramid, stage_share=shares,
+                per_rank_ms=dict(value=[round(x, 3) for x in t_dev["per_rank_ms"]], e2e=[round(x, 3) for x in t_host["per_rank_ms"]]),
+                host=dict(value=t_dev["host"], e2e=t_host["host"], cores=os.cpu_count()),
                 keypoints_per_image=float(cnt[:, :2].mean()), tracked_per_frame=float(cnt[:, 6].mean()),
-                match_gflop_per_step=2.0 * mm * 128 / 1e9 / args.steps, match_gemm_ms_per_step=gemm_ms / args.steps)
-    if world == 1 and not args.no_match_leg:
+                match_gflop_per_step=2.0 * mm * 128 / 1e9 / args.steps, match_gemm_ms_per_step=gemm_ms / args.steps,
+                trajectory=trajectory, throughput_variant=tv)
+    side = []
+    if world == 1 and not args.quick:
+        side += [("match_gemm", lambda: match_gemm_leg(ctx, torch, pk, check=not args.no_cpu)),
+                 ("e2e_dropin", lambda: dropin_leg(sleft, sright, gt)),
+                 ("e2e_from_png", lambda: png_leg(sleft, sright, B))]
+    if not args.quick:
+        side += [("reloc", lambda: reloc_leg(args, torch, dist, ctx, rank, world, pk))]
+    if world == 1 and not args.no_cpu and not args.quick:
+        side += [("cpu_baseline", lambda: cpu_leg(sleft, sright, gt, rel_all, status_all, trajectory))]
+    for name, fn in side:
+        t0 = time.time()
         try:
-            line["match_gemm"] = match_gemm_leg(ctx, torch, pk)
-        except Exception as e:  # keep the headline line even if the side leg fails
-            line["match_gemm"] = dict(error=str(e))
-        if not args.no_cpu:
-            line["cpu_baseline"] = cpu_oracle_sample()
+            line[name] = fn()
+        except Exception as e:  # keep the headline line even if a side leg fails  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            line[name] = dict(error=f"{type(e).__name__}: {e}")
+        log(f"{name}: {time.time() - t0:.1f} s")
+    pz = [line["trajectory"].get("parity_vs_oracle"), (line.get("match_gemm") or {}).get("parity_all_bit_exact"),
+          (line.get("reloc") or {}).get("parity_rows_bit_exact"), (line.get("e2e_dropin") or {}).get("equals_vo_frames")]
+    line["parity"] = dict(trajectory_vs_oracle=pz[0], match_sweep_bit_exact=pz[1], reloc_rows_bit_exact=pz[2], dropin_equals_batched=pz[3])
     emit(line)
+    if _POOL is not None:
+        _POOL.terminate()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def cpu_leg(sleft, sright, gt, rel_gpu, status_gpu, trajectory):
+    """The oracle on every host core over the first frames of the sequence: cpu_baseline, and the oracle's
+    trajectory next to the GPU's on the same frames (north star: t_err / r_err within 2 %)."""
+    cores = os.cpu_count() or 1
+    n = min(len(sleft), 225)
+    rel_o, status_o, dt, tracked = oracle_sequence(sleft, sright, n)
+    to = trajectory_errors(rel_o, gt, n)
+    tg = trajectory_errors(rel_gpu, gt, n)
+    dmax = float(np.abs(rel_o[:n] - rel_gpu[:n]).max())
+    same_status = bool(np.array_equal(status_o[:n], status_gpu[:n]))
+    rt = abs(tg["t_err_pct"] - to["t_err_pct"]) / max(to["t_err_pct"], 1e-12)
+    rr = abs(tg["r_err_deg_per_m"] - to["r_err_deg_per_m"]) / max(to["r_err_deg_per_m"], 1e-12)
+    trajectory.update(oracle=to, gpu_on_oracle_frames=tg, rel_pose_max_abs_diff=dmax, status_equal=same_status,
+                      t_err_rel_diff=rt, r_err_rel_diff=rr, parity_vs_oracle=bool(rt <= 0.02 and rr <= 0.02 and same_status))
+    out = dict(value=(n - 1) / dt, unit=UNIT, cores=cores, kind="port",
+               sample=f"frames 0..{n - 1} of the same sequence ({2 * n} SIFT, {n} stereo matches, {n - 1} tracked pairs + P3P) "
+                      f"in {dt:.1f} s on {cores} processes (one per core), C oracle (MATLAB + Computer Vision Toolbox not "
+                      "installed: BASELINE.md)",
+               per_core=(n - 1) / dt / cores, tracked_median=float(np.median(tracked)))
+    out["cv2"] = cv2_info(sleft, sright)
+    return out
+
+
+def dropin_leg(sleft, sright, gt):
+    """The literal drop-in: MATLAB-side calls through the .mexa64 gateways, driven by the stand-in
+    MATLAB host (csrc/mex/mexshim.cpp).  Two forms: the six-call loop of VO.m (one gateway call per toolbox call),
+    and the batched gateway vo_frames_mex (image stacks in, poses out)."""
+    from vo_b200 import mexhost
+    return mexhost.bench_dropin(sleft, sright, n_percall=24, n_batched=129, batch=32)
+
+
+def png_leg(sleft, sright, B):
+    """PNG files -> poses: the frames are written as 8-bit gray PNGs, then io.run_sequence decodes batch k+1 on
+    host threads while vo_frames runs batch k."""
+    import tempfile
+    import cv2
+    from vo_b200 import io, synth, vo
+    n = min(len(sleft), 4 * B + 1)
+    d = tempfile.mkdtemp(prefix="vo_b200_png_")
+    lf, rf = [], []
+    nbytes = 0
+    for i in range(n):
+        for name, arr, lst in (("image_0", sleft, lf), ("image_1", sright, rf)):
+            os.makedirs(os.path.join(d, name), exist_ok=True)
+            p = os.path.join(d, name, f"{i:06d}.png")
+            cv2.imwrite(p, arr[i]); lst.append(p); nbytes += os.path.getsize(p)
+    try:
+        io.run_sequence(lf[:B + 1], rf[:B + 1], synth.KITTI_P0, synth.KITTI_P1, batch=B, seed=1)       # warm-up
+        t0 = time.perf_counter()
+        rel, status, counts = io.run_sequence(lf, rf, synth.KITTI_P0, synth.KITTI_P1, batch=B, seed=1)
+        dt = time.perf_counter() - t0
+        ref = vo.run_frames(sleft[:B + 1], sright[:B + 1], synth.KITTI_P0, synth.KITTI_P1, seed=1)
+        same = bool(np.array_equal(rel[:B + 1], ref[0]))
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
+    return dict(value=(n - 1) / dt, unit=UNIT, frames=n - 1, png_bytes_per_frame=nbytes / n, decode_threads=os.cpu_count(),
+                equals_vo_frames=same, note="wall clock; files in the page cache; decode of batch k+1 overlaps vo_frames of batch k")
+
+
+def reloc_leg(args, torch, dist, ctx, rank, world, pk):
+    """BASELINE.json configs[4] (every rank calls this)."""
+    from vo_b200 import reloc
+    r = reloc.run(ctx, rank, world, dist, queries_per_rank=131072, landmarks=1048576, hyps=4096, reps=3,
+                  oracle_rows=None if args.no_cpu else oracle_top2_rows, oracle_keep=oracle_keep)
+    if r is not None:
+        r["frac_of_2x_burst_peak_per_gpu"] = r["aggregate_tops_gemm"] / world / (2 * pk["tf_burst"])
+    return r
 
 
 def main():
@@ -450,8 +762,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="new frames per step per GPU")
     ap.add_argument("--inflight", type=int, default=3, help="batches kept in flight per GPU (contexts / streams / host threads)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-match-leg", action="store_true", help="skip the stand-alone match GEMM sweep (used for the ncu launch list)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip every oracle leg (cpu_baseline, parity checks)")
+    ap.add_argument("--quick", action="store_true", help="headline + trajectory only (used for the ncu launch list)")
     args = ap.parse_args()
     _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
@@ -459,6 +771,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        if _POOL is not None:
+            _POOL.terminate()
         return
     if args.warmup < 3:
         args.warmup = 3

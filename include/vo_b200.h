@@ -92,6 +92,14 @@ int vo_sift_batch(vo_ctx* ctx, const uint8_t* imgs, int n_img, int rows, int col
                   const vo_sift_opts* opts, int capacity, vo_keypoint* kps, float* desc,
                   int* n_out);
 
+/* Same for a stack of n_img images of identical size held as ONE array: col_major = 1 is MATLAB's H x W x N
+ * uint8 array (element (r,c,k) at imgs[k*rows*cols + c*rows + r]), col_major = 0 equals vo_sift_batch.
+ * desc_col_major = 1: image b's descriptors are returned as MATLAB holds an M x 128 single matrix (element
+ * (i,k) at desc[b*capacity*128 + k*M + i], M = min(n_out[b], capacity)); the transpose runs on the device. */
+int vo_sift_stack(vo_ctx* ctx, const uint8_t* imgs, int n_img, int rows, int cols, int col_major,
+                  const vo_sift_opts* opts, int capacity, vo_keypoint* kps, float* desc,
+                  int desc_col_major, int* n_out);
+
 /* ----------------------------------------------------------------------------------- match */
 typedef struct {
   float match_threshold; /* MATLAB MatchThreshold in percent; <= 0 -> 1.0 (SSD <= 0.04)      */
@@ -188,6 +196,8 @@ typedef struct {
   int max_keypoints;   /* per-image capacity; <= 0 -> 8192 */
   int first_frame;     /* absolute index of frame 0 of this batch: keys the MSAC random stream so a
                           frame gets the same samples however the sequence is cut into batches */
+  int col_major;       /* 1: every image is MATLAB-ordered (element (r,c) at img[c*rows + r], i.e. an
+                          H x W x N uint8 array as MATLAB holds it); transposed on the device        */
 } vo_frames_opts;
 
 /* One pass of the VO.m loop body over n_frames consecutive stereo frames held in host memory

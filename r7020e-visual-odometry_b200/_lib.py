@@ -38,13 +38,13 @@ class P3POpts(C.Structure):
 
 class FramesOpts(C.Structure):
     _fields_ = [("sift", SiftOpts), ("match", MatchOpts), ("p3p", P3POpts),
-                ("max_keypoints", C.c_int), ("first_frame", C.c_int)]
+                ("max_keypoints", C.c_int), ("first_frame", C.c_int), ("col_major", C.c_int)]
 
 
 # every symbol include/vo_b200.h declares (tests check that the .so exports each one)
 EXPORTS = [
     "vo_version", "vo_last_error", "vo_ctx_create", "vo_ctx_destroy", "vo_ctx_sync",
-    "vo_ctx_stream", "vo_profile_enable", "vo_kernel_launches", "vo_profile_count", "vo_profile_get", "vo_frames_dev", "vo_sift", "vo_sift_batch", "vo_match", "vo_match_top2", "vo_match_dev",
+    "vo_ctx_stream", "vo_profile_enable", "vo_kernel_launches", "vo_profile_count", "vo_profile_get", "vo_frames_dev", "vo_sift", "vo_sift_batch", "vo_sift_stack", "vo_match", "vo_match_top2", "vo_match_dev",
     "vo_match_top2_dev", "vo_match_best2_dev", "vo_match_stats", "vo_match_debug_gemm", "vo_triangulate", "vo_p3p",
     "vo_frames", "vo_png_info", "vo_png_decode_gray8", "vo_png_read_batch", "vo_inflate_zlib",
 ]

@@ -24,6 +24,8 @@ typedef enum { mxREAL = 0, mxCOMPLEX } mxComplexity;
 size_t mxGetM(const mxArray* a);
 size_t mxGetN(const mxArray* a);
 size_t mxGetNumberOfElements(const mxArray* a);
+mwSize mxGetNumberOfDimensions(const mxArray* a);
+const mwSize* mxGetDimensions(const mxArray* a);
 void* mxGetData(const mxArray* a);
 double* mxGetPr(const mxArray* a);
 double mxGetScalar(const mxArray* a);
@@ -32,6 +34,7 @@ int mxIsChar(const mxArray* a);
 int mxIsEmpty(const mxArray* a);
 int mxGetString(const mxArray* a, char* buf, mwSize buflen);
 mxArray* mxCreateNumericMatrix(mwSize m, mwSize n, mxClassID cls, mxComplexity c);
+mxArray* mxCreateNumericArray(mwSize ndim, const mwSize* dims, mxClassID cls, mxComplexity c);
 mxArray* mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity c);
 mxArray* mxCreateLogicalMatrix(mwSize m, mwSize n);
 mxArray* mxCreateString(const char* s);

@@ -32,6 +32,19 @@ static int vo_mex_opt(int nrhs, const mxArray* prhs[], int first, const char* na
   }
   return 0;
 }
+// an integer option that may exceed 2^53 (the RNG seed): uint64 / int64 scalars are read exactly
+static int vo_mex_opt_u64(int nrhs, const mxArray* prhs[], int first, const char* name, uint64_t* value) {
+  for (int i = first; i + 1 < nrhs; i += 2) {
+    char key[64];
+    if (!mxIsChar(prhs[i]) || mxGetString(prhs[i], key, sizeof(key)) != 0) continue;
+    if (strcmp(key, name) != 0) continue;
+    const mxClassID c = mxGetClassID(prhs[i + 1]);
+    if (c == mxUINT64_CLASS || c == mxINT64_CLASS) *value = *(const uint64_t*)mxGetData(prhs[i + 1]);
+    else *value = (uint64_t)mxGetScalar(prhs[i + 1]);
+    return 1;
+  }
+  return 0;
+}
 static void vo_mex_check_pairs(int nrhs, int first) {
   if ((nrhs - first) % 2 != 0) mexErrMsgIdAndTxt("vo:args:pairs", "name-value arguments must come in pairs");
 }

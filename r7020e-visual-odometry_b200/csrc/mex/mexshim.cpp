@@ -7,7 +7,8 @@
 #include <stdlib.h>
 #include <string.h>
 
-struct mxArray_tag { mxClassID cls; size_t m, n; void* data; };
+// m = dims[0], n = product of the remaining dimensions (what MATLAB's mxGetN returns for N-D arrays)
+struct mxArray_tag { mxClassID cls; size_t m, n; void* data; size_t ndim; size_t dims[4]; };
 
 static size_t elem_size(mxClassID c) {
   switch (c) {
@@ -26,6 +27,8 @@ extern "C" {
 size_t mxGetM(const mxArray* a) { return a->m; }
 size_t mxGetN(const mxArray* a) { return a->n; }
 size_t mxGetNumberOfElements(const mxArray* a) { return a->m * a->n; }
+mwSize mxGetNumberOfDimensions(const mxArray* a) { return a->ndim; }
+const mwSize* mxGetDimensions(const mxArray* a) { return a->dims; }
 void* mxGetData(const mxArray* a) { return a->data; }
 double* mxGetPr(const mxArray* a) { return (double*)a->data; }
 mxClassID mxGetClassID(const mxArray* a) { return a->cls; }
@@ -37,6 +40,8 @@ double mxGetScalar(const mxArray* a) {
     case mxSINGLE_CLASS: return *(float*)a->data;
     case mxINT32_CLASS: return *(int32_t*)a->data;
     case mxUINT32_CLASS: return *(uint32_t*)a->data;
+    case mxINT64_CLASS: return (double)*(int64_t*)a->data;
+    case mxUINT64_CLASS: return (double)*(uint64_t*)a->data;
     case mxLOGICAL_CLASS: case mxUINT8_CLASS: return *(uint8_t*)a->data;
     default: return 0;
   }
@@ -50,8 +55,16 @@ int mxGetString(const mxArray* a, char* buf, mwSize buflen) {
 }
 mxArray* mxCreateNumericMatrix(mwSize m, mwSize n, mxClassID cls, mxComplexity) {
   mxArray* a = (mxArray*)malloc(sizeof(mxArray));
-  a->cls = cls; a->m = m; a->n = n;
+  a->cls = cls; a->m = m; a->n = n; a->ndim = 2; a->dims[0] = m; a->dims[1] = n; a->dims[2] = a->dims[3] = 1;
   a->data = calloc(m * n ? m * n : 1, elem_size(cls));
+  return a;
+}
+mxArray* mxCreateNumericArray(mwSize ndim, const mwSize* dims, mxClassID cls, mxComplexity c) {
+  size_t rest = 1;
+  for (size_t k = 1; k < ndim; ++k) rest *= dims[k];
+  mxArray* a = mxCreateNumericMatrix(ndim ? dims[0] : 0, ndim > 1 ? rest : 1, cls, c);
+  a->ndim = ndim < 2 ? 2 : (ndim > 4 ? 4 : ndim);
+  for (size_t k = 0; k < 4; ++k) a->dims[k] = k < ndim ? dims[k] : 1;
   return a;
 }
 mxArray* mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity c) { return mxCreateNumericMatrix(m, n, mxDOUBLE_CLASS, c); }
@@ -78,7 +91,13 @@ int mexAtExit(void (*fn)(void)) { g_atexit = fn; return 0; }
 // ---- host-side helpers for the test driver
 mxArray* shim_from_buffer(int cls, size_t m, size_t n, const void* src) {
   mxArray* a = mxCreateNumericMatrix(m, n, (mxClassID)cls, mxREAL);
-  if (src && m * n) memcpy(a->data, src, m * n * elem_size((mxClassID)cls));
+  if (src && m * n != 0) memcpy(a->data, src, m * n * elem_size((mxClassID)cls));
+  return a;
+}
+// N-D array (up to 4 dimensions, column-major like MATLAB)
+mxArray* shim_from_buffer_nd(int cls, size_t ndim, const size_t* dims, const void* src) {
+  mxArray* a = mxCreateNumericArray(ndim, dims, (mxClassID)cls, mxREAL);
+  if (src && a->m * a->n != 0) memcpy(a->data, src, a->m * a->n * elem_size((mxClassID)cls));
   return a;
 }
 typedef void (*mexfn_t)(int, mxArray**, int, const mxArray**);

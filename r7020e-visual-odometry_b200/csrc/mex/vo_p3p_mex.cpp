@@ -24,7 +24,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   if (vo_mex_opt(nrhs, prhs, 3, "MaxNumTrials", &v)) o.max_num_trials = (int)v;
   if (vo_mex_opt(nrhs, prhs, 3, "Confidence", &v)) o.confidence = v;
   if (vo_mex_opt(nrhs, prhs, 3, "MaxReprojectionError", &v)) o.max_reproj_error = v;
-  if (vo_mex_opt(nrhs, prhs, 3, "Seed", &v)) o.seed = (uint64_t)v;
+  vo_mex_opt_u64(nrhs, prhs, 3, "Seed", &o.seed);
   plhs[0] = mxCreateDoubleMatrix(4, 4, mxREAL);
   mxArray* inl = mxCreateLogicalMatrix(n, 1);
   int status = 0;

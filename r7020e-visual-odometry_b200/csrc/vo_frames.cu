@@ -75,8 +75,14 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
   const size_t img_bytes = (size_t)rows * cols;
   uint8_t* dimg = sift_plan_images(plan);
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  VO_CUDA(cudaMemcpy2DAsync(dimg, 2 * img_bytes, left, img_bytes, img_bytes, n, kind, st));
-  VO_CUDA(cudaMemcpy2DAsync(dimg + img_bytes, 2 * img_bytes, right, img_bytes, img_bytes, n, kind, st));
+  if (opts && opts->col_major) {   // MATLAB H x W x N stacks: staged as they are, transposed on the device
+    VO_TRY(sift_load_col_major(plan, 0, 2, left, n, on_device != 0, st));
+    VO_TRY(sift_load_col_major(plan, 1, 2, right, n, on_device != 0, st));
+    ctx->kernel_launches += 2;
+  } else {
+    VO_CUDA(cudaMemcpy2DAsync(dimg, 2 * img_bytes, left, img_bytes, img_bytes, n, kind, st));
+    VO_CUDA(cudaMemcpy2DAsync(dimg + img_bytes, 2 * img_bytes, right, img_bytes, img_bytes, n, kind, st));
+  }
   VO_TRY(sift_run_device(ctx, plan, 2 * n, so, st));
   const float* desc = sift_plan_desc(plan);
   const vo_keypoint* kps = sift_plan_keypoints(plan);

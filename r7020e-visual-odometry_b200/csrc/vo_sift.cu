@@ -149,8 +149,10 @@ __device__ __forceinline__ float dbl_at(const uint8_t* __restrict__ img, int row
   return wya * (wxa * a + wxb * b) + wyb * (wxa * c + wxb * d);
 }
 
-__global__ void sift_transpose_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int rows, int cols, int ld) {
+__global__ void sift_transpose_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int rows, int cols, int ld,
+                                         size_t src_step, size_t dst_step) {
   __shared__ uint8_t t[32][33];
+  src += blockIdx.z * src_step; dst += blockIdx.z * dst_step;
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;   // bx over cols, by over rows
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {    // read src (col-major): element (r,c) at src[c*ld + r]
     const int c = bx + i, r = by + threadIdx.x;
@@ -1574,6 +1576,19 @@ int sift_prepare(vo_ctx* ctx, int rows, int cols, int batch, const vo_sift_opts*
   return get_plan(ctx, rows, cols, batch, *filled, capacity, plan);
 }
 uint8_t* sift_plan_images(SiftPlan* p) { return p->img; }
+// n MATLAB-ordered images (contiguous, rows*cols bytes each) -> plan images first_img, first_img + img_step, ...
+int sift_load_col_major(SiftPlan* p, int first_img, int img_step, const uint8_t* src, int n, bool on_device, cudaStream_t st) {
+  const size_t ib = (size_t)p->rows * p->cols;
+  const uint8_t* stage = src;
+  if (!on_device) {
+    VO_CUDA(cudaMemcpy2DAsync(p->img_t + (size_t)first_img * ib, (size_t)img_step * ib, src, ib, ib, n, cudaMemcpyHostToDevice, st));
+    stage = p->img_t + (size_t)first_img * ib;
+  }
+  const size_t sstep = on_device ? ib : (size_t)img_step * ib;
+  dim3 g(div_up(p->cols, 32), div_up(p->rows, 32), n);
+  sift_transpose_u8_kernel<<<g, dim3(32, 8), 0, st>>>(stage, p->img + (size_t)first_img * ib, p->rows, p->cols, p->rows, sstep, (size_t)img_step * ib);
+  return VO_OK;
+}
 vo_keypoint* sift_plan_keypoints(SiftPlan* p) { return p->final_kp; }
 float* sift_plan_desc(SiftPlan* p) { return p->desc; }
 int* sift_plan_counters(SiftPlan* p) { return p->counters; }
@@ -1583,8 +1598,18 @@ int sift_plan_kp_cap(SiftPlan* p) { return p->kp_cap; }
 
 using namespace vo;
 
+// dst[k*n + i] = src[i*128 + k]: one image's descriptors as a MATLAB M x 128 matrix
+__global__ void __launch_bounds__(256)
+sift_desc_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  __shared__ float t[32][33];
+  const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) if (i0 + r < n) t[r][threadIdx.x] = src[(size_t)(i0 + r) * 128 + k0 + threadIdx.x];
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) if (i0 + threadIdx.x < n) dst[(size_t)(k0 + r) * n + i0 + threadIdx.x] = t[threadIdx.x][r];
+}
+
 static int sift_host(vo_ctx* ctx, const uint8_t* imgs, int n_img, int rows, int cols, int ld, int col_major,
-                     const vo_sift_opts* opts, int capacity, vo_keypoint* kps, float* desc, int* n_out) {
+                     const vo_sift_opts* opts, int capacity, vo_keypoint* kps, float* desc, int* n_out, int desc_col_major = 0) {
   VO_CHECK_ARG(ctx && imgs && n_out, "null argument");
   VO_CHECK_ARG(n_img > 0 && rows > 0 && cols > 0 && capacity >= 0, "bad size");
   VO_CHECK_ARG(capacity == 0 || (kps && desc), "null output");
@@ -1595,9 +1620,8 @@ static int sift_host(vo_ctx* ctx, const uint8_t* imgs, int n_img, int rows, int 
   if (col_major) {
     for (int b = 0; b < n_img; ++b)
       VO_CUDA(cudaMemcpy2DAsync(p->img_t + (size_t)b * rows * cols, rows, imgs + (size_t)b * ld * cols, ld, rows, cols, cudaMemcpyHostToDevice, st));
-    dim3 g(div_up(cols, 32), div_up(rows, 32));
-    for (int b = 0; b < n_img; ++b)
-      sift_transpose_u8_kernel<<<g, dim3(32, 8), 0, st>>>(p->img_t + (size_t)b * rows * cols, p->img + (size_t)b * rows * cols, rows, cols, rows);
+    dim3 g(div_up(cols, 32), div_up(rows, 32), n_img);
+    sift_transpose_u8_kernel<<<g, dim3(32, 8), 0, st>>>(p->img_t, p->img, rows, cols, rows, (size_t)rows * cols, (size_t)rows * cols);
   } else if (ld == cols) {
     VO_CUDA(cudaMemcpyAsync(p->img, imgs, (size_t)n_img * rows * cols, cudaMemcpyHostToDevice, st));
   } else {
@@ -1619,7 +1643,15 @@ static int sift_host(vo_ctx* ctx, const uint8_t* imgs, int n_img, int rows, int 
     if (n > capacity) { if (rc == VO_OK) set_error("vo_sift: %d keypoints exceed capacity %d", n, capacity); rc = VO_ERR_CAPACITY; n = capacity; }
     if (n > 0) {
       VO_CUDA(cudaMemcpyAsync(kps + (size_t)b * capacity, p->final_kp + (size_t)b * p->kp_cap, (size_t)n * sizeof(vo_keypoint), cudaMemcpyDeviceToHost, st));
-      VO_CUDA(cudaMemcpyAsync(desc + (size_t)b * capacity * 128, p->desc + (size_t)b * p->kp_cap * 128, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost, st));
+      const float* dsrc = p->desc + (size_t)b * p->kp_cap * 128;
+      if (desc_col_major) {
+        float* dt; VO_TRY(dev_buf(ctx, "sift_desc_t", (size_t)n_img * p->kp_cap * 128, &dt));
+        dt += (size_t)b * p->kp_cap * 128;
+        sift_desc_transpose_kernel<<<dim3(div_up(n, 32), 4), dim3(32, 8), 0, st>>>(dsrc, dt, n);
+        ++ctx->kernel_launches;
+        dsrc = dt;
+      }
+      VO_CUDA(cudaMemcpyAsync(desc + (size_t)b * capacity * 128, dsrc, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
   }
   VO_CUDA(cudaStreamSynchronize(st));
@@ -1636,6 +1668,11 @@ int vo_sift(vo_ctx* ctx, const uint8_t* img, int rows, int cols, int ld, int col
 int vo_sift_batch(vo_ctx* ctx, const uint8_t* imgs, int n_img, int rows, int cols, const vo_sift_opts* opts,
                   int capacity, vo_keypoint* kps, float* desc, int* n_out) {
   return sift_host(ctx, imgs, n_img, rows, cols, cols, 0, opts, capacity, kps, desc, n_out);
+}
+
+int vo_sift_stack(vo_ctx* ctx, const uint8_t* imgs, int n_img, int rows, int cols, int col_major, const vo_sift_opts* opts,
+                  int capacity, vo_keypoint* kps, float* desc, int desc_col_major, int* n_out) {
+  return sift_host(ctx, imgs, n_img, rows, cols, col_major ? rows : cols, col_major, opts, capacity, kps, desc, n_out, desc_col_major);
 }
 
 }  // extern "C"

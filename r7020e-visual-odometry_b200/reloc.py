@@ -1,0 +1,127 @@
+"""Map relocalisation (BASELINE.json configs[4]): N1 query x N2 landmark SIFT-128 descriptors,
+queries row-sharded over the ranks, landmarks replicated, one NCCL all-gather of the 16-byte best-2 records,
+then P3P-MSAC with exactly ``hyps`` hypotheses on the surviving matches (rank 0).
+
+``run`` is called by every rank (bench.py's ``reloc`` leg, tools/reloc_bench.py).  Descriptors are synthetic
+(OpenCV-SIFT statistics, generated on the device); half of the queries are noisy copies of landmark rows.
+Matched landmarks carry synthetic 3-D positions seen by a camera with KITTI intrinsics, so the recovered pose
+is checked against the known one.  Device time is the max over ranks.
+"""
+import time
+
+import numpy as np
+
+
+def sift_like(n, gen, device):
+    import torch
+    g = torch.randn((n, 128), generator=gen, device=device).abs_().pow_(1.5)
+    g *= 512.0 / g.norm(dim=1, keepdim=True)
+    g.clamp_(max=0.2 * 512.0)
+    g *= 512.0 / g.norm(dim=1, keepdim=True)
+    return g.round_().clamp_(0, 255)
+
+
+def run(ctx, rank, world, dist, queries_per_rank=131072, landmarks=1048576, hyps=4096, reps=3,
+        oracle_rows=None, oracle_keep=None, n_check=48):
+    """Returns the result dict on rank 0 (None elsewhere).  ``oracle_rows(f1_rows, f2) -> (j1, s1, s2)`` and
+    ``oracle_keep(s1, s2, n2) -> bool mask`` are the CPU checkers (bench.py passes the oracle; the product never
+    imports it): ``n_check`` sampled query rows of the gathered records are compared bit for bit."""
+    import torch
+    from . import api, shard
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n1, n2 = queries_per_rank * world, landmarks
+    gl = torch.Generator(device=dev); gl.manual_seed(5678)
+    land = sift_like(n2, gl, dev)                                   # replicated: same seed on every rank
+    lo, hi = shard.row_chunks(n1, world)[rank]
+    gq = torch.Generator(device=dev); gq.manual_seed(1234)
+    src_all = torch.randint(0, n2, (n1,), generator=gq, device=dev)          # landmark each query row imitates
+    copy_all = torch.rand((n1,), generator=gq, device=dev) < 0.5             # ... for half of the rows
+    gn = torch.Generator(device=dev); gn.manual_seed(99 + rank)
+    q = sift_like(hi - lo, gn, dev)
+    sel = copy_all[lo:hi]
+    noisy = (land[src_all[lo:hi]] + 6.0 * torch.randn((hi - lo, 128), generator=gn, device=dev)).round_().clamp_(0, 255)
+    q[sel] = noisy[sel]
+    del noisy
+    torch.cuda.synchronize()
+
+    def one():
+        return shard.relocalise_row_sharded_dev(ctx, q, land, rank, world, dist)
+
+    for _ in range(2):
+        rec, counts = one()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ctx.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        rec, counts = one()
+    e1.record()
+    torch.cuda.synchronize()
+    prof = ctx.profile(); ctx.profile_enable(False)
+    g = prof["match_gemm_topk"]
+    ms = torch.tensor([e0.elapsed_time(e1) / reps, g["ms"] / g["launches"]], device=dev, dtype=torch.float64)
+    per_rank = [ms.clone()]
+    if dist is not None:
+        per_rank = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(per_rank, ms)
+    ms_call = max(float(t[0]) for t in per_rank)
+    ms_gemm = max(float(t[1]) for t in per_rank)
+    # the sampled query rows live on different ranks: gather them to rank 0 (tiny)
+    rows = np.sort(np.random.default_rng(5).permutation(n1)[:n_check])
+    mine = torch.zeros((n_check, 128), device=dev)
+    for k, r in enumerate(rows):
+        if lo <= r < hi:
+            mine[k] = q[r - lo]
+    if dist is not None:
+        dist.all_reduce(mine)
+    if rank != 0:
+        return None
+    r = rec.cpu().numpy()
+    keep = r[:, 3] == 1
+    j1 = r[:, 0].view(np.uint32)
+    truth = src_all.cpu().numpy()
+    cp = copy_all.cpu().numpy()
+    correct = int((j1[keep] == truth[keep]).sum())
+    parity = None
+    if oracle_rows is not None:
+        f1 = mine.cpu().numpy()
+        oj, os1, os2 = oracle_rows(f1, land.cpu().numpy().astype(np.uint8))
+        ok = oracle_keep(os1, os2, n2)
+        rr = r[rows]
+        same_keep = np.array_equal(rr[:, 3] == 1, ok)
+        same_j = np.array_equal(rr[ok, 0].view(np.uint32), oj[ok])
+        same_s = np.array_equal(rr[ok, 1].view(np.uint32), os1[ok].view(np.uint32))
+        parity = bool(same_keep and same_j and same_s)
+    # synthetic geometry: landmark j sits at a fixed 3-D point; the query camera sees it through KITTI intrinsics
+    rng = np.random.default_rng(7)
+    K = (718.856, 718.856, 607.1928, 185.2157)
+    ang = 0.05
+    Rwc = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    twc = np.array([0.4, -0.1, 1.2])
+    idx = np.nonzero(keep)[0]
+    if len(idx) > 20000:
+        idx = idx[rng.permutation(len(idx))[:20000]]
+    cam = np.column_stack([rng.uniform(-8, 8, len(idx)), rng.uniform(-2, 2, len(idx)), rng.uniform(6, 40, len(idx))])
+    world_pts = cam @ Rwc.T + twc                                   # X_w = R_wc X_c + t_wc
+    img = np.column_stack([K[0] * cam[:, 0] / cam[:, 2] + K[2], K[1] * cam[:, 1] / cam[:, 2] + K[3]]) + rng.normal(0, 0.3, (len(idx), 2))
+    wrong = j1[idx] != truth[idx]                                   # false matches become outliers
+    img[wrong] = rng.uniform(0, 1200, (int(wrong.sum()), 2))
+    t0 = time.time()
+    res = api.estworldpose(img, world_pts, K, MaxNumTrials=hyps, Adaptive=False, Seed=3, full=True, ctx=ctx)
+    A, inl, status = np.asarray(res["A"]), res["inliers"], res["status"]
+    t_p3p = time.time() - t0
+    err_t = float(np.linalg.norm(A[:3, 3] - twc)); err_R = float(np.linalg.norm(A[:3, :3] - Rwc))
+    ops = 2.0 * n1 * n2 * 128
+    return dict(workload="map relocalisation (BASELINE.json configs[4]): queries row-sharded, landmarks replicated, all-gather of "
+                         "16-byte best-2 records, P3P-MSAC with a fixed hypothesis count",
+                n_gpus=world, queries=n1, landmarks=n2, queries_per_rank=counts,
+                ms_per_call_max_over_ranks=ms_call, ms_match_gemm_max_over_ranks=ms_gemm,
+                per_rank_ms_call=[round(float(t[0]), 3) for t in per_rank],
+                aggregate_tops_call=ops / ms_call / 1e9, aggregate_tops_gemm=ops / ms_gemm / 1e9,
+                allgather_bytes_per_rank=16 * max(counts), kept_rows=int(keep.sum()), kept_correct=correct,
+                copied_rows=int(cp.sum()), parity_rows_checked=int(n_check) if parity is not None else 0,
+                parity_rows_bit_exact=parity,
+                p3p=dict(points=int(len(idx)), hypotheses=hyps, status=int(status), inliers=int(np.sum(inl)),
+                         ms_host_call=1e3 * t_p3p, pose_err_t=err_t, pose_err_R=err_R))

@@ -148,16 +148,19 @@ class VisualOdometry:
         return rel
 
 
-def run_frames(left, right, P1, P2, seed=0, first_frame=0, max_keypoints=8192, ctx=None, device_ptrs=None):
+def run_frames(left, right, P1, P2, seed=0, first_frame=0, max_keypoints=8192, ctx=None, device_ptrs=None, col_major=False):
     """Batched device-resident loop body (vo_frames).  left/right: [n, rows, cols] uint8 host
     arrays (NumPy, or pinned torch CPU tensors via .numpy()).  With ``device_ptrs=(lptr, rptr,
     n, rows, cols)`` the images are already in HBM (vo_frames_dev) and left/right are ignored.
+    ``col_major=True``: left/right are [n, cols, rows] arrays, i.e. the memory of MATLAB H x W x N stacks.
     Returns (rel_pose [n,4,4], status [n], counts [n,8])."""
     ctx = ctx or api.default_context()
     if device_ptrs is None:
         left = np.ascontiguousarray(left, dtype=np.uint8)
         right = np.ascontiguousarray(right, dtype=np.uint8)
         n, rows, cols = left.shape
+        if col_major:
+            rows, cols = cols, rows
     else:
         n, rows, cols = device_ptrs[2:]
     P1 = np.ascontiguousarray(P1, dtype=np.float64).reshape(12)
@@ -168,6 +171,7 @@ def run_frames(left, right, P1, P2, seed=0, first_frame=0, max_keypoints=8192, c
     o.p3p.adaptive = -1
     o.max_keypoints = max_keypoints
     o.first_frame = first_frame
+    o.col_major = 1 if col_major else 0
     rel = np.zeros((n, 4, 4))
     status = np.zeros(n, dtype=np.int32)
     counts = np.zeros((n, 8), dtype=np.int32)

@@ -22,15 +22,7 @@ def ctx():
     c.close()
 
 
-def sift_like_descriptors(n, seed, dim=128):
-    """Integer-valued descriptors with OpenCV-SIFT statistics:
-    g ~ |N(0,1)|^1.5, normalise to 512, clip at 0.2*512, renormalise, round to 0..255."""
-    rng = np.random.default_rng(seed)
-    g = np.abs(rng.standard_normal((n, dim))) ** 1.5
-    g *= 512.0 / np.linalg.norm(g, axis=1, keepdims=True)
-    g = np.minimum(g, 0.2 * 512.0)
-    g *= 512.0 / np.linalg.norm(g, axis=1, keepdims=True)
-    return np.clip(np.rint(g), 0, 255).astype(np.float32)
+from vo_b200.synth import sift_like_descriptors  # noqa: E402,F401  (SURVEY 8d config 4 generator, shared with bench.py)
 
 
 def correlated_pair(n1, n2, seed, frac=0.5, noise=6.0):

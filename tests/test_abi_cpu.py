@@ -46,7 +46,7 @@ def test_product_never_imports_the_oracle():
 
 def test_mex_gateways_export_mexfunction():
     d = os.path.join(ROOT, "r7020e-visual-odometry_b200", "csrc", "mex")
-    for name in ("vo_sift_mex", "vo_match_mex", "vo_triangulate_mex", "vo_p3p_mex"):
+    for name in ("vo_sift_mex", "vo_match_mex", "vo_triangulate_mex", "vo_p3p_mex", "vo_frames_mex"):
         so = os.path.join(d, name + ".mexa64")
         assert os.path.exists(so), f"{so} missing: run python __graft_entry__.py"
         lib = C.CDLL(so, mode=os.RTLD_LAZY)

@@ -204,3 +204,70 @@ def test_sequence_runner_and_pipeline_host_logic(tmp_path, monkeypatch):
     monkeypatch.setattr(vo, "run_frames", boom)
     with pytest.raises(RuntimeError, match="device fault"):
         vo.FramePipeline(depth=2).map(batches, np.eye(3, 4), np.eye(3, 4))
+
+
+def test_street_world_is_a_consistent_static_scene():
+    """The benchmark workload (synth.StreetWorld): deterministic, and geometrically exact -- a pixel of the left
+    image, lifted to 3-D with the renderer's own depth, lands on the same grey value in the right image (P1) and
+    in the next frame's left image (relative ground-truth pose): one static world, exact stereo and motion."""
+    cv2 = pytest.importorskip("cv2")
+    from vo_b200 import synth
+    d = np.load(os.path.join(G, "kitti00_reference_data.npz"))
+    gt = np.tile(np.eye(4), (12, 1, 1)); gt[:, :3, :] = d["poses"][:12]
+    w = synth.StreetWorld(gt, seed=3)
+    l0, r0, zl0, zr0 = w.render(0, depth=True)
+    l0b, r0b = synth.StreetWorld(gt, seed=3).render(0)
+    assert np.array_equal(l0, l0b) and np.array_equal(r0, r0b)
+    assert (l0 > 0).mean() > 0.5 and not np.array_equal(l0, r0)
+    l1, _, zl1, _ = w.render(1, depth=True)
+    K = synth.KITTI_P0[:, :3]
+    ys, xs = np.mgrid[20:356:5, 20:1221:7]
+    Z = zl0[ys, xs]
+    ok = np.isfinite(Z)
+    X = np.stack([(xs - K[0, 2]) * Z / K[0, 0], (ys - K[1, 2]) * Z / K[1, 1], Z], axis=-1)       # camera-0 coordinates
+    rel = np.linalg.inv(gt[1]) @ gt[0]                                                            # camera 0 -> camera 1
+    for img, zb, Rt in ((r0, zr0, np.c_[np.eye(3), [-synth.KITTI_BASELINE, 0, 0]]), (l1, zl1, rel[:3])):
+        Y = X @ Rt[:, :3].T + Rt[:, 3]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            u = K[0, 0] * Y[..., 0] / Y[..., 2] + K[0, 2]; v = K[1, 1] * Y[..., 1] / Y[..., 2] + K[1, 2]
+        inside = ok & (u > 1) & (u < 1239) & (v > 1) & (v < 374)
+        ui = np.clip(np.rint(np.nan_to_num(u)), 0, 1240).astype(int); vi = np.clip(np.rint(np.nan_to_num(v)), 0, 375).astype(int)
+        with np.errstate(invalid="ignore"):
+            vis = inside & (np.abs(zb[vi, ui] - Y[..., 2]) < 0.02 * Y[..., 2])                     # not occluded in the other view
+        a = l0[ys, xs][vis].astype(np.float64)
+        b = cv2.remap(img, np.nan_to_num(u).astype(np.float32), np.nan_to_num(v).astype(np.float32), cv2.INTER_LINEAR)[vis].astype(np.float64)
+        assert vis.sum() > 2000 and np.corrcoef(a, b)[0, 1] > 0.9, (vis.sum(), np.corrcoef(a, b)[0, 1])
+
+
+def test_descriptor_sets_kinds():
+    from vo_b200 import synth
+    for kind in ("integer", "ties", "float"):
+        f1, f2 = synth.descriptor_sets(kind, 300, 400, seed=5)
+        assert f1.shape == (300, 128) and f2.shape == (400, 128) and f1.dtype == np.float32
+        g1, g2 = synth.descriptor_sets(kind, 300, 400, seed=5)
+        assert np.array_equal(f1, g1) and np.array_equal(f2, g2)
+    f1, f2 = synth.descriptor_sets("ties", 300, 400, seed=5)
+    assert len(np.unique(f2, axis=0)) < 400 and np.array_equal(f1, np.rint(f1))
+    f1, _ = synth.descriptor_sets("float", 300, 400, seed=5)
+    assert np.allclose(np.linalg.norm(f1, axis=1), 1.0, atol=1e-5) and not np.array_equal(f1, np.rint(f1))
+
+
+def test_bench_oracle_row_checker_equals_the_oracle():
+    """bench.py spreads the oracle's best-2 search over worker processes (column chunks) and applies the acceptance
+    tests of oracle/match.c to the merged scores: both must equal the oracle called directly, bit for bit."""
+    import bench
+    from oracle import oracle
+    from vo_b200 import synth
+    try:
+        for kind in ("integer", "ties", "float"):
+            f1, f2 = synth.descriptor_sets(kind, 64, 20000, seed=11)
+            j, s1, s2 = bench.oracle_top2_rows(f1, f2)
+            oj, os1, os2 = oracle.match_top2(f1, f2)
+            assert np.array_equal(j, oj) and np.array_equal(s1.view(np.uint32), os1.view(np.uint32))
+            assert np.array_equal(s2.view(np.uint32), os2.view(np.uint32))
+            keep = bench.oracle_keep(s1, s2, len(f2))
+            pairs, metric = oracle.match(f1, f2)
+            assert np.array_equal(np.nonzero(keep)[0].astype(np.uint32), pairs[:, 0]) and np.array_equal(j[keep], pairs[:, 1])
+    finally:
+        if bench._POOL is not None:
+            bench._POOL.terminate(); bench._POOL = None

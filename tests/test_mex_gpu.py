@@ -1,57 +1,13 @@
-"""The four MEX gateways driven by a fake MATLAB host (csrc/mex/mexshim.cpp): column-major inputs,
-1-based uint32 indexPairs, class-preserving triangulate, estworldpose-style erroring."""
-import ctypes as C
-import os
-
+"""The MEX gateways driven by a stand-in MATLAB host (vo_b200/mexhost.py over csrc/mex/mexshim.cpp):
+column-major inputs, 1-based uint32 indexPairs, class-preserving triangulate, estworldpose-style erroring,
+H x W x N stacks for vo_sift_mex and the batched loop gateway vo_frames_mex."""
 import numpy as np
 import pytest
 
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
-D = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "r7020e-visual-odometry_b200", "csrc", "mex")
-CLS = {np.dtype("float64"): 6, np.dtype("float32"): 7, np.dtype("uint8"): 9, np.dtype("int32"): 12, np.dtype("uint32"): 13}
-NP = {6: np.float64, 7: np.float32, 9: np.uint8, 12: np.int32, 13: np.uint32, 3: np.uint8}
-
-
-class Host:
-    def __init__(self):
-        self.shim = C.CDLL(os.path.join(D, "libmexshim.so"), mode=C.RTLD_GLOBAL)
-        s = self.shim
-        s.shim_from_buffer.restype = C.c_void_p
-        s.shim_from_buffer.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_void_p]
-        s.mxCreateString.restype = C.c_void_p
-        s.mxGetData.restype = C.c_void_p
-        s.mxGetData.argtypes = [C.c_void_p]
-        for f in ("mxGetM", "mxGetN"):
-            getattr(s, f).restype = C.c_size_t
-            getattr(s, f).argtypes = [C.c_void_p]
-        s.mxGetClassID.argtypes = [C.c_void_p]
-        s.shim_last_error_id.restype = C.c_char_p
-        s.shim_last_error_msg.restype = C.c_char_p
-        s.shim_call.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
-        self.gates = {}
-
-    def mx(self, a):
-        if isinstance(a, str):
-            return self.shim.mxCreateString(a.encode())
-        a = np.asfortranarray(np.atleast_2d(a))                   # MATLAB arrays are column-major
-        return self.shim.shim_from_buffer(CLS[a.dtype], a.shape[0], a.shape[1], a.ctypes.data_as(C.c_void_p))
-
-    def call(self, gate, nlhs, *args):
-        if gate not in self.gates:
-            self.gates[gate] = C.CDLL(os.path.join(D, gate + ".mexa64"))
-        fn = C.cast(self.gates[gate].mexFunction, C.c_void_p)
-        prhs = (C.c_void_p * len(args))(*[self.mx(a) for a in args])
-        plhs = (C.c_void_p * max(nlhs, 1))()
-        if self.shim.shim_call(fn, nlhs, plhs, len(args), prhs):
-            raise RuntimeError(self.shim.shim_last_error_id().decode() + ": " + self.shim.shim_last_error_msg().decode())
-        outs = []
-        for k in range(max(nlhs, 1)):
-            m, n, cls = self.shim.mxGetM(plhs[k]), self.shim.mxGetN(plhs[k]), self.shim.mxGetClassID(plhs[k])
-            buf = (C.c_char * (m * n * np.dtype(NP[cls]).itemsize)).from_address(self.shim.mxGetData(plhs[k])) if m * n else b""
-            outs.append(np.frombuffer(bytes(buf), dtype=NP[cls]).reshape((n, m)).T.copy())
-        return outs
+from vo_b200.mexhost import Host, MexOps, frames as mex_frames
 
 
 @pytest.fixture(scope="module")
@@ -105,3 +61,53 @@ def test_triangulate_and_p3p_gateways(host):
         host.call("vo_p3p_mex", 1, x1[:3], X[:3], synth.KITTI_K4)         # errors like estworldpose
     _, _, st = host.call("vo_p3p_mex", 3, x1[:3], X[:3], synth.KITTI_K4)
     assert st[0, 0] == 1
+
+
+def test_sift_gateway_stack(host):
+    """vo_sift_mex(cat(3, lf, rf)): both images of VO.m:79-84 in one call; rows concatenated, count per image."""
+    from vo_b200 import synth
+    l, r = synth.shift_stream(1, seed=3, h=120, w=200)
+    o = host.call("vo_sift_mex", 8, np.stack([l[0], r[0]], axis=2))
+    cnt = o[7][:, 0]
+    a = host.call("vo_sift_mex", 7, l[0]); b = host.call("vo_sift_mex", 7, r[0])
+    assert cnt.tolist() == [len(a[0]), len(b[0])] and len(a[0]) > 50
+    for k in range(7):
+        assert np.array_equal(o[k], np.concatenate([a[k], b[k]], axis=0))
+    with pytest.raises(RuntimeError, match="vo:sift:class"):
+        host.call("vo_sift_mex", 1, np.zeros((20, 20), np.int32))
+
+
+def test_frames_gateway_equals_vo_frames(host, ctx):
+    """[relA, status, counts] = vo_frames_mex(L, R, P1, P2, ...) on H x W x N stacks is bit-identical to vo_frames
+    on the same frames (and to the column-major form of the C ABI), relA ready for rigidtform3d (column-major)."""
+    from vo_b200 import synth, vo
+    left, right = synth.shift_stream(5, seed=6, h=188, w=620)
+    want = vo.run_frames(left, right, synth.KITTI_P0, synth.KITTI_P1, seed=7, first_frame=3, ctx=ctx)
+    got = mex_frames(host, left, right, synth.KITTI_P0, synth.KITTI_P1, seed=7, first_frame=3)
+    assert (want[1][1:] == 0).all() and (want[2][1:, 6] > 30).all()
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    lt = np.ascontiguousarray(np.transpose(left, (0, 2, 1))); rt = np.ascontiguousarray(np.transpose(right, (0, 2, 1)))
+    cm = vo.run_frames(lt, rt, synth.KITTI_P0, synth.KITTI_P1, seed=7, first_frame=3, ctx=ctx, col_major=True)
+    for a, b in zip(cm, want):
+        assert np.array_equal(a, b)
+    # 4x3 legacy camMatrix form and argument errors
+    relA, = host.call("vo_frames_mex", 1, np.transpose(left, (1, 2, 0)), np.transpose(right, (1, 2, 0)),
+                      synth.KITTI_P0.T.copy(), synth.KITTI_P1.T.copy(), "Seed", np.uint64(7), "FirstFrame", np.float64(3))
+    assert np.array_equal(np.transpose(relA, (2, 0, 1)), want[0])
+    with pytest.raises(RuntimeError, match="vo:frames:size"):
+        host.call("vo_frames_mex", 1, np.transpose(left, (1, 2, 0)), np.transpose(right[:4], (1, 2, 0)), synth.KITTI_P0, synth.KITTI_P1)
+    with pytest.raises(RuntimeError, match="vo:frames:class"):
+        host.call("vo_frames_mex", 1, left[0].astype(np.float32), right[0].astype(np.float32), synth.KITTI_P0, synth.KITTI_P1)
+
+
+def test_six_call_loop_through_gateways_equals_batched(host, ctx):
+    """The literal drop-in: VO.m's loop with every toolbox call answered by a gateway (MexOps) gives the same
+    relative poses as the batched loop."""
+    from vo_b200 import synth, vo
+    left, right = synth.shift_stream(4, seed=8, h=188, w=620)
+    g = vo.VisualOdometry(synth.KITTI_P0, synth.KITTI_P1, MexOps(host, seed=5))
+    rels = [g.step(left[i], right[i]) for i in range(4)]
+    want = vo.run_frames(left, right, synth.KITTI_P0, synth.KITTI_P1, seed=5, ctx=ctx)
+    for i in range(1, 4):
+        assert np.array_equal(rels[i], want[0][i])

@@ -139,3 +139,40 @@ def test_frames_with_empty_and_blank_inputs(ctx):
     g = vo.VisualOdometry(synth.KITTI_P0, synth.KITTI_P1, vo.CudaOps(ctx=ctx, seed=1))
     g.step(left[0], right[0]); a = g.step(left[1], right[1])
     assert np.array_equal(a, rel[1])
+
+
+def test_trajectory_parity_on_225_street_frames(ctx):
+    """North-star trajectory criterion at devkit scale: 225 frames (164 m, KITTI devkit 100 m segments every 10
+    frames) of the rendered street world along kitti/poses/00.txt -- the benchmark workload of bench.py.  The CUDA
+    path runs them through the batched loop (7 batches of 32 + a halo frame); the oracle's run over the same
+    frames is the committed golden file tests/golden/street_oracle_225.npz (make_street_golden.py; re-run here
+    if the renderer's pixels differ on this machine).  t_err / r_err within 2 % of the oracle's, in fact equal."""
+    import os
+    import sys
+    pytest.importorskip("cv2")
+    from vo_b200 import vo, synth
+    g = os.path.join(os.path.dirname(__file__), "golden")
+    sys.path.insert(0, g)
+    import bench
+    import make_street_golden as msg
+    n = msg.N
+    left, right, gt = bench.street_frames(n)
+    gold = np.load(os.path.join(g, "street_oracle_225.npz"))
+    if str(gold["sha256"]) == msg.frames_hash(left, right):
+        rel_o, status_o = gold["rel"], gold["status"]
+    else:                                                  # different pixels here: ask the oracle again (minutes)
+        rel_o, status_o, _, _ = bench.oracle_sequence(left, right, n)
+        bench._POOL.terminate(); bench._POOL = None
+    B = 32
+    rel = np.tile(np.eye(4), (n, 1, 1)); status = np.zeros(n, dtype=np.int32); tracked = np.zeros(n, dtype=np.int32)
+    for b0 in range(0, n - 1, B):
+        r, s, c = vo.run_frames(left[b0:b0 + B + 1], right[b0:b0 + B + 1], synth.KITTI_P0, synth.KITTI_P1, seed=1, first_frame=b0, ctx=ctx)
+        rel[b0 + 1:b0 + B + 1] = r[1:]; status[b0 + 1:b0 + B + 1] = s[1:]; tracked[b0 + 1:b0 + B + 1] = c[1:, 6]
+    assert (status == 0).all() and np.array_equal(status, status_o)
+    assert tracked[1:].min() >= 50
+    eg, eo = bench.trajectory_errors(rel, gt, n), bench.trajectory_errors(rel_o, gt, n)
+    assert eg["segments"] == eo["segments"] >= 5 and eg["lengths_m"] == [100]
+    assert abs(eg["t_err_pct"] - eo["t_err_pct"]) <= 0.02 * eo["t_err_pct"], (eg, eo)
+    assert abs(eg["r_err_deg_per_m"] - eo["r_err_deg_per_m"]) <= 0.02 * eo["r_err_deg_per_m"], (eg, eo)
+    assert eg["t_err_pct"] < 2.0 and eg["xz_err_max_m"] < 3.0, eg          # and the odometry itself is sane
+    assert np.abs(rel - rel_o).max() < 1e-6                                 # same MSAC trial, same inliers, same pose

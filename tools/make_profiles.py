@@ -104,7 +104,7 @@ def bench_launches():
     shares = "\n".join(f"| `{k}` | {100 * v:.1f} % |" for k, v in live["stage_share"].items())
     open(os.path.join(P, "r1_launches_bench.md"), "w").write(
         "# Round 1 -- ncu launch list of `bench.py` itself\n\n"
-        "`python bench.py --steps 3 --warmup 3 --no-cpu --no-match-leg` (exit 0 plain, then the same command under "
+        "`python bench.py --steps 3 --warmup 3 --no-cpu --quick` (exit 0 plain, then the same command under "
         "`ncu --metrics gpu__time_duration.sum --clock-control none --csv`): every kernel launch of the warm-up, the "
         "device-resident pass, the host-buffer (e2e) pass and the profiled serial pass -- 30 frame-loop steps of 33 stereo frames.  "
         "Times under ncu are cold-cache and serialised; the SHARES are what to compare with the live CUDA-event shares below.\n\n"

@@ -25,7 +25,7 @@ def main():
     a = ap.parse_args()
     for v in a.values:
         env = dict(os.environ, **{a.var: v})
-        out = subprocess.run([sys.executable, os.path.join(R, "bench.py"), "--no-cpu", "--no-match-leg", "--steps", str(a.steps),
+        out = subprocess.run([sys.executable, os.path.join(R, "bench.py"), "--no-cpu", "--quick", "--steps", str(a.steps),
                               "--warmup", "3", "--batch", str(a.batch)], env=env, capture_output=True, text=True)
         if out.returncode != 0:
             print(f"{a.var}={v}: bench.py failed\n{out.stderr[-800:]}")
