@@ -149,13 +149,14 @@ def street_frames(n, rank=0, barrier=None):
     """(left, right, gt) of the first n frames of the street sequence.  Rendered once per box (rank 0, all host
     cores) and cached in the temp dir; the other ranks and the reference arm load the cache."""
     import tempfile
-    gt = gt_poses(n)
+    world_poses = gt_poses(10 ** 9)          # the world is laid out along ALL poses of the fixture, whatever n is rendered
+    gt = world_poses[:n]
     n = len(gt)
-    path = os.path.join(tempfile.gettempdir(), f"vo_b200_street_s{SEQ_SEED}_n{n}_{H}x{W}.npy")
+    path = os.path.join(tempfile.gettempdir(), f"vo_b200_street_s{SEQ_SEED}_w{len(world_poses)}_n{n}_{H}x{W}.npy")
     if rank == 0 and not os.path.exists(path):
         from vo_b200 import synth
         t0 = time.time()
-        left, right = synth.street_sequence(gt, seed=SEQ_SEED, h=H, w=W)
+        left, right = synth.street_sequence(world_poses, seed=SEQ_SEED, h=H, w=W, frames=n)
         np.save(path + ".tmp.npy", np.stack([left, right]))
         os.replace(path + ".tmp.npy", path)
         log(f"rendered {n} street frames in {time.time() - t0:.1f} s")

@@ -218,6 +218,17 @@ int vo_frames_dev(vo_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev
                   int rows, int cols, const double P1[12], const double P2[12],
                   const vo_frames_opts* opts, double* rel_pose, int* status, int* counts);
 
+/* Landmark map (VO.m:145-161, CreateLandmarksFromFeatures.m:1-21) for the frames of the most recent
+ * vo_frames / vo_frames_dev call on this context, entirely on the device: selection of the stereo-matched features
+ * that "did not exist in the previous frame" (the reference's x-OR-y comparison), every second one triangulated,
+ * depth filter 0 <= z <= 80, transformPointsForward with the frame's world pose.
+ * poses: n_frames x 16 doubles, row-major 4x4 world pose of every frame of the batch AFTER the caller's pose chain
+ * (pose = pose * rel_pose, VO.m:130; the chain is sequential and stays with the caller).
+ * landmarks: [n_frames][cap][3] doubles, rows[n_frames]: frame i contributes rows[i] rows (what the reference
+ * appends at VO.m:160: zero rows for skipped / rejected features included, 0 rows for frame 0 and for frames whose
+ * estworldpose failed).  VO_ERR_STATE without a preceding vo_frames call, VO_ERR_CAPACITY if cap is too small. */
+int vo_frames_landmarks(vo_ctx* ctx, const double* poses, int n_frames, int cap, double* landmarks, int* rows);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,16 @@
 
 namespace vo {
 
-struct FramePlan { int unused = 0; };
+// What the landmark pass (vo_frames_landmarks) needs from the most recent vo_frames call on the context: the device
+// arrays live in the context's scratch buffers and stay valid until the next vo_frames call.
+struct FramePlan {
+  int n = 0, kc = 0;
+  const vo_keypoint* kps = nullptr;
+  const uint32_t *l0 = nullptr, *r0 = nullptr;
+  const int* K = nullptr;                // K[s*n + p]
+  const double *old_l = nullptr, *old_r = nullptr, *dP = nullptr;
+  const int* dstat = nullptr;
+};
 void frame_plan_destroy(FramePlan* p) { delete p; }
 
 // out_k[p][k] = src_k[p][idx[p][k]] for k < cnt[p]   (up to two arrays share one index list)
@@ -169,6 +178,12 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
     pp.seed = po.seed + (uint64_t)(first_frame + 1) * 0x9E3779B97F4A7C15ull;
     VO_TRY(p3p_batch_device(ctx, cur_l, world, K + 4 * n, kc, np, dP + 24, pp, dA, nullptr, dstat, dstat + n, st));
   }
+  if (!ctx->frame_plan) ctx->frame_plan = new FramePlan();
+  {
+    FramePlan* fp = ctx->frame_plan;
+    fp->n = n; fp->kc = kc; fp->kps = kps; fp->l0 = l0; fp->r0 = r0; fp->K = K; fp->old_l = old_l; fp->old_r = old_r; fp->dP = dP;
+    fp->dstat = dstat;
+  }
   // results
   double* hA; VO_TRY(pin_buf(ctx, "fr_hA", (size_t)n * 16, &hA));
   int* hI; VO_TRY(pin_buf(ctx, "fr_hI", (size_t)n * 4 + (size_t)5 * n + (size_t)2 * n * 4 + 16, &hI));
@@ -209,7 +224,51 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
   return rc;
 }
 
+// VO.m:145-161 for every frame of the last batch, after the caller has multiplied the pose chain (VO.m:130).
+static int frames_landmarks(vo_ctx* ctx, const double* poses, int n, int cap, double* landmarks, int* rows) {
+  VO_CHECK_ARG(ctx && poses && landmarks && rows, "null argument");
+  FramePlan* fp = ctx->frame_plan;
+  if (!fp || fp->n < 1) { set_error("vo_frames_landmarks: no vo_frames call has run on this context"); return VO_ERR_STATE; }
+  VO_CHECK_ARG(n == fp->n, "vo_frames_landmarks: n_frames differs from the last vo_frames call");
+  VO_CHECK_ARG(cap >= 2, "vo_frames_landmarks: cap must be at least 2");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int kc = fp->kc;
+  const int dcap = cap < kc ? cap : kc;      // a frame has at most kc stereo matches
+  uint32_t* newidx; VO_TRY(dev_buf(ctx, "lm_idx", (size_t)n * kc, &newidx));
+  int* cnt; VO_TRY(dev_buf(ctx, "lm_cnt", (size_t)2 * n, &cnt));        // n_new[n], rows[n]
+  double* dposes; VO_TRY(dev_buf(ctx, "lm_pose", (size_t)n * 16, &dposes));
+  double* dout; VO_TRY(dev_buf(ctx, "lm_out", (size_t)n * dcap * 3, &dout));
+  VO_CUDA(cudaMemcpyAsync(dposes, poses, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, st));
+  VO_CUDA(cudaMemsetAsync(cnt, 0, (size_t)2 * n * sizeof(int), st));
+  VO_CUDA(cudaMemsetAsync(dout, 0, (size_t)n * dcap * 3 * sizeof(double), st));
+  {
+    ProfScope ps(ctx, st, "landmarks", 0.0, 0.0, 2);
+    VO_TRY(landmarks_device(fp->kps, kc, fp->l0, fp->r0, fp->K, fp->old_l, fp->old_r, fp->K + 4 * n, fp->dstat, fp->dP, dposes, n,
+                            newidx, cnt, dout, dcap, cnt + n, st));
+  }
+  int* h; VO_TRY(pin_buf(ctx, "lm_h", (size_t)3 * n, &h));             // n_new[p], rows[i], status[p]
+  VO_CUDA(cudaMemcpyAsync(h, cnt, (size_t)2 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (n > 1) VO_CUDA(cudaMemcpyAsync(h + 2 * n, fp->dstat, (size_t)(n - 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaStreamSynchronize(st));
+  int rc = VO_OK;
+  rows[0] = 0;
+  for (int i = 1; i < n; ++i) {
+    // the reference's array starts as zeros(2, 3) and grows to the last row written (CreateLandmarksFromFeatures.m:2, 17)
+    const int r = h[2 * n + i - 1] != 0 ? 0 : (h[n + i] > 2 ? h[n + i] : 2);
+    if (h[i - 1] > dcap) { set_error("vo_frames_landmarks: frame %d has %d new features, cap is %d", i, h[i - 1], cap); rc = VO_ERR_CAPACITY; }
+    rows[i] = r;
+    if (r > 0)
+      VO_CUDA(cudaMemcpyAsync(landmarks + (size_t)i * cap * 3, dout + (size_t)i * dcap * 3, (size_t)r * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  VO_CUDA(cudaStreamSynchronize(st));
+  return rc;
+}
+
 extern "C" {
+int vo_frames_landmarks(vo_ctx* ctx, const double* poses, int n_frames, int cap, double* landmarks, int* rows) {
+  return frames_landmarks(ctx, poses, n_frames, cap, landmarks, rows);
+}
 int vo_frames(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n, int rows, int cols, const double P1[12],
               const double P2[12], const vo_frames_opts* opts, double* rel_pose, int* status, int* counts) {
   return frames_core(ctx, left, right, 0, n, rows, cols, P1, P2, opts, rel_pose, status, counts);

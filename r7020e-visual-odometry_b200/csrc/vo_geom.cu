@@ -480,6 +480,101 @@ int p3p_batch_device(vo_ctx* ctx, const double* img, const double* world, const 
   return VO_OK;
 }
 
+// ------------------------------------------------------------------- landmark map
+// VO.m:145-161 + CreateLandmarksFromFeatures.m:1-21 on the device, for frame pair p = (frame p, frame p+1):
+//   matched positions of the CURRENT frame i = p + 1:  ml[k] = kps[2i][l0[i][k]], mr[k] = kps[2i+1][r0[i][k]], k < K0[i]
+//   "old" = tracked positions of the PREVIOUS frame after find_remaining_points: old_l[p][m], old_r[p][m], m < K4[p]
+// A feature is new iff NONE of the old points shares its x OR its y coordinate, left and right (the reference's
+// `find(old.Location == loc(index,:), 1)` compares an N x 2 array with a 1 x 2 row: VO.m:147-154).
+__global__ void __launch_bounds__(256)
+landmark_select_kernel(const vo_keypoint* __restrict__ kps, int kc, const uint32_t* __restrict__ l0, const uint32_t* __restrict__ r0,
+                       const int* __restrict__ K0, const double* __restrict__ old_l, const double* __restrict__ old_r,
+                       const int* __restrict__ K4, uint32_t* __restrict__ newidx, int* __restrict__ n_new) {
+  __shared__ float s_old[4][256];
+  __shared__ int s_warp[8];
+  __shared__ int s_carry;
+  const int p = blockIdx.x, i = p + 1;
+  const int n0 = min(K0[i], kc), n4 = min(K4[p], kc);
+  const vo_keypoint* kl = kps + (size_t)(2 * i) * kc;
+  const vo_keypoint* kr = kps + (size_t)(2 * i + 1) * kc;
+  const double* ol = old_l + (size_t)p * kc * 2;
+  const double* orr = old_r + (size_t)p * kc * 2;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n0; base += 256) {
+    const int k = base + tid;
+    float lx = 0, ly = 0, rx = 0, ry = 0;
+    if (k < n0) {
+      const vo_keypoint a = kl[l0[(size_t)i * kc + k]], b = kr[r0[(size_t)i * kc + k]];
+      lx = a.x; ly = a.y; rx = b.x; ry = b.y;
+    }
+    bool seen = false;
+    for (int m0 = 0; m0 < n4; m0 += 256) {
+      __syncthreads();
+      if (m0 + tid < n4) {
+        s_old[0][tid] = (float)ol[2 * (m0 + tid)]; s_old[1][tid] = (float)ol[2 * (m0 + tid) + 1];
+        s_old[2][tid] = (float)orr[2 * (m0 + tid)]; s_old[3][tid] = (float)orr[2 * (m0 + tid) + 1];
+      }
+      __syncthreads();
+      const int mm = min(256, n4 - m0);
+      for (int m = 0; m < mm; ++m)
+        seen = seen || lx == s_old[0][m] || ly == s_old[1][m] || rx == s_old[2][m] || ry == s_old[3][m];
+    }
+    const bool fresh = k < n0 && !seen;
+    const unsigned bal = __ballot_sync(0xffffffffu, fresh);
+    if (lane == 0) s_warp[wrp] = __popc(bal);
+    __syncthreads();
+    int before = s_carry;
+    for (int w = 0; w < wrp; ++w) before += s_warp[w];
+    if (fresh) newidx[(size_t)p * kc + before + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)k;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_warp[w]; s_carry += t; }
+    __syncthreads();
+  }
+  if (tid == 0) n_new[p] = s_carry;
+}
+
+// Every second new feature (i = 1:2:n) is triangulated, kept when 0 <= z <= 80 and moved to world coordinates with
+// the frame's pose (CreateLandmarksFromFeatures.m:4-18).  Row q of the frame's block is feature q of the new list;
+// skipped and rejected rows stay zero like the reference's zero-initialised array, rows[p] = last written row + 1.
+__global__ void __launch_bounds__(128)
+landmark_build_kernel(const vo_keypoint* __restrict__ kps, int kc, const uint32_t* __restrict__ l0, const uint32_t* __restrict__ r0,
+                      const uint32_t* __restrict__ newidx, const int* __restrict__ n_new, const int* __restrict__ status,
+                      const double* __restrict__ P, const double* __restrict__ poses, double* __restrict__ out, int cap,
+                      int* __restrict__ rows) {
+  const int p = blockIdx.y, i = p + 1;
+  if (status[p] != 0) return;                               // VO.m stops at a failed estworldpose: no landmarks
+  const int n = min(n_new[p], cap);
+  const int q = 2 * (blockIdx.x * 128 + threadIdx.x);
+  if (q >= n) return;
+  const uint32_t k = newidx[(size_t)p * kc + q];
+  const vo_keypoint a = kps[(size_t)(2 * i) * kc + l0[(size_t)i * kc + k]];
+  const vo_keypoint b = kps[(size_t)(2 * i + 1) * kc + r0[(size_t)i * kc + k]];
+  const double p1[2] = {(double)a.x, (double)a.y}, p2[2] = {(double)b.x, (double)b.y};
+  double X[4];
+  dlt_point(p1, p2, P, P + 12, X);
+  const double x = X[0] / X[3], y = X[1] / X[3], z = X[2] / X[3];
+  if (z < 0 || z > 80) return;
+  const double* A = poses + (size_t)i * 16;
+  double* o = out + ((size_t)i * cap + q) * 3;
+  o[0] = ((x * A[0] + y * A[1]) + z * A[2]) + A[3];
+  o[1] = ((x * A[4] + y * A[5]) + z * A[6]) + A[7];
+  o[2] = ((x * A[8] + y * A[9]) + z * A[10]) + A[11];
+  atomicMax(&rows[i], q + 1);
+}
+
+int landmarks_device(const vo_keypoint* kps, int kc, const uint32_t* l0, const uint32_t* r0, const int* K0, const double* old_l,
+                     const double* old_r, const int* K4, const int* status, const double* P_dev, const double* poses_dev,
+                     int n_frames, uint32_t* newidx, int* n_new, double* out, int cap, int* rows, cudaStream_t st) {
+  if (n_frames < 2) return VO_OK;
+  landmark_select_kernel<<<n_frames - 1, 256, 0, st>>>(kps, kc, l0, r0, K0, old_l, old_r, K4, newidx, n_new);
+  landmark_build_kernel<<<dim3(div_up(div_up(cap, 2), 128), n_frames - 1), 128, 0, st>>>(kps, kc, l0, r0, newidx, n_new, status, P_dev,
+                                                                                        poses_dev, out, cap, rows);
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
 int triangulate_batch_device(const double* pts1, const double* pts2, const int* n_dev, int n_stride, int cap, int n_prob,
                              const double* P_dev, double* xyz, cudaStream_t st) {
   if (cap <= 0 || n_prob <= 0) return VO_OK;

@@ -21,4 +21,7 @@ int p3p_batch_device(vo_ctx* ctx, const double* img, const double* world, const 
                      int* info_dev, cudaStream_t st);
 int triangulate_batch_device(const double* pts1, const double* pts2, const int* n_dev, int n_stride, int cap, int n_prob,
                              const double* P_dev, double* xyz, cudaStream_t st);
+int landmarks_device(const vo_keypoint* kps, int kc, const uint32_t* l0, const uint32_t* r0, const int* K0, const double* old_l,
+                     const double* old_r, const int* K4, const int* status, const double* P_dev, const double* poses_dev,
+                     int n_frames, uint32_t* newidx, int* n_new, double* out, int cap, int* rows, cudaStream_t st);
 }  // namespace vo

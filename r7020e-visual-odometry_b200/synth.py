@@ -320,13 +320,14 @@ def _street_render(i):
     return _WORLD.render(i)
 
 
-def street_sequence(poses, seed=7, h=KITTI_H, w=KITTI_W, workers=None):
-    """(left, right) uint8 [n, h, w] of a StreetWorld built on ``poses``, rendered on ``workers`` processes."""
+def street_sequence(poses, seed=7, h=KITTI_H, w=KITTI_W, workers=None, frames=None):
+    """(left, right) uint8 [n, h, w] of a StreetWorld built on ``poses``, rendered on ``workers`` processes;
+    ``frames``: render only the first so many poses (the world still spans all of them)."""
     global _WORLD
     import multiprocessing as mp
     import os
     _WORLD = StreetWorld(poses, seed=seed, h=h, w=w)
-    n = len(_WORLD.poses)
+    n = len(_WORLD.poses) if frames is None else min(frames, len(_WORLD.poses))
     workers = workers or min(os.cpu_count() or 1, 32)
     if workers > 1 and n > 4:
         with mp.get_context("fork").Pool(workers) as pool:

@@ -187,6 +187,20 @@ def run_frames(left, right, P1, P2, seed=0, first_frame=0, max_keypoints=8192, c
     return rel, status, counts
 
 
+def frames_landmarks(poses, cap=4096, ctx=None):
+    """The landmark rows VO.m:145-161 appends for every frame of the batch that ``run_frames`` just processed on
+    ``ctx`` (device-side selection, triangulation, depth filter and world transform: vo_frames_landmarks).
+    poses: [n, 4, 4] world poses of the batch's frames (after the pose chain).  Returns a list of [rows_i, 3] arrays."""
+    ctx = ctx or api.default_context()
+    poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 16)
+    n = len(poses)
+    out = np.zeros((n, cap, 3))
+    rows = np.zeros(n, dtype=np.int32)
+    check(_lib.lib().vo_frames_landmarks(ctx.handle, poses.ctypes.data_as(C.POINTER(C.c_double)), n, cap,
+                                         out.ctypes.data_as(C.POINTER(C.c_double)), rows.ctypes.data_as(C.POINTER(C.c_int))))
+    return [out[i, :rows[i]].copy() for i in range(n)]
+
+
 def chain_poses(rel_poses, start=None):
     """pose = pose * rel_pose (VO.m:130); returns the list of world poses (one per rel pose)."""
     pose = np.eye(4) if start is None else np.asarray(start, dtype=np.float64)

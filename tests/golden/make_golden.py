@@ -30,6 +30,17 @@ for tag, shape, seed in (("small", (120, 160), 1), ("wide", (188, 620), 2)):
                         octave=np.array([p.octave for p in kps], dtype=np.int32), desc=desc.astype(np.uint8))
     print(tag, len(kps), "keypoints")
 
+# ---- SIFT at the BASELINE image size: a 376 x 1241 frame of the benchmark's street sequence (bench.street_frames)
+if os.environ.get("VO_GOLDEN_FULLSIZE", "1") == "1":
+    sys.path.insert(0, ROOT)
+    import bench  # noqa: E402
+    img = bench.street_frames(225)[0][40]
+    kps, desc = cv2.SIFT_create().detectAndCompute(img, None)
+    k = np.array([[p.pt[0], p.pt[1], p.size, p.angle, p.response, p.octave] for p in kps], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "sift_cv2_kitti_size.npz"), image=img, kps=k.astype(np.float32),
+                        octave=np.array([p.octave for p in kps], dtype=np.int32), desc=desc.astype(np.uint8))
+    print("kitti_size", len(kps), "keypoints")
+
 # ---- SIFT with non-default options (the MATLAB name-value pairs NumLayersInOctave, Sigma,
 # ContrastThreshold, EdgeThreshold map onto these OpenCV constructor arguments)
 img = synth.texture(150, 210, seed=9)

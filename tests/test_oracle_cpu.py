@@ -11,8 +11,9 @@ from oracle import oracle
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("tag", ["small", "wide"])
+@pytest.mark.parametrize("tag", ["small", "wide", "kitti_size"])
 def test_sift_oracle_vs_opencv(tag):
+    """kitti_size: a 376 x 1241 frame of the benchmark's street sequence, i.e. the BASELINE image size."""
     from scipy.spatial import cKDTree
     g = np.load(os.path.join(G, f"sift_cv2_{tag}.npz"))
     okp, odesc = oracle.sift(g["image"])

@@ -176,3 +176,51 @@ def test_trajectory_parity_on_225_street_frames(ctx):
     assert abs(eg["r_err_deg_per_m"] - eo["r_err_deg_per_m"]) <= 0.02 * eo["r_err_deg_per_m"], (eg, eo)
     assert eg["t_err_pct"] < 2.0 and eg["xz_err_max_m"] < 3.0, eg          # and the odometry itself is sane
     assert np.abs(rel - rel_o).max() < 1e-6                                 # same MSAC trial, same inliers, same pose
+
+
+def test_landmark_map_on_device_equals_the_loop_mirror(ctx):
+    """vo_frames_landmarks (selection with the reference's x-OR-y quirk, every second new feature,
+    triangulation, 0 <= z <= 80, world transform -- all on the device, for a whole batch) appends exactly the rows
+    that the line-by-line mirror of VO.m:145-161 / CreateLandmarksFromFeatures.m appends frame by frame."""
+    from vo_b200 import vo, synth
+    left, right = _frames(6, seed=17)
+    g = vo.VisualOdometry(synth.KITTI_P0, synth.KITTI_P1, vo.CudaOps(ctx=ctx, seed=5), view_3D=True)
+    sizes = [0]
+    for i in range(6):
+        g.step(left[i], right[i]); sizes.append(len(g.landmarks))
+    rel, status, counts = vo.run_frames(left, right, synth.KITTI_P0, synth.KITTI_P1, seed=5, ctx=ctx)
+    assert (status == 0).all()
+    poses = np.array([np.eye(4)] + vo.chain_poses(rel[1:]))
+    lm = vo.frames_landmarks(poses, cap=4096, ctx=ctx)
+    assert len(lm[0]) == 0
+    for i in range(6):
+        want = g.landmarks[sizes[i]:sizes[i + 1]]
+        assert lm[i].shape == want.shape, (i, lm[i].shape, want.shape)
+        assert np.allclose(lm[i], want, rtol=1e-9, atol=1e-9)
+        assert np.array_equal(np.abs(lm[i]).sum(1) == 0, np.abs(want).sum(1) == 0)      # the same zero rows
+    assert sum(len(a) for a in lm) >= 10
+    # geometric frames: real parallax, features entering the view every frame
+    import os
+    pytest.importorskip("cv2")
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "kitti00_reference_data.npz"))
+    gt = np.tile(np.eye(4), (5, 1, 1)); gt[:, :3, :] = d["poses"][40:45]
+    left, right = synth.street_sequence(gt, seed=7, workers=1)
+    g = vo.VisualOdometry(synth.KITTI_P0, synth.KITTI_P1, vo.CudaOps(ctx=ctx, seed=2), view_3D=True)
+    sizes = [0]
+    for i in range(5):
+        g.step(left[i], right[i]); sizes.append(len(g.landmarks))
+    rel, status, counts = vo.run_frames(left, right, synth.KITTI_P0, synth.KITTI_P1, seed=2, ctx=ctx)
+    lm = vo.frames_landmarks(np.array([np.eye(4)] + vo.chain_poses(rel[1:])), cap=8192, ctx=ctx)
+    for i in range(5):
+        want = g.landmarks[sizes[i]:sizes[i + 1]]
+        assert lm[i].shape == want.shape and np.allclose(lm[i], want, rtol=1e-9, atol=1e-9)
+    nz = np.concatenate(lm); nz = nz[np.abs(nz).sum(1) > 0]
+    assert len(nz) > 100                                                          # real new landmarks, in front of the rig
+    # error paths
+    import vo_b200
+    c2 = vo_b200.Context(0)
+    with pytest.raises(vo_b200.VoError, match="no vo_frames call"):
+        vo.frames_landmarks(poses, ctx=c2)
+    c2.close()
+    with pytest.raises(vo_b200.VoError, match="n_frames differs"):
+        vo.frames_landmarks(poses[:3], ctx=ctx)
