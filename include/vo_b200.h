@@ -207,7 +207,8 @@ typedef struct {
  * rel_pose[16*i] = rel_pose.A of frame i (row-major; identity for i = 0), status[i] = estworldpose
  * status (0 ok, 1 too few points, 2 too few inliers),
  * counts[8*i..] = {N_L, N_R, K0 (stereo), K1, K2, K3, K4 (tracked), inliers}  (may be NULL).
- * opts->match.unique must be 0 (VO.m never sets Unique; VO_ERR_ARG otherwise -- use vo_match for it).
+ * opts->match.unique = 1 applies Unique (forward-backward consistency) to all five matchFeatures calls (VO.m never
+ * sets it; every match then also runs in the reverse direction).
  * The pose chain pose = pose * rel_pose (VO.m:130) is left to the caller: it is sequential.
  * To stream a long sequence call with overlapping batches [i0-1, i0+B). */
 int vo_frames(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_frames, int rows,

@@ -70,11 +70,10 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
                        int* status, int* counts) {
   VO_CHECK_ARG(ctx && left && right && P1 && P2 && rel_pose && status, "null argument");
   VO_CHECK_ARG(n >= 1 && rows > 0 && cols > 0, "bad size");
-  VO_CHECK_ARG(!(opts && opts->match.unique), "vo_frames: match.unique is not supported by the batched loop (VO.m never sets Unique); use vo_match");
   VO_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   vo_match_opts mo; fill_match_opts(opts ? &opts->match : nullptr, &mo);
-  mo.index_base = 0; mo.unique = 0;
+  mo.index_base = 0;
   vo_p3p_opts po; fill_p3p_opts(opts ? &opts->p3p : nullptr, &po);
   const int want_cap = (opts && opts->max_keypoints > 0) ? opts->max_keypoints : 8192;
   const int first_frame = opts ? opts->first_frame : 0;
@@ -113,13 +112,18 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
   auto gath_op = [&](int first_img, const uint32_t* g, const int* c) {
     MatchOperand o = raw_op(first_img); o.gather = g; o.gather_stride = kc; o.count = c; o.count_stride = 1; return o;
   };
-  MatchTop2 t;
+  MatchTop2 t, tb;
   const MatchFilter mflt = make_match_filter(mo);
+  // matchFeatures(A, B) of VO.m for a batch of problems; with Unique also the reversed problems (B, A)
+  auto match = [&](const MatchOperand& A, const MatchOperand& B, int nprob, uint32_t* i1, uint32_t* i2, int* npairs) -> int {
+    VO_TRY(match_batch_top2(ctx, A, B, nprob, 128, "fr", nullptr, st, &t, &mflt));
+    if (mo.unique) VO_TRY(match_batch_top2(ctx, B, A, nprob, 128, "frb", nullptr, st, &tb, &mflt));
+    return match_batch_select(ctx, t, A, B, nprob, mo, i1, i2, nullptr, kc, npairs, 1, st, mo.unique ? &tb : nullptr);
+  };
   // matched = matchFeatures(l_desc, r_desc)                                      VO.m:87
   {
     MatchOperand A = raw_op(0), B = raw_op(1);
-    VO_TRY(match_batch_top2(ctx, A, B, n, 128, "fr", nullptr, st, &t, &mflt));
-    VO_TRY(match_batch_select(ctx, t, A, B, n, mo, l0, r0, nullptr, kc, K, 1, st));
+    VO_TRY(match(A, B, n, l0, r0, K));
   }
   const int np = n - 1;
   const dim3 cg(8, np > 0 ? np : 1);
@@ -127,31 +131,27 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
     // M1 = matchFeatures(cur.l_desc, old.l_desc)                                 VO.m:283
     {
       MatchOperand A = raw_op(2), B = gath_op(0, l0, K);
-      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t, &mflt));
-      VO_TRY(match_batch_select(ctx, t, A, B, np, mo, a1, b1, nullptr, kc, K + n, 1, st));
+      VO_TRY(match(A, B, np, a1, b1, K + n));
       compose_kernel<<<cg, 256, 0, st>>>(oL1, l0, oR1, r0, b1, K + n, kc);            // VO.m:287-290
       ctx->kernel_launches += 6;   // 5 compose launches + gather_points below
     }
     // M2 = matchFeatures(cur.r_desc, old.r_desc)                                 VO.m:293
     {
       MatchOperand A = raw_op(3), B = gath_op(1, oR1, K + n);
-      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t, &mflt));
-      VO_TRY(match_batch_select(ctx, t, A, B, np, mo, a2, b2, nullptr, kc, K + 2 * n, 1, st));
+      VO_TRY(match(A, B, np, a2, b2, K + 2 * n));
       compose_kernel<<<cg, 256, 0, st>>>(oL2, oL1, oR2, oR1, b2, K + 2 * n, kc);      // VO.m:297-300
     }
     // M3 = matchFeatures(cur.l_desc(M1(:,1)), cur.r_desc(M2(:,1)))               VO.m:305-311
     {
       MatchOperand A = gath_op(2, a1, K + n), B = gath_op(3, a2, K + 2 * n);
-      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t, &mflt));
-      VO_TRY(match_batch_select(ctx, t, A, B, np, mo, a3, b3, nullptr, kc, K + 3 * n, 1, st));
+      VO_TRY(match(A, B, np, a3, b3, K + 3 * n));
       compose_kernel<<<cg, 256, 0, st>>>(cL3, a1, nullptr, nullptr, a3, K + 3 * n, kc);  // VO.m:314-315
       compose_kernel<<<cg, 256, 0, st>>>(cR3, a2, nullptr, nullptr, b3, K + 3 * n, kc);  // VO.m:316-317
     }
     // M4 = matchFeatures(cur.l_desc, old.l_desc)                                 VO.m:323
     {
       MatchOperand A = gath_op(2, cL3, K + 3 * n), B = gath_op(0, oL2, K + 2 * n);
-      VO_TRY(match_batch_top2(ctx, A, B, np, 128, "fr", nullptr, st, &t, &mflt));
-      VO_TRY(match_batch_select(ctx, t, A, B, np, mo, a4, b4, nullptr, kc, K + 4 * n, 1, st));
+      VO_TRY(match(A, B, np, a4, b4, K + 4 * n));
     }
   }
   // triangulate the old pair (VO.m:114) and estimate the pose (VO.m:123-127)

@@ -1532,7 +1532,8 @@ match_select_block_kernel(const uint32_t* __restrict__ j1, const float* __restri
                           int row_stride, const int* __restrict__ n1p, int n1_stride, int cap1,
                           const int* __restrict__ n2p, int n2_stride, int cap2, float thr, float max_ratio,
                           int index_base, uint32_t* __restrict__ idx1, uint32_t* __restrict__ idx2,
-                          float* __restrict__ metric, int out_stride, int* __restrict__ n_pairs, int np_stride) {
+                          float* __restrict__ metric, int out_stride, int* __restrict__ n_pairs, int np_stride,
+                          const uint32_t* __restrict__ back_j1, int back_stride) {
   __shared__ int warp_sums[32];
   __shared__ int carry;
   const int prob = blockIdx.x;
@@ -1543,7 +1544,9 @@ match_select_block_kernel(const uint32_t* __restrict__ j1, const float* __restri
   for (int base = 0; base < n1 && n2 > 0; base += 1024) {
     const int i = base + threadIdx.x;
     const size_t row = (size_t)prob * row_stride + i;
-    const bool keep = (i < n1) && keep_row(s1[row], s2[row], n2, thr, max_ratio);
+    bool keep = (i < n1) && keep_row(s1[row], s2[row], n2, thr, max_ratio);
+    // Unique: the landmark's own nearest query row must be this row (forward-backward consistency)
+    if (keep && back_j1 != nullptr) keep = back_j1[(size_t)prob * back_stride + j1[row]] == (uint32_t)i;
     const unsigned ballot = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) warp_sums[w] = __popc(ballot);
     __syncthreads();
@@ -1909,14 +1912,15 @@ void fill_match_opts(const vo_match_opts* in, vo_match_opts* o) {
 
 int match_batch_select(vo_ctx* ctx, const MatchTop2& t, const MatchOperand& A, const MatchOperand& B, int n_prob,
                        const vo_match_opts& o, uint32_t* idx1, uint32_t* idx2, float* metric, int out_stride,
-                       int* n_pairs, int np_stride, cudaStream_t st) {
+                       int* n_pairs, int np_stride, cudaStream_t st, const MatchTop2* back) {
   (void)ctx;
   if (n_prob <= 0) return VO_OK;
   const float thr = o.match_threshold * 0.04f;
   ProfScope ps(ctx, st, "match_select");
   match_select_block_kernel<<<n_prob, 1024, 0, st>>>(t.j1, t.s1, t.s2, t.row_stride, A.count, A.count_stride, A.cap, B.count,
                                                      B.count_stride, B.cap, thr, o.max_ratio, o.index_base, idx1, idx2, metric,
-                                                     out_stride, n_pairs, np_stride);
+                                                     out_stride, n_pairs, np_stride, back ? back->j1 : nullptr,
+                                                     back ? back->row_stride : 0);
   VO_CUDA(cudaGetLastError());
   return VO_OK;
 }

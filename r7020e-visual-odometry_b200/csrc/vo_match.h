@@ -40,10 +40,11 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
                      const MatchFilter* filter = nullptr);
 
 // threshold / ratio tests + ordered compaction, one block per problem.
-// idx1/idx2/metric: [n_prob][out_stride]; n_pairs[p*np_stride].
+// idx1/idx2/metric: [n_prob][out_stride]; n_pairs[p*np_stride].  back (Unique): the top-2 of the reversed problems
+// (match_batch_top2(B, A) under a different tag); a row is kept only if its landmark's nearest query row is that row.
 int match_batch_select(vo_ctx* ctx, const MatchTop2& t, const MatchOperand& A, const MatchOperand& B, int n_prob,
                        const vo_match_opts& o, uint32_t* idx1, uint32_t* idx2, float* metric, int out_stride,
-                       int* n_pairs, int np_stride, cudaStream_t st);
+                       int* n_pairs, int np_stride, cudaStream_t st, const MatchTop2* back = nullptr);
 
 void fill_match_opts(const vo_match_opts* in, vo_match_opts* o);
 }  // namespace vo

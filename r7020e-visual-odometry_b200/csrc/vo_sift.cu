@@ -295,8 +295,14 @@ __device__ __forceinline__ u64 f2_bcast(float k) { const float2 v = make_float2(
 // leaves a single __syncthreads per chunk.
 constexpr int TS_W = 128, TS_G = 16, TS_HALO = 16, TS_BOXW = TS_W + 2 * TS_HALO;   // 160-float box rows
 __host__ __device__ constexpr int TS_MIRROR(int r) { return 3 + 2 * r; }
-template <int R>
-__global__ void __launch_bounds__(256, 3)
+// PACK: the row pass runs on packed f32x2 too.  A lane's four outputs are the pairs (c, c+1) and (c+2, c+3); the tap
+// pairs (in[c+d], in[c+d+1]) are 8-byte aligned in the stage for even d only, so each warp first writes a copy of its
+// row shifted by one column (three shared-memory instructions per lane), where the odd-d pairs are aligned.  (A second
+// TMA box from x0 - 15 cannot do that: a tiled TMA load whose innermost start is not 16-byte aligned faults.)  2R + 1
+// packed operations per output pair instead of 2(2R + 1) scalar ones; each f32x2 lane is an IEEE fmaf / add, so the
+// bits do not change.
+template <int R, bool PACK>
+__global__ void __launch_bounds__(256, PACK ? 2 : 3)
 sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* __restrict__ dst,
                      float* __restrict__ dog, const float* __restrict__ src, int h, int w, int pitch,
                      int seg_rows, const Taps taps) {
@@ -305,9 +311,11 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
   // column window reads are always contiguous in shared memory (one base address, immediate offsets)
   constexpr int RING = 64, MIRROR = TS_MIRROR(R);
   extern __shared__ __align__(128) uint8_t tsm[];      // > 48 KB: dynamic shared memory (opt-in)
+  constexpr int SROW_BYTES = PACK ? 8 * TS_BOXW * 4 : 0;   // PACK: one shifted row per warp
   float (*stage)[TS_G][TS_BOXW] = reinterpret_cast<float (*)[TS_G][TS_BOXW]>(tsm);                        // [2]
-  float (*ring)[TS_W] = reinterpret_cast<float (*)[TS_W]>(tsm + 2 * TS_G * TS_BOXW * 4);                   // [RING + MIRROR]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(tsm + 2 * TS_G * TS_BOXW * 4 + (RING + MIRROR) * TS_W * 4);
+  float (*srow)[TS_BOXW] = reinterpret_cast<float (*)[TS_BOXW]>(tsm + 2 * TS_G * TS_BOXW * 4);            // [8]
+  float (*ring)[TS_W] = reinterpret_cast<float (*)[TS_W]>(tsm + 2 * TS_G * TS_BOXW * 4 + SROW_BYTES);      // [RING + MIRROR]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(tsm + 2 * TS_G * TS_BOXW * 4 + SROW_BYTES + (RING + MIRROR) * TS_W * 4);
   const int b = blockIdx.z;
   const int x0 = blockIdx.x * TS_W;
   const int ys = blockIdx.y * seg_rows, ye = min(ys + seg_rows, h);
@@ -356,6 +364,46 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
     for (int rr = wrp; rr < TS_G; rr += 8) {
       const int row = row0 + rr;
       if (row < 0 || row >= h || row < ys - R) continue;        // warp-uniform
+      const int slot = row & (RING - 1);
+      if constexpr (PACK) {
+        // tap pair T(d) = (in[c+d], in[c+d+1]), c = 4*lane: even d from the plain stage, odd d from the shifted one
+        __syncwarp();                                            // the previous row's reads of srow are done
+#pragma unroll
+        for (int q = lane; q < TS_BOXW / 4; q += 32) {           // srow[x] = row[x + 1]
+          const float4 v = *reinterpret_cast<const float4*>(&sg[rr][4 * q]);
+          const float e = 4 * q + 4 < TS_BOXW ? sg[rr][4 * q + 4] : 0.f;
+          *reinterpret_cast<float4*>(&srow[wrp][4 * q]) = make_float4(v.y, v.z, v.w, e);
+        }
+        __syncwarp();
+        const float* pe = &sg[rr][TS_HALO + 4 * lane];
+        const float* po = &srow[wrp][TS_HALO + 4 * lane];
+        constexpr int QE0 = -((R - (R & 1) + 3) / 4), QE1 = (R + 2) / 4;          // float4 at 4q holds T(4q), T(4q+2):   d in [-R, R+2]
+        constexpr int QO0 = -((R - 1 + (R & 1) + 4) / 4), QO1 = (R + 1) / 4;      // float4 at 4q holds T(4q+1), T(4q+3)
+        u64 te[2 * (QE1 - QE0 + 1)], to[2 * (QO1 - QO0 + 1)];
+#pragma unroll
+        for (int q = QE0; q <= QE1; ++q) {
+          const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(pe + 4 * q);
+          te[2 * (q - QE0)] = v.x; te[2 * (q - QE0) + 1] = v.y;
+        }
+#pragma unroll
+        for (int q = QO0; q <= QO1; ++q) {
+          const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(po + 4 * q);
+          to[2 * (q - QO0)] = v.x; to[2 * (q - QO0) + 1] = v.y;
+        }
+        // T(d): d even -> te[(d - 4*QE0) / 2], d odd -> to[(d - 1 - 4*QO0) / 2]
+        auto T = [&](int d) -> u64 { return (d & 1) ? to[(d - 1 - 4 * QO0) / 2] : te[(d - 4 * QE0) / 2]; };
+        const u64 k0 = f2_bcast(taps.k[0]);
+        u64 a0 = f2_mul(k0, T(0)), a1 = f2_mul(k0, T(2));
+#pragma unroll
+        for (int i = 1; i <= R; ++i) {
+          const u64 ki = f2_bcast(taps.k[i]);
+          a0 = f2_fma(ki, f2_add(T(-i), T(i)), a0);
+          a1 = f2_fma(ki, f2_add(T(2 - i), T(2 + i)), a1);
+        }
+        const ulonglong2 o2 = make_ulonglong2(a0, a1);
+        *reinterpret_cast<ulonglong2*>(&ring[slot][4 * lane]) = o2;
+        if (slot < MIRROR) *reinterpret_cast<ulonglong2*>(&ring[RING + slot][4 * lane]) = o2;   // warp-uniform
+      } else {
       const float* p = &sg[rr][4 * lane];                       // box col 0 <-> x0 - 16
       constexpr int Q0 = (TS_HALO - R) / 4, Q1 = (TS_HALO + 4 + R + 3) / 4;   // float4s that hold needed taps
       float win[4 * (Q1 - Q0)];
@@ -373,10 +421,10 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
 #pragma unroll
         for (int o = 0; o < 4; ++o) acc[o] = fmaf(taps.k[i], win[C + o - i] + win[C + o + i], acc[o]);
       }
-      const int slot = row & (RING - 1);
       const float4 o4 = make_float4(acc[0], acc[1], acc[2], acc[3]);
       *reinterpret_cast<float4*>(&ring[slot][4 * lane]) = o4;
       if (slot < MIRROR) *reinterpret_cast<float4*>(&ring[RING + slot][4 * lane]) = o4;   // warp-uniform
+      }
     }
   };
 
@@ -1341,8 +1389,8 @@ static int launch_blur_t(const float* src, const uint8_t* src8, float* dst, floa
   return VO_OK;
 }
 
-template <int R>
-static int launch_tma_t(const CUtensorMap& tm, int z_base, const float* src, float* dst, float* dog, int h, int w, int pitch,
+template <int R, bool PACK>
+static int launch_tma_t2(const CUtensorMap& tm, int z_base, const float* src, float* dst, float* dog, int h, int w, int pitch,
                         int batch, const Taps& t, int num_sms, cudaStream_t st) {
   const int strips = div_up(w, TS_W);
   int n_seg = 1;
@@ -1352,10 +1400,19 @@ static int launch_tma_t(const CUtensorMap& tm, int z_base, const float* src, flo
   if (seg_rows < 4 * TS_G) seg_rows = 4 * TS_G;
   n_seg = div_up(h, seg_rows);
   dim3 grid(strips, n_seg, batch);
-  constexpr int smem = 2 * TS_G * TS_BOXW * 4 + (64 + TS_MIRROR(R)) * TS_W * 4 + 64;
-  VO_TRY(ensure_dyn_smem_of(sift_blur_tma_kernel<R>, smem));
-  sift_blur_tma_kernel<R><<<grid, 256, smem, st>>>(tm, z_base, dst, dog, src, h, w, pitch, seg_rows, t);
+  constexpr int smem = 2 * TS_G * TS_BOXW * 4 + (PACK ? 8 * TS_BOXW * 4 : 0) + (64 + TS_MIRROR(R)) * TS_W * 4 + 64;
+  VO_TRY(ensure_dyn_smem_of(sift_blur_tma_kernel<R, PACK>, smem));
+  sift_blur_tma_kernel<R, PACK><<<grid, 256, smem, st>>>(tm, z_base, dst, dog, src, h, w, pitch, seg_rows, t);
   return VO_OK;
+}
+// VO_BLUR_PACK=1 selects the packed row pass (measured slower: 3.27 vs 2.45 ms per step -- the kernel is bound by
+// shared-memory bandwidth, and the packed form reads 60 B/px in the row pass instead of 36; kept for A/B runs)
+template <int R>
+static int launch_tma_t(const CUtensorMap& tm, int z_base, const float* src, float* dst, float* dog, int h, int w, int pitch,
+                        int batch, const Taps& t, int num_sms, cudaStream_t st) {
+  static const bool pack = [] { const char* e = getenv("VO_BLUR_PACK"); return e ? atoi(e) != 0 : false; }();
+  return pack ? launch_tma_t2<R, true>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st)
+              : launch_tma_t2<R, false>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
 }
 
 // tm/z_base: tensor map of the octave's Gaussian stack and the z index of image 0 of the source layer

@@ -22,10 +22,11 @@ from ._lib import check
 class CudaOps:
     """The toolbox calls of VO.m bound to libvo_b200 (no CPU fallback)."""
 
-    def __init__(self, ctx=None, seed=0, capacity=16384):
+    def __init__(self, ctx=None, seed=0, capacity=16384, Unique=False):
         self.ctx = ctx or api.default_context()
         self.seed = seed
         self.capacity = capacity
+        self.Unique = Unique
 
     def detect_and_extract(self, img):
         pts = api.detectSIFTFeatures(img, index_base=1, capacity=self.capacity, ctx=self.ctx)
@@ -33,7 +34,7 @@ class CudaOps:
         return feats, pts.Location
 
     def matchFeatures(self, f1, f2):
-        return api.matchFeatures(f1, f2, ctx=self.ctx)
+        return api.matchFeatures(f1, f2, Unique=self.Unique, ctx=self.ctx)
 
     def triangulate(self, p1, p2, P1, P2):
         return api.triangulate(np.asarray(p1, np.float64), np.asarray(p2, np.float64), P1, P2, ctx=self.ctx)
@@ -148,7 +149,8 @@ class VisualOdometry:
         return rel
 
 
-def run_frames(left, right, P1, P2, seed=0, first_frame=0, max_keypoints=8192, ctx=None, device_ptrs=None, col_major=False):
+def run_frames(left, right, P1, P2, seed=0, first_frame=0, max_keypoints=8192, ctx=None, device_ptrs=None, col_major=False,
+               Unique=False):
     """Batched device-resident loop body (vo_frames).  left/right: [n, rows, cols] uint8 host
     arrays (NumPy, or pinned torch CPU tensors via .numpy()).  With ``device_ptrs=(lptr, rptr,
     n, rows, cols)`` the images are already in HBM (vo_frames_dev) and left/right are ignored.
@@ -172,6 +174,7 @@ def run_frames(left, right, P1, P2, seed=0, first_frame=0, max_keypoints=8192, c
     o.max_keypoints = max_keypoints
     o.first_frame = first_frame
     o.col_major = 1 if col_major else 0
+    o.match.unique = 1 if Unique else 0          # matchFeatures(..., "Unique", true) in all five calls of the loop
     rel = np.zeros((n, 4, 4))
     status = np.zeros(n, dtype=np.int32)
     counts = np.zeros((n, 8), dtype=np.int32)

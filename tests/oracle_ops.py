@@ -6,8 +6,9 @@ from oracle import oracle
 
 
 class OracleOps:
-    def __init__(self, seed=0):
+    def __init__(self, seed=0, unique=False):
         self.seed = seed
+        self.unique = unique
 
     def detect_and_extract(self, img):
         kps, desc = oracle.sift(img)
@@ -15,7 +16,7 @@ class OracleOps:
         return desc, loc
 
     def matchFeatures(self, f1, f2):
-        return oracle.match(f1, f2)[0]
+        return oracle.match(f1, f2, unique=self.unique)[0]
 
     def triangulate(self, p1, p2, P1, P2):
         return oracle.triangulate(np.asarray(p1, np.float64), np.asarray(p2, np.float64), P1, P2)[0]

@@ -224,3 +224,21 @@ def test_landmark_map_on_device_equals_the_loop_mirror(ctx):
     c2.close()
     with pytest.raises(vo_b200.VoError, match="n_frames differs"):
         vo.frames_landmarks(poses[:3], ctx=ctx)
+
+
+def test_vo_frames_with_unique_matches(ctx):
+    """SURVEY 8f N4 tail: matchFeatures(..., "Unique", true) inside the batched loop (every match also runs in the
+    reverse direction on the device) equals the loop mirror with Unique matches, GPU and oracle."""
+    from vo_b200 import vo, synth
+    left, right = _frames(4, seed=23)
+    rel, status, counts = vo.run_frames(left, right, synth.KITTI_P0, synth.KITTI_P1, seed=3, ctx=ctx, Unique=True)
+    plain = vo.run_frames(left, right, synth.KITTI_P0, synth.KITTI_P1, seed=3, ctx=ctx)
+    assert (status == 0).all() and (counts[:, 2] <= plain[2][:, 2]).all() and (counts[1:, 6] > 30).all()
+    g = vo.VisualOdometry(synth.KITTI_P0, synth.KITTI_P1, vo.CudaOps(ctx=ctx, seed=3, Unique=True))
+    o = vo.VisualOdometry(synth.KITTI_P0, synth.KITTI_P1, OracleOps(seed=3, unique=True))
+    for i in range(4):
+        a = g.step(left[i], right[i]); b = o.step(left[i], right[i])
+        if i:
+            assert np.array_equal(a, rel[i]) and np.allclose(a, b, atol=1e-9)
+            assert [g.log[i][k] for k in ("k0", "k1", "k2", "k3", "k4")] == counts[i, 2:7].tolist()
+            assert [o.log[i][k] for k in ("k0", "k1", "k2", "k3", "k4")] == counts[i, 2:7].tolist()
