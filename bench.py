@@ -77,6 +77,12 @@ CONFIG = dict(workload="VO.m loop body (VO.m:64-232) on 1241x376 stereo frames o
               rows=H, cols=W, halo_frames=1, sequence="synth.StreetWorld(seed=7), frames 0..n of kitti/poses/00.txt")
 
 
+# Measured on B200 with tools/ubench_tmem.cu (profiles/r1_ubench_tmem.txt): back-to-back tcgen05.mma.kind::i8,
+# cta_group::1, M = 128, N = 256, K = 32 with both operands in shared memory take 171.2 cycles (ideal 128), i.e.
+# 2*128*256*32 / 171.2 op per cycle and SM x 148 SMs x 1.965 GHz.  The only measured peak of the pipe the match uses.
+I8_MMA_RATE_TOPS = 2 * 128 * 256 * 32 / 171.2 * 148 * 1.965e9 / 1e12
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -387,7 +393,7 @@ def match_gemm_leg(ctx, torch, pk, check=True):
                 t_call = e0.elapsed_time(e1) / reps
                 d = dict(kernel_ms=1e3 * t_kernel, call_ms=t_call, tflops=tf, call_tflops=flops / (t_call * 1e-3) / 1e12,
                          frac_of_burst_peak=tf / pk["tf_burst"], frac_of_sustained_peak=tf / pk["tf_sust"],
-                         frac_of_2x_burst_peak=tf / (2 * pk["tf_burst"]))
+                         frac_of_2x_burst_peak=tf / (2 * pk["tf_burst"]), frac_of_measured_i8_mma_rate=tf / I8_MMA_RATE_TOPS)
                 if mode == "match":
                     d["pairs"] = int(npairs.item())
                     rec.update(d)
@@ -414,7 +420,7 @@ def match_gemm_leg(ctx, torch, pk, check=True):
     head = [d for d in ints if d["n1"] == 32768][0]
     return dict(head, sweep=out, parity_all_bit_exact=all_ok if check else None, best_tflops=best["tflops"],
                 best_frac_of_burst_peak=best["frac_of_burst_peak"], peak_tflops_burst=pk["tf_burst"],
-                peak_tflops_sustained=pk["tf_sust"], peak_source=pk["src"],
+                peak_tflops_sustained=pk["tf_sust"], peak_source=pk["src"], measured_i8_mma_rate_tops=I8_MMA_RATE_TOPS,
                 path="integer / ties: u8 x u8 -> s32 tcgen05.mma.kind::i8 (exact integer dot, K = 128), fused integer-prefilter "
                      "top-3 epilogue, no C written; float: split-bf16 kind::f16 GEMM + exact FP32 re-rank; ops counted as "
                      "2*N1*N2*128; peaks are the measured bf16 cuBLAS figures (the int8 pipe's nominal peak is 2x bf16: "

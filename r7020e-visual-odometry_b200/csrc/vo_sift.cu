@@ -51,6 +51,7 @@ struct SiftPlan {
   uint8_t* img_t = nullptr;     // staging for column-major input
   Taps taps[8]; Taps base_taps;
   CUtensorMap tm_gauss[MAX_OCT];   // {w, h, layer*batch} view of every octave's Gaussian stack (blur input via TMA)
+  CUtensorMap tm_dog[MAX_OCT];     // the same view of the DoG stack, box {256, 4, 1} (extrema input via TMA)
   int cand_cap = 0, kp_cap = 0;
   uint32_t* cand = nullptr; int* counters = nullptr;   // counters[b*4 + {0:cand,1:raw kp,2:final}]
   vo_keypoint* raw = nullptr; vo_keypoint* sorted = nullptr; vo_keypoint* final_kp = nullptr;
@@ -700,7 +701,7 @@ constexpr int EX_COLS = 30, EX_ROWS = 32;
 template <int NL>
 __global__ void __launch_bounds__(128)
 sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int batch, int h, int w, int pitch,
-                    float threshold, uint32_t* __restrict__ cand, int cand_cap, int* __restrict__ counters) {
+                    float threshold, uint32_t* __restrict__ cand, int cand_cap, int* __restrict__ counters, int pf_rows) {
   constexpr int L = NL + 2;
   const int lane = threadIdx.x & 31;
   const int strip = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -734,6 +735,13 @@ sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int batch, int h
       const size_t off = (size_t)min(max(r + 1, 0), h - 1) * pitch;
 #pragma unroll
       for (int l = 0; l < L; ++l) nxt[l] = __ldg(img + (size_t)l * layer_stride + off);
+      // the rows further down are pulled into L2 now (no registers held): the loads above then see L2 latency, not HBM's.
+      // Lanes 0 and 31 touch the two 128-byte lines a warp's row segment can straddle.
+      if (pf_rows > 0 && (lane == 0 || lane == 31) && r + 1 + pf_rows < y_end + 1) {
+        const size_t offp = (size_t)min(r + 1 + pf_rows, h - 1) * pitch;
+#pragma unroll
+        for (int l = 0; l < L; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(img + (size_t)l * layer_stride + offp));
+      }
     }
 #pragma unroll
     for (int l = 0; l < L; ++l) {
@@ -772,6 +780,112 @@ sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int batch, int h
         }
       }
     }
+  }
+}
+
+// TMA-fed form for the wide octaves (an experiment kept behind VO_EXT_TMA=1, bit-identical results).  The register
+// form above keeps only one row per layer in flight per warp (about 20 KB per SM) and runs at 48 % of the HBM
+// roofline, so the question was whether it starves for bytes in flight.  Here a block of 8 warps walks a strip of 240
+// columns down a row segment and the DoG rows arrive through cp.async.bulk.tensor in groups of 4 rows x (NL + 2)
+// layers x 256 columns (20 KB), three groups deep: 40 KB per block and 120 KB per SM in flight without holding a
+// register.  Measured: 1.26 ms per step against 1.03 ms (ncu: same 1.5e8 warp instructions, issue-active 63 % against
+// 71 %, top stalls wait + barrier instead of long_scoreboard): the test is bound by instruction issue, not by memory
+// parallelism -- as were a second row in registers, per-lane cp.async rings (round 1) and L2 prefetches (VO_EXT_PF).
+// Out-of-image halo columns / rows are zero-filled by TMA and only ever feed windows of border pixels, which cannot
+// be keypoints.
+constexpr int XT_WARPS = 8, XT_COLS = XT_WARPS * EX_COLS, XT_BOXW = 256, XT_G = 4, XT_NST = 3;
+template <int NL>
+__global__ void __launch_bounds__(XT_WARPS * 32, 3)
+sift_extrema_tma_kernel(const __grid_constant__ CUtensorMap tm, int oct, int batch_stride, int h, int w, int seg_rows,
+                        float threshold, uint32_t* __restrict__ cand, int cand_cap, int* __restrict__ counters) {
+  constexpr int L = NL + 2;
+  extern __shared__ __align__(128) uint8_t xsm[];
+  float (*stage)[L][XT_G][XT_BOXW] = reinterpret_cast<float (*)[L][XT_G][XT_BOXW]>(xsm);     // [XT_NST]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(xsm + XT_NST * L * XT_G * XT_BOXW * 4);
+  constexpr uint32_t GROUP_BYTES = L * XT_G * XT_BOXW * 4, LAYER_BYTES = XT_G * XT_BOXW * 4;
+  const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+  const int b = blockIdx.z;
+  const int xs = blockIdx.x * XT_COLS;
+  const int ys = max(blockIdx.y * seg_rows, SIFT_BORDER), ye = min((blockIdx.y + 1) * seg_rows, h - SIFT_BORDER);
+  if (ys >= ye) return;                                   // block-uniform
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  const uint32_t stage0 = smem_u32(&stage[0][0][0][0]);
+  if (tid == 0) {
+    for (int k = 0; k < XT_NST; ++k) mbar_init(bar0 + 8 * k, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // group g = rows [ys - 1 + XT_G * g, ys - 1 + XT_G * (g + 1)); rows ys - 1 .. ye are needed
+  const int n_groups = (ye - ys + 2 + XT_G - 1) / XT_G;
+  auto issue = [&](int g) {   // one thread
+    const int slot = g % XT_NST;
+    const uint32_t bar = bar0 + 8 * slot;
+    mbar_expect_tx(bar, GROUP_BYTES);
+#pragma unroll
+    for (int l = 0; l < L; ++l)
+      tma_load_3d(stage0 + slot * GROUP_BYTES + l * LAYER_BYTES, &tm, bar, xs - 4, ys - 1 + XT_G * g, l * batch_stride + b);
+  };
+  if (tid == 0)
+    for (int g = 0; g < XT_NST && g < n_groups; ++g) issue(g);
+  const int x = xs - 1 + EX_COLS * wq + lane;             // global column of this lane (lanes 0 and 31 are halo)
+  const int bc = 3 + EX_COLS * wq + lane;                 // its column inside the box (box column 0 <-> xs - 4)
+  const bool col_ok = lane >= 1 && lane <= EX_COLS && x >= SIFT_BORDER && x < w - SIFT_BORDER;
+  const bool warp_on = xs + EX_COLS * wq < w;             // warp-uniform: this warp's strip holds image columns
+  float hxA[L], hxB[L], hxC[L], hnA[L], hnB[L], hnC[L], cB[L], cC[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) { hxA[l] = hxB[l] = hxC[l] = hnA[l] = hnB[l] = hnC[l] = cB[l] = cC[l] = 0.f; }
+  for (int g = 0; g < n_groups; ++g) {
+    const int slot = g % XT_NST;
+    mbar_wait(bar0 + 8 * slot, (uint32_t)((g / XT_NST) & 1));
+    if (warp_on) {
+#pragma unroll
+      for (int rr = 0; rr < XT_G; ++rr) {
+        const int r = ys - 1 + XT_G * g + rr;             // the row now entering the window
+        if (r > ye) break;                                // block-uniform
+        float v[L];
+#pragma unroll
+        for (int l = 0; l < L; ++l) v[l] = stage[slot][l][rr][bc];
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          const float lf = __shfl_up_sync(0xffffffffu, v[l], 1), rt = __shfl_down_sync(0xffffffffu, v[l], 1);
+          hxA[l] = hxB[l]; hxB[l] = hxC[l]; hnA[l] = hnB[l]; hnB[l] = hnC[l]; cB[l] = cC[l];
+          hxC[l] = fmaxf(fmaxf(lf, v[l]), rt);
+          hnC[l] = fminf(fminf(lf, v[l]), rt);
+          cC[l] = v[l];
+        }
+        const int y = r - 1;                              // the row whose 3x3 windows are now complete
+        if (y < ys) continue;                             // block-uniform (window warm-up)
+        float mx[L], mn[L];
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          mx[l] = fmaxf(fmaxf(hxA[l], hxB[l]), hxC[l]);
+          mn[l] = fminf(fminf(hnA[l], hnB[l]), hnC[l]);
+        }
+#pragma unroll
+        for (int layer = 1; layer <= NL; ++layer) {
+          const float val = cB[layer];
+          bool ext = false;
+          if (col_ok && fabsf(val) > threshold) {
+            if (val > 0) ext = val >= mx[layer - 1] && val >= mx[layer] && val >= mx[layer + 1];
+            else ext = val <= mn[layer - 1] && val <= mn[layer] && val <= mn[layer + 1];
+          }
+          const unsigned mask = __ballot_sync(0xffffffffu, ext);
+          if (mask) {
+            const int leader = __ffs(mask) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&counters[b * 4 + 0], __popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (ext) {
+              const int slot_c = base + __popc(mask & ((1u << lane) - 1u));
+              if (slot_c < cand_cap)
+                cand[(size_t)b * cand_cap + slot_c] = ((uint32_t)oct << 28) | ((uint32_t)layer << 25) | ((uint32_t)y << 13) | (uint32_t)x;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();                                      // every warp is done with this slot
+    if (tid == 0 && g + XT_NST < n_groups) issue(g + XT_NST);
   }
 }
 
@@ -1512,6 +1626,12 @@ static int get_plan(vo_ctx* ctx, int rows, int cols, int batch, const vo_sift_op
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { set_error("vo_sift: cuTensorMapEncodeTiled failed (%d) for octave %d", (int)r, oc); sift_plan_destroy(p); return VO_ERR_CUDA; }
+      cuuint64_t ddim[3] = {(cuuint64_t)p->w[oc], (cuuint64_t)p->h[oc], (cuuint64_t)(nl + 2) * batch};
+      cuuint32_t dbox[3] = {(cuuint32_t)XT_BOXW, (cuuint32_t)XT_G, 1};
+      r = enc(&p->tm_dog[oc], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)(p->dog + p->doff[oc]), ddim, gstr, dbox, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("vo_sift: cuTensorMapEncodeTiled failed (%d) for the DoG stack of octave %d", (int)r, oc); sift_plan_destroy(p); return VO_ERR_CUDA; }
     }
   }
   ctx->sift_plan = p; *out = p;
@@ -1581,7 +1701,25 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
     if (p->h[oc] <= 2 * SIFT_BORDER || p->w[oc] <= 2 * SIFT_BORDER) continue;
     dim3 g(div_up(div_up(p->w[oc], EX_COLS), 4), div_up(p->h[oc], EX_ROWS), batch);
     ProfScope ps(ctx, st, "sift_extrema", (double)batch * p->h[oc] * p->w[oc] * 4.0 * (nl + 2));
-#define VO_EXTREMA(NLV) sift_extrema_kernel<NLV><<<g, 128, 0, st>>>(p->D(oc, 0), oc, p->batch, p->h[oc], p->w[oc], p->pitch[oc], threshold, p->cand, p->cand_cap, p->counters)
+    // VO_EXT_TMA=1: the TMA-fed form (measured slower, 1.26 vs 1.03 ms per step: the test is bound by instruction issue,
+    // 71 % issue-active under ncu, not by bytes in flight; the block barriers of the staged form cost more than its loads save)
+    static const bool ext_tma = [] { const char* e = getenv("VO_EXT_TMA"); return e ? atoi(e) != 0 : false; }();
+    if (ext_tma && nl == 3 && p->w[oc] >= XT_COLS && p->h[oc] >= 64) {
+      // row segments: enough blocks for a few waves of 3 per SM, at least 64 rows each
+      const int strips = div_up(p->w[oc], XT_COLS);
+      int n_seg = div_up(ctx->num_sms * 3 * 3, strips * batch);
+      if (n_seg < 1) n_seg = 1;
+      int seg_rows = div_up(p->h[oc], n_seg);
+      if (seg_rows < 64) seg_rows = 64;
+      n_seg = div_up(p->h[oc], seg_rows);
+      constexpr int smem = XT_NST * 5 * XT_G * XT_BOXW * 4 + 64;
+      VO_TRY(ensure_dyn_smem_of(sift_extrema_tma_kernel<3>, smem));
+      sift_extrema_tma_kernel<3><<<dim3(strips, n_seg, batch), XT_WARPS * 32, smem, st>>>(p->tm_dog[oc], oc, p->batch, p->h[oc], p->w[oc], seg_rows,
+                                                                                       threshold, p->cand, p->cand_cap, p->counters);
+      continue;
+    }
+    static const int ext_pf = [] { const char* e = getenv("VO_EXT_PF"); return e ? atoi(e) : 0; }();
+#define VO_EXTREMA(NLV) sift_extrema_kernel<NLV><<<g, 128, 0, st>>>(p->D(oc, 0), oc, p->batch, p->h[oc], p->w[oc], p->pitch[oc], threshold, p->cand, p->cand_cap, p->counters, ext_pf)
     switch (nl) {
       case 1: VO_EXTREMA(1); break;
       case 2: VO_EXTREMA(2); break;

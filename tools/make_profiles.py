@@ -10,6 +10,8 @@ import csv, io, json, os, re, shutil, subprocess, sys
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(R, "gpurun_out"), os.path.join(R, "profiles")
 IMAGES = 36.0   # tools/prof_targets.py 8: 2 steps x 9 stereo frames
+RP = os.environ.get("VO_ROUND", "r2")          # file prefix of the round being written
+RN = RP[1:]
 
 STAGE_OF = [("sift_descriptor_kernel", "sift_descriptor"), ("sift_trig_kernel", "sift_descriptor"),
             ("sift_blur_tma_kernel", "sift_blur_tma_kernel"), ("sift_refine_kernel", "sift_refine_orient"), ("sift_orient_kernel", "sift_refine_orient"),
@@ -23,10 +25,10 @@ def run(*a):
 
 
 def launches():
-    src = os.path.join(G, "r1_launches_traffic.csv")
+    src = os.path.join(G, RP + "_launches_traffic.csv")
     if not os.path.exists(src):
         return
-    shutil.copy(src, os.path.join(P, "r1_launches_traffic.csv"))
+    shutil.copy(src, os.path.join(P, RP + "_launches_traffic.csv"))
     md = run(sys.executable, os.path.join(R, "tools", "launches_summary.py"), src)
     per_kernel = json.loads(run(sys.executable, os.path.join(R, "tools", "launches_summary.py"), src, str(IMAGES), "--json"))
     stage = {}
@@ -35,11 +37,11 @@ def launches():
             if k.startswith(pat):
                 stage[st] = stage.get(st, 0.0) + v
     json.dump({"source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, "
-                         "python tools/prof_targets.py 8 (2 steps x 9 stereo frames = 36 images of 1241x376), B200, round 1; "
+                         "python tools/prof_targets.py 8 (2 steps x 9 stereo frames = 36 images of 1241x376), B200, round " + RN + "; "
                          "dram__bytes_read.sum + dram__bytes_write.sum per image, launches grouped by bench.py stage",
-               "dram_bytes_per_image": stage}, open(os.path.join(P, "r1_traffic.json"), "w"), indent=1)
-    open(os.path.join(P, "r1_launches_summary.md"), "w").write(
-        "# Round 1 -- ncu launch list of `python tools/prof_targets.py 8`\n\n"
+               "dram_bytes_per_image": stage}, open(os.path.join(P, RP + "_traffic.json"), "w"), indent=1)
+    open(os.path.join(P, RP + "_launches_summary.md"), "w").write(
+        "# Round " + RN + " -- ncu launch list of `python tools/prof_targets.py 8`\n\n"
         "2 steps of `vo_frames_dev` on 9 stereo frames (18 images of 1241x376 per step) followed by two 32768 x 32768 x 128 "
         "exact top-2 matches.  `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none`. "
         "Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's live CUDA-event numbers.\n\n" + md)
@@ -55,7 +57,9 @@ def full(rep, out, title, cmd):
     cols = [("gpu__time_duration.sum", "time"), ("launch__grid_size", "grid"), ("launch__registers_per_thread", "regs"),
             ("dram__bytes_read.sum", "DRAM rd"), ("dram__bytes_write.sum", "DRAM wr"),
             ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"),
-            ("l1tex__throughput.avg.pct_of_peak_sustained_active", "L1 %"), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
+            ("l1tex__throughput.avg.pct_of_peak_sustained_active", "L1 %"),
+            ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem wavefronts %"),
+            ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
             ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps %"),
             ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"), ("smsp__inst_executed.sum", "warp inst")]
     stall = [h for h in H if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio")]
@@ -95,22 +99,22 @@ def opmix(rep, rx, out, which="0"):
 
 def bench_launches():
     """ncu launch list of bench.py itself, compared with the live stage shares of the same command run plain."""
-    src, plain = os.path.join(G, "r1_launches_bench.csv"), os.path.join(G, "bench_ll_plain.json")
+    src, plain = os.path.join(G, RP + "_launches_bench.csv"), os.path.join(G, "bench_ll_plain.json")
     if not (os.path.exists(src) and os.path.exists(plain)):
         return
-    shutil.copy(src, os.path.join(P, "r1_launches_bench.csv"))
+    shutil.copy(src, os.path.join(P, RP + "_launches_bench.csv"))
     md = run(sys.executable, os.path.join(R, "tools", "launches_summary.py"), src)
     live = json.load(open(plain))
     shares = "\n".join(f"| `{k}` | {100 * v:.1f} % |" for k, v in live["stage_share"].items())
-    open(os.path.join(P, "r1_launches_bench.md"), "w").write(
-        "# Round 1 -- ncu launch list of `bench.py` itself\n\n"
+    open(os.path.join(P, RP + "_launches_bench.md"), "w").write(
+        "# Round " + RN + " -- ncu launch list of `bench.py` itself\n\n"
         "`python bench.py --steps 3 --warmup 3 --no-cpu --quick` (exit 0 plain, then the same command under "
         "`ncu --metrics gpu__time_duration.sum --clock-control none --csv`): every kernel launch of the warm-up, the "
         "device-resident pass, the host-buffer (e2e) pass and the profiled serial pass -- 30 frame-loop steps of 33 stereo frames.  "
         "Times under ncu are cold-cache and serialised; the SHARES are what to compare with the live CUDA-event shares below.\n\n"
         + md + "\n## Live stage shares of the same command run without ncu (`stage_share` of its JSON line)\n\n"
         "| stage | share of the step |\n|---|---|\n" + shares + "\n\n"
-        f"Live: {live['value']:.0f} frames/s ({live['ms_per_step']:.2f} ms per step with {live['config']['batches_in_flight']} batches in flight, "
+        f"Live: {live['value']:.0f} frames/s ({live['ms_per_step']:.2f} ms per step with {live['run']['batches_in_flight']} batches in flight, "
         f"{live['ms_per_step_profiled_serial']:.2f} ms per step in the serial profiled pass).\n")
 
 
@@ -118,14 +122,12 @@ if __name__ == "__main__":
     os.makedirs(P, exist_ok=True)
     launches()
     bench_launches()
-    full("r1_sift2.ncu-rep", "r1_ncu_full_sift.md", "Round 1 -- ncu `--set full`: SIFT, sort, prep and geometry kernels of one frame-loop step (18 images of 1241x376)",
-         'ncu --set full --clock-control none --import-source on -k regex:"sift_descriptor_kernel|sift_refine_kernel|sift_orient_kernel|sift_extrema_kernel|sift_blur_tma_kernel|sift_base_stream|sift_small_oct|sift_rank_bucket" -c 33 python tools/prof_targets.py 8')
-    full("r1_match_u8.ncu-rep", "r1_ncu_full_match.md", "Round 1 -- ncu `--set full`: match_topk_u8_kernel, 32768 x 32768 x 128, matchFeatures mode",
+    full(RP + "_sift.ncu-rep", RP + "_ncu_full_sift.md", "Round " + RN + " -- ncu `--set full`: SIFT, sort, prep and geometry kernels of one frame-loop step (18 images of 1241x376)",
+         'ncu --set full --clock-control none --import-source on -k regex:"sift_descriptor_kernel|sift_refine_kernel|sift_orient_kernel|sift_extrema|sift_blur_tma_kernel|sift_base_stream|sift_small_oct|sift_rank_bucket|landmark" -c 40 python tools/prof_targets.py 8')
+    full(RP + "_match_u8.ncu-rep", RP + "_ncu_full_match.md", "Round " + RN + " -- ncu `--set full`: match_topk_u8_kernel, 32768 x 32768 x 128, matchFeatures mode",
          "ncu --set full --clock-control none --import-source on -k regex:match_topk_u8 -s 2 -c 1 python tools/prof_match.py 32768 match")
-    full("r1_match_frames.ncu-rep", "r1_ncu_full_match_frames.md", "Round 1 -- ncu `--set full`: match_topk_u8_kernel inside the frame loop (9 problems of ~4100 x 4100)",
-         "ncu --set full --clock-control none --import-source on -k regex:match_topk_u8 -c 2 python tools/prof_targets.py 8")
-    opmix("r1_match_u8.ncu-rep", "match_topk_u8", "r1_opmix_match_u8.txt")
-    opmix("r1_sift2.ncu-rep", "sift_descriptor", "r1_opmix_descriptor.txt")
-    opmix("r1_sift2.ncu-rep", "sift_blur_tma", "r1_opmix_blur_tma_r13.txt", "4")
-    opmix("r1_sift2.ncu-rep", "sift_extrema", "r1_opmix_extrema.txt")
+    opmix(RP + "_match_u8.ncu-rep", "match_topk_u8", RP + "_opmix_match_u8.txt")
+    opmix(RP + "_sift.ncu-rep", "sift_descriptor", RP + "_opmix_descriptor.txt")
+    opmix(RP + "_sift.ncu-rep", "sift_blur_tma", RP + "_opmix_blur_tma_r13.txt", "4")
+    opmix(RP + "_sift.ncu-rep", "sift_extrema", RP + "_opmix_extrema.txt")
     print(sorted(os.listdir(P)))

@@ -13,7 +13,8 @@ import ctypes as C
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
 ctx = vo_b200.Context(0)
-l, r = synth.shift_stream(B + 1, seed=20260)
+import bench
+l, r, _ = bench.street_frames(B + 1)              # the benchmark workload (rendered street sequence)
 dl, dr = torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()
 for i in range(2):
     rel, st, cnt = vo.run_frames(None, None, synth.KITTI_P0, synth.KITTI_P1, seed=1, ctx=ctx,
