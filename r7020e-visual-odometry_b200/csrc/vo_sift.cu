@@ -294,7 +294,9 @@ __device__ __forceinline__ u64 f2_bcast(float k) { const float2 v = make_float2(
 // chunk of compute ahead of its use, so no warp waits on HBM latency.  The ring holds 4 groups
 // (64 rows): the column pass of chunk c reads groups c..c+2 while group c+3 is being written, which
 // leaves a single __syncthreads per chunk.
-constexpr int TS_W = 128, TS_G = 16, TS_HALO = 16, TS_BOXW = TS_W + 2 * TS_HALO;   // 160-float box rows
+// Box rows hold 164 floats (x0 - 16 .. x0 + 147) and ring rows 132: both strides are 4 (mod 32) banks, so eight lanes
+// that read or write 16 bytes in eight different rows / row-column combinations touch 32 different banks (MODE 2).
+constexpr int TS_W = 128, TS_G = 16, TS_HALO = 16, TS_BOXW = TS_W + 2 * TS_HALO + 4, TS_RS = TS_W + 4;
 __host__ __device__ constexpr int TS_MIRROR(int r) { return 3 + 2 * r; }
 // PACK: the row pass runs on packed f32x2 too.  A lane's four outputs are the pairs (c, c+1) and (c+2, c+3); the tap
 // pairs (in[c+d], in[c+d+1]) are 8-byte aligned in the stage for even d only, so each warp first writes a copy of its
@@ -302,8 +304,11 @@ __host__ __device__ constexpr int TS_MIRROR(int r) { return 3 + 2 * r; }
 // TMA box from x0 - 15 cannot do that: a tiled TMA load whose innermost start is not 16-byte aligned faults.)  2R + 1
 // packed operations per output pair instead of 2(2R + 1) scalar ones; each f32x2 lane is an IEEE fmaf / add, so the
 // bits do not change.
-template <int R, bool PACK>
-__global__ void __launch_bounds__(256, PACK ? 2 : 3)
+// MODE 2: a lane computes EIGHT consecutive outputs of one row, and a warp covers two rows (lane = segment * 2 + row):
+// 8 + 2R taps are loaded for 8 outputs instead of 4 + 2R for 4, i.e. 20 instead of 36 bytes of shared memory per pixel at
+// R = 13 -- the kernel is bound by shared-memory traffic, not by its arithmetic.
+template <int R, int MODE>
+__global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3)
 sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* __restrict__ dst,
                      float* __restrict__ dog, const float* __restrict__ src, int h, int w, int pitch,
                      int seg_rows, const Taps taps) {
@@ -312,11 +317,12 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
   // column window reads are always contiguous in shared memory (one base address, immediate offsets)
   constexpr int RING = 64, MIRROR = TS_MIRROR(R);
   extern __shared__ __align__(128) uint8_t tsm[];      // > 48 KB: dynamic shared memory (opt-in)
+  constexpr bool PACK = MODE == 1;
   constexpr int SROW_BYTES = PACK ? 8 * TS_BOXW * 4 : 0;   // PACK: one shifted row per warp
   float (*stage)[TS_G][TS_BOXW] = reinterpret_cast<float (*)[TS_G][TS_BOXW]>(tsm);                        // [2]
   float (*srow)[TS_BOXW] = reinterpret_cast<float (*)[TS_BOXW]>(tsm + 2 * TS_G * TS_BOXW * 4);            // [8]
-  float (*ring)[TS_W] = reinterpret_cast<float (*)[TS_W]>(tsm + 2 * TS_G * TS_BOXW * 4 + SROW_BYTES);      // [RING + MIRROR]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(tsm + 2 * TS_G * TS_BOXW * 4 + SROW_BYTES + (RING + MIRROR) * TS_W * 4);
+  float (*ring)[TS_RS] = reinterpret_cast<float (*)[TS_RS]>(tsm + 2 * TS_G * TS_BOXW * 4 + SROW_BYTES);    // [RING + MIRROR]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(tsm + 2 * TS_G * TS_BOXW * 4 + SROW_BYTES + (RING + MIRROR) * TS_RS * 4);
   const int b = blockIdx.z;
   const int x0 = blockIdx.x * TS_W;
   const int ys = blockIdx.y * seg_rows, ye = min(ys + seg_rows, h);
@@ -362,6 +368,37 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
       }
       __syncthreads();
     }
+    if constexpr (MODE == 2) {
+      const int seg = lane >> 1, rr = 2 * wrp + (lane & 1);
+      const int row = row0 + rr;
+      if (!(row < 0 || row >= h || row < ys - R)) {
+        const float* p = &sg[rr][8 * seg];                         // box col 0 <-> x0 - 16
+        constexpr int Q0 = (TS_HALO - R) / 4, Q1 = (TS_HALO + 8 + R + 3) / 4;   // float4s that hold needed taps
+        float win[4 * (Q1 - Q0)];
+#pragma unroll
+        for (int q = Q0; q < Q1; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(p + 4 * q);
+          win[4 * (q - Q0)] = v.x; win[4 * (q - Q0) + 1] = v.y; win[4 * (q - Q0) + 2] = v.z; win[4 * (q - Q0) + 3] = v.w;
+        }
+        constexpr int C = TS_HALO - 4 * Q0;                        // index of output 0's centre tap in win
+        float acc[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] = taps.k[0] * win[C + o];
+#pragma unroll
+        for (int i = 1; i <= R; ++i) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) acc[o] = fmaf(taps.k[i], win[C + o - i] + win[C + o + i], acc[o]);
+        }
+        const int slot = row & (RING - 1);
+        const float4 oa = make_float4(acc[0], acc[1], acc[2], acc[3]), ob = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        *reinterpret_cast<float4*>(&ring[slot][8 * seg]) = oa;
+        *reinterpret_cast<float4*>(&ring[slot][8 * seg + 4]) = ob;
+        if (slot < MIRROR) {
+          *reinterpret_cast<float4*>(&ring[RING + slot][8 * seg]) = oa;
+          *reinterpret_cast<float4*>(&ring[RING + slot][8 * seg + 4]) = ob;
+        }
+      }
+    } else {
     for (int rr = wrp; rr < TS_G; rr += 8) {
       const int row = row0 + rr;
       if (row < 0 || row >= h || row < ys - R) continue;        // warp-uniform
@@ -427,6 +464,7 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
       if (slot < MIRROR) *reinterpret_cast<float4*>(&ring[RING + slot][4 * lane]) = o4;   // warp-uniform
       }
     }
+    }
   };
 
   const int cp = tid & 63, rg = tid >> 6;
@@ -452,7 +490,7 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
       if (yf - R >= 0 && yf + 3 + R < h) {
         const float* base = &ring[s0][2 * cp];   // s0 + q <= RING - 1 + MIRROR
 #pragma unroll
-        for (int q = 0; q < 4 + 2 * R; ++q) win[q] = *reinterpret_cast<const u64*>(base + q * TS_W);
+        for (int q = 0; q < 4 + 2 * R; ++q) win[q] = *reinterpret_cast<const u64*>(base + q * TS_RS);
       } else {
 #pragma unroll
         for (int q = 0; q < 4 + 2 * R; ++q) {
@@ -1503,7 +1541,7 @@ static int launch_blur_t(const float* src, const uint8_t* src8, float* dst, floa
   return VO_OK;
 }
 
-template <int R, bool PACK>
+template <int R, int MODE>
 static int launch_tma_t2(const CUtensorMap& tm, int z_base, const float* src, float* dst, float* dog, int h, int w, int pitch,
                         int batch, const Taps& t, int num_sms, cudaStream_t st) {
   const int strips = div_up(w, TS_W);
@@ -1514,19 +1552,20 @@ static int launch_tma_t2(const CUtensorMap& tm, int z_base, const float* src, fl
   if (seg_rows < 4 * TS_G) seg_rows = 4 * TS_G;
   n_seg = div_up(h, seg_rows);
   dim3 grid(strips, n_seg, batch);
-  constexpr int smem = 2 * TS_G * TS_BOXW * 4 + (PACK ? 8 * TS_BOXW * 4 : 0) + (64 + TS_MIRROR(R)) * TS_W * 4 + 64;
-  VO_TRY(ensure_dyn_smem_of(sift_blur_tma_kernel<R, PACK>, smem));
-  sift_blur_tma_kernel<R, PACK><<<grid, 256, smem, st>>>(tm, z_base, dst, dog, src, h, w, pitch, seg_rows, t);
+  constexpr int smem = 2 * TS_G * TS_BOXW * 4 + (MODE == 1 ? 8 * TS_BOXW * 4 : 0) + (64 + TS_MIRROR(R)) * TS_RS * 4 + 64;
+  VO_TRY(ensure_dyn_smem_of(sift_blur_tma_kernel<R, MODE>, smem));
+  sift_blur_tma_kernel<R, MODE><<<grid, 256, smem, st>>>(tm, z_base, dst, dog, src, h, w, pitch, seg_rows, t);
   return VO_OK;
 }
-// VO_BLUR_PACK=1 selects the packed row pass (measured slower: 3.27 vs 2.45 ms per step -- the kernel is bound by
-// shared-memory bandwidth, and the packed form reads 60 B/px in the row pass instead of 36; kept for A/B runs)
+// VO_BLUR_ROW selects the row pass: 2 (default) = eight outputs per lane, 0 = four outputs per lane (round 1),
+// 1 = packed f32x2 (measured slower: 3.27 vs 2.45 ms per step, it reads more shared memory per pixel; kept for A/B runs)
 template <int R>
 static int launch_tma_t(const CUtensorMap& tm, int z_base, const float* src, float* dst, float* dog, int h, int w, int pitch,
                         int batch, const Taps& t, int num_sms, cudaStream_t st) {
-  static const bool pack = [] { const char* e = getenv("VO_BLUR_PACK"); return e ? atoi(e) != 0 : false; }();
-  return pack ? launch_tma_t2<R, true>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st)
-              : launch_tma_t2<R, false>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
+  static const int mode = [] { const char* e = getenv("VO_BLUR_ROW"); return e ? atoi(e) : 2; }();
+  if (mode == 1) return launch_tma_t2<R, 1>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
+  if (mode == 0) return launch_tma_t2<R, 0>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
+  return launch_tma_t2<R, 2>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
 }
 
 // tm/z_base: tensor map of the octave's Gaussian stack and the z index of image 0 of the source layer
