@@ -723,12 +723,18 @@ def dropin_leg(sleft, sright, gt):
 
 
 def png_leg(sleft, sright, B):
-    """PNG files -> poses: the frames are written as 8-bit gray PNGs, then io.run_sequence decodes batch k+1 on
-    host threads while vo_frames runs batch k."""
+    """PNG files -> poses.  The frames are written as 8-bit gray PNGs (OpenCV / libpng: adaptive row
+    filters, dynamic Huffman blocks), then read back two ways: "host" = io.run_sequence (the library's host decoder on
+    every core decodes batch k+1 while vo_frames runs batch k, one batch at a time) and "device" =
+    io.run_sequence_device (the files go to the GPU as they are; inflate + un-filter kernels, one warp per image;
+    four / eight batches in flight on their own contexts, the host only reads files)."""
+    import shutil
     import tempfile
     import cv2
+    import torch
+    import vo_b200
     from vo_b200 import io, synth, vo
-    n = min(len(sleft), 4 * B + 1)
+    n = min(len(sleft), 12 * B + 1)
     d = tempfile.mkdtemp(prefix="vo_b200_png_")
     lf, rf = [], []
     nbytes = 0
@@ -737,18 +743,37 @@ def png_leg(sleft, sright, B):
             os.makedirs(os.path.join(d, name), exist_ok=True)
             p = os.path.join(d, name, f"{i:06d}.png")
             cv2.imwrite(p, arr[i]); lst.append(p); nbytes += os.path.getsize(p)
+    out = dict(unit=UNIT, frames=n - 1, png_bytes_per_image=nbytes / (2 * n), host_cores=os.cpu_count())
     try:
+        ref = vo.run_frames(sleft[:B + 1], sright[:B + 1], synth.KITTI_P0, synth.KITTI_P1, seed=1)
         io.run_sequence(lf[:B + 1], rf[:B + 1], synth.KITTI_P0, synth.KITTI_P1, batch=B, seed=1)       # warm-up
         t0 = time.perf_counter()
         rel, status, counts = io.run_sequence(lf, rf, synth.KITTI_P0, synth.KITTI_P1, batch=B, seed=1)
         dt = time.perf_counter() - t0
-        ref = vo.run_frames(sleft[:B + 1], sright[:B + 1], synth.KITTI_P0, synth.KITTI_P1, seed=1)
-        same = bool(np.array_equal(rel[:B + 1], ref[0]))
+        out["host"] = dict(value=(n - 1) / dt, equals_vo_frames=bool(np.array_equal(rel[:B + 1], ref[0])),
+                           note="host decode on every core, decode of batch k+1 overlaps vo_frames of batch k, one batch at a time")
+        for depth in (4, 8):
+            pipe = io.DevicePngPipeline(H, W, batch=B, depth=depth, device=torch.cuda.current_device())
+            pipe.run(lf[:depth * B + 1], rf[:depth * B + 1], synth.KITTI_P0, synth.KITTI_P1, seed=1)      # warm-up: plans, buffers
+            t0 = time.perf_counter()
+            rel, status, counts = pipe.run(lf, rf, synth.KITTI_P0, synth.KITTI_P1, seed=1)
+            dt = time.perf_counter() - t0
+            pipe.close()
+            out[f"device_depth{depth}"] = dict(value=(n - 1) / dt, equals_vo_frames=bool(np.array_equal(rel[:B + 1], ref[0])))
+        # the decode kernels alone: one batch of 2 * (B + 1) images
+        c = vo_b200.Context(torch.cuda.current_device())
+        buf = torch.empty((2 * (B + 1), H, W), dtype=torch.uint8, device="cuda")
+        io.read_batch_dev(lf[:B + 1] + rf[:B + 1], H, W, buf, c)
+        c.profile_enable(True)
+        io.read_batch_dev(lf[:B + 1] + rf[:B + 1], H, W, buf, c)
+        pr = c.profile(); c.profile_enable(False); c.close()
+        out["decode_kernels_ms_per_batch"] = dict(images=2 * (B + 1), inflate=pr["png_inflate"]["ms"], unfilter=pr["png_unfilter"]["ms"])
+        out["value"] = max(out["device_depth4"]["value"], out["device_depth8"]["value"])
+        out["equals_vo_frames"] = bool(out["host"]["equals_vo_frames"] and out["device_depth4"]["equals_vo_frames"] and out["device_depth8"]["equals_vo_frames"])
+        out["note"] = "wall clock, files in the page cache; value = the device-decode form (contexts created beforehand)"
     finally:
-        import shutil
         shutil.rmtree(d, ignore_errors=True)
-    return dict(value=(n - 1) / dt, unit=UNIT, frames=n - 1, png_bytes_per_frame=nbytes / n, decode_threads=os.cpu_count(),
-                equals_vo_frames=same, note="wall clock; files in the page cache; decode of batch k+1 overlaps vo_frames of batch k")
+    return out
 
 
 def reloc_leg(args, torch, dist, ctx, rank, world, pk):

@@ -60,6 +60,33 @@ def read_batch(paths, rows=None, cols=None, out=None, threads=0):
     return out[:n] if out.ndim == 3 else out
 
 
+def decode_batch_dev(files, rows, cols, out_dev, ctx=None):
+    """Device-side decode (vo_png_decode_batch_dev): ``files`` = encoded PNG files as bytes objects, ``out_dev`` a
+    torch uint8 CUDA tensor with room for [n, rows, cols] (or an int device pointer).  The DEFLATE streams are
+    inflated and un-filtered by CUDA kernels; the host only gathers the IDAT chunks."""
+    from . import api
+    ctx = ctx or api.default_context()
+    n = len(files)
+    bufs = [np.frombuffer(f, dtype=np.uint8) for f in files]
+    ptrs = (C.POINTER(C.c_uint8) * n)(*[b.ctypes.data_as(C.POINTER(C.c_uint8)) for b in bufs])
+    sizes = (C.c_size_t * n)(*[len(b) for b in bufs])
+    dptr = out_dev if isinstance(out_dev, int) else out_dev.data_ptr()
+    check(_lib.lib().vo_png_decode_batch_dev(ctx.handle, ptrs, sizes, n, rows, cols, C.c_void_p(dptr)))
+    return out_dev
+
+
+def read_batch_dev(paths, rows, cols, out_dev, ctx=None, threads=0):
+    """Files on disk -> device batch buffer (vo_png_read_batch_dev: a few host threads read, the GPU decodes)."""
+    from . import api
+    ctx = ctx or api.default_context()
+    paths = [os.fspath(p) for p in paths]
+    n = len(paths)
+    arr = (C.c_char_p * n)(*[p.encode() for p in paths])
+    dptr = out_dev if isinstance(out_dev, int) else out_dev.data_ptr()
+    check(_lib.lib().vo_png_read_batch_dev(ctx.handle, arr, n, rows, cols, C.c_void_p(dptr), threads))
+    return out_dev
+
+
 class ImageDatastore:
     """imageDatastore(folder) as VO.m uses it: sorted ``Files`` and ``readimage(i)`` (1-based)."""
 
@@ -120,3 +147,71 @@ def run_sequence(left_files, right_files, P1, P2, batch=32, seed=0, threads=0, c
             first = 0 if lo == 0 else 1          # the halo frame's outputs belong to the previous chunk
             rel[lo + first:hi] = r[first:]; status[lo + first:hi] = s[first:]; counts[lo + first:hi] = c[first:]
     return rel, status, counts
+
+
+class DevicePngPipeline:
+    """PNG files -> poses with the decode on the GPU (vo_png.cu) and ``depth`` batches in flight: one context, one
+    device batch buffer and one host thread per slot.  A slot reads the files of its batch (left and right together:
+    one decode launch, one warp per image), then runs vo_frames_dev on the decoded buffer.  The serial inflate of a
+    batch (tens of milliseconds of latency, a few per cent of the SMs) hides behind the SIFT kernels of the other
+    slots; the host only reads files and gathers IDAT chunks."""
+
+    def __init__(self, rows, cols, batch=32, depth=6, device=0, threads=2):
+        import torch
+        from . import api
+        self.rows, self.cols, self.batch, self.device, self.threads = rows, cols, batch, device, threads
+        self.ctxs = [api.Context(device) for _ in range(max(1, depth))]
+        self.bufs = [torch.empty((2 * (batch + 1), rows, cols), dtype=torch.uint8, device=torch.device("cuda", device))
+                     for _ in self.ctxs]
+
+    def run(self, left_files, right_files, P1, P2, seed=0):
+        """Returns (rel_pose [n,4,4], status [n], counts [n,8])."""
+        import threading
+        from . import vo
+        n, batch, rows, cols = len(left_files), self.batch, self.rows, self.cols
+        assert len(right_files) == n and n > 0
+        chunks = [(max(b0 - 1, 0), min(b0 + batch, n)) for b0 in range(0, n, batch)]   # [lo, hi) with halo
+        rel = np.tile(np.eye(4), (n, 1, 1)); status = np.zeros(n, dtype=np.int32); counts = np.zeros((n, 8), dtype=np.int32)
+        nxt = iter(range(len(chunks)))
+        lock = threading.Lock()
+        err = []
+
+        def worker(ctx, buf):
+            try:
+                while not err:
+                    with lock:
+                        k = next(nxt, None)
+                    if k is None:
+                        return
+                    lo, hi = chunks[k]
+                    m = hi - lo
+                    read_batch_dev(list(left_files[lo:hi]) + list(right_files[lo:hi]), rows, cols, buf, ctx, self.threads)
+                    r, s, c = vo.run_frames(None, None, P1, P2, seed=seed, first_frame=lo, ctx=ctx,
+                                            device_ptrs=(buf[0].data_ptr(), buf[m].data_ptr(), m, rows, cols))
+                    first = 0 if lo == 0 else 1
+                    rel[lo + first:hi] = r[first:]; status[lo + first:hi] = s[first:]; counts[lo + first:hi] = c[first:]
+            except BaseException as e:   # noqa: BLE001  (surfaced in the caller's thread)
+                err.append(e)
+        th = [threading.Thread(target=worker, args=(c, b)) for c, b in zip(self.ctxs, self.bufs)][:len(chunks)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        if err:
+            raise err[0]
+        return rel, status, counts
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+        self.bufs = []
+
+
+def run_sequence_device(left_files, right_files, P1, P2, batch=32, seed=0, depth=6, device=0, threads=2):
+    """run_sequence with the PNG decode on the GPU (DevicePngPipeline for one call)."""
+    with open(left_files[0], "rb") as f:
+        rows, cols, _, _ = png_info(f.read(64))
+    pipe = DevicePngPipeline(rows, cols, batch=batch, depth=min(depth, max(1, (len(left_files) + batch - 1) // batch)), device=device,
+                             threads=threads)
+    try:
+        return pipe.run(left_files, right_files, P1, P2, seed=seed)
+    finally:
+        pipe.close()
