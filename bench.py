@@ -576,7 +576,9 @@ def run_ours(args, rank, world, local_rank):
         cnt_all[b * B + 1: b * B + B + 1] = c_[1:]
     if rank != 0:
         if dist is not None:
-            reloc_leg(args, torch, dist, ctx, rank, world, pk)
+            if not args.quick:
+                reloc_leg(args, torch, dist, ctx, rank, world, pk)
+                png_leg_all_ranks(torch, dist, sleft, sright, B, rank, world)
             dist.destroy_process_group()
         return
     trajectory = dict(gpu=trajectory_errors(rel_all, gt, n_seq), status_ok=int((status_all[1:] == 0).sum()),
@@ -670,6 +672,8 @@ def run_ours(args, rank, world, local_rank):
                  ("e2e_from_png", lambda: png_leg(sleft, sright, B))]
     if not args.quick:
         side += [("reloc", lambda: reloc_leg(args, torch, dist, ctx, rank, world, pk))]
+        if world > 1:
+            side += [("e2e_from_png", lambda: png_leg_all_ranks(torch, dist, sleft, sright, B, rank, world))]
     if world == 1 and not args.no_cpu and not args.quick:
         side += [("cpu_baseline", lambda: cpu_leg(sleft, sright, gt, rel_all, status_all, trajectory))]
     for name, fn in side:
@@ -683,7 +687,8 @@ def run_ours(args, rank, world, local_rank):
         log(f"{name}: {time.time() - t0:.1f} s")
     pz = [line["trajectory"].get("parity_vs_oracle"), (line.get("match_gemm") or {}).get("parity_all_bit_exact"),
           (line.get("reloc") or {}).get("parity_rows_bit_exact"), (line.get("e2e_dropin") or {}).get("equals_vo_frames")]
-    line["parity"] = dict(trajectory_vs_oracle=pz[0], match_sweep_bit_exact=pz[1], reloc_rows_bit_exact=pz[2], dropin_equals_batched=pz[3])
+    line["parity"] = dict(trajectory_vs_oracle=pz[0], match_sweep_bit_exact=pz[1], reloc_rows_bit_exact=pz[2], dropin_equals_batched=pz[3],
+                          png_paths_equal_vo_frames=(line.get("e2e_from_png") or {}).get("equals_vo_frames"))
     emit(line)
     if _POOL is not None:
         _POOL.terminate()
@@ -752,7 +757,7 @@ def png_leg(sleft, sright, B):
         dt = time.perf_counter() - t0
         out["host"] = dict(value=(n - 1) / dt, equals_vo_frames=bool(np.array_equal(rel[:B + 1], ref[0])),
                            note="host decode on every core, decode of batch k+1 overlaps vo_frames of batch k, one batch at a time")
-        for depth in (4, 8):
+        for depth in (8,):
             pipe = io.DevicePngPipeline(H, W, batch=B, depth=depth, device=torch.cuda.current_device())
             pipe.run(lf[:depth * B + 1], rf[:depth * B + 1], synth.KITTI_P0, synth.KITTI_P1, seed=1)      # warm-up: plans, buffers
             t0 = time.perf_counter()
@@ -768,12 +773,36 @@ def png_leg(sleft, sright, B):
         io.read_batch_dev(lf[:B + 1] + rf[:B + 1], H, W, buf, c)
         pr = c.profile(); c.profile_enable(False); c.close()
         out["decode_kernels_ms_per_batch"] = dict(images=2 * (B + 1), inflate=pr["png_inflate"]["ms"], unfilter=pr["png_unfilter"]["ms"])
-        out["value"] = max(out["device_depth4"]["value"], out["device_depth8"]["value"])
-        out["equals_vo_frames"] = bool(out["host"]["equals_vo_frames"] and out["device_depth4"]["equals_vo_frames"] and out["device_depth8"]["equals_vo_frames"])
-        out["note"] = "wall clock, files in the page cache; value = the device-decode form (contexts created beforehand)"
+        out["device"] = out.pop("device_depth8")
+        out["device"]["note"] = ("files go to the GPU as they are, inflate + un-filter kernels (one warp per image), eight batches in flight on "
+                                 "their own contexts; the host reads files and gathers IDAT chunks (2 threads per slot)")
+        out["value"] = max(out["host"]["value"], out["device"]["value"])
+        out["equals_vo_frames"] = bool(out["host"]["equals_vo_frames"] and out["device"]["equals_vo_frames"])
+        out["note"] = ("wall clock, files in the page cache; value = the better of the two forms on this box: the host form scales with the "
+                       "cores per GPU (400-700 images/s per core), the device form does not need them")
     finally:
         shutil.rmtree(d, ignore_errors=True)
     return out
+
+
+def png_leg_all_ranks(torch, dist, sleft, sright, B, rank, world):
+    """N > 1: every rank runs the PNG leg at the same time (they share the host's cores, as a real multi-GPU job does);
+    rank 0 reports its own line plus the slowest rank's rates."""
+    dist.barrier()
+    try:
+        r = png_leg(sleft, sright, B)
+        v = [r["host"]["value"], r["device"]["value"]]
+    except Exception as e:   # noqa: BLE001
+        r = dict(error=f"{type(e).__name__}: {e}")
+        v = [0.0, 0.0]
+    t = torch.tensor(v, device="cuda", dtype=torch.float64)
+    allv = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allv, t)
+    if rank == 0 and "error" not in r:
+        r["all_ranks"] = dict(host_per_rank=[round(float(x[0])) for x in allv], device_per_rank=[round(float(x[1])) for x in allv],
+                              host_total=float(sum(x[0] for x in allv)), device_total=float(sum(x[1] for x in allv)),
+                              cores_per_gpu=(os.cpu_count() or 1) / world)
+    return r
 
 
 def reloc_leg(args, torch, dist, ctx, rank, world, pk):

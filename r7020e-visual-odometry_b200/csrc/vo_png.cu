@@ -25,8 +25,10 @@ namespace vo {
 
 namespace png {
 constexpr int LL_BITS = 11, D_BITS = 8, PRE_BITS = 7;
-constexpr int LL_CAP = (1 << LL_BITS) + 288 * 16, D_CAP = (1 << D_BITS) + 32 * 128;
-constexpr uint32_t WIN = 32768;
+// second-level capacity (entries).  FULL covers every legal code; SMALL covers what image data produces (a handful of
+// codes longer than the first level) in a third of the shared memory, so that a decode block does not take the room of
+// two blur blocks on its SM while it walks its stream.  A stream that does not fit SMALL is decoded again with FULL.
+constexpr int LL_SUB_FULL = 288 * 16, D_SUB_FULL = 32 * 128, LL_SUB_SMALL = 1024, D_SUB_SMALL = 256;
 constexpr uint32_t E_LIT = 1u << 31, E_EOB = 1u << 30, E_SUB = 1u << 29, E_BAD = 1u << 28, E_LIT2 = 1u << 27;
 
 __constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -35,7 +37,8 @@ __constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49
 __constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t c_pre_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-enum { ST_OK = 0, ST_HEADER = 1, ST_BLOCK = 2, ST_CODE = 3, ST_OVERRUN = 4, ST_DIST = 5, ST_LENGTH = 6, ST_ADLER = 7, ST_FILTER = 8, ST_TRUNC = 9 };
+enum { ST_OK = 0, ST_HEADER = 1, ST_BLOCK = 2, ST_CODE = 3, ST_OVERRUN = 4, ST_DIST = 5, ST_LENGTH = 6, ST_ADLER = 7, ST_FILTER = 8, ST_TRUNC = 9,
+       ST_BIG = 10 /* the code tables need the full-capacity kernel */ };
 
 struct Job { uint32_t in_off, in_len; };   // zlib stream inside the staging buffer (16-byte aligned offset)
 
@@ -53,13 +56,14 @@ __device__ __forceinline__ uint32_t bit_reverse(uint32_t c, int len) { return __
 
 // Canonical code lengths -> two-level table (same layout as vo_inflate.cu).  kind: 0 literal/length, 1 distance,
 // 2 code-length code.  Called by lane 0; `table` was cleared to E_BAD | 1 by the whole warp.
-__device__ bool build_table(const uint8_t* lens, int n, int tb, uint32_t* table, int cap, int kind, uint8_t* sub_bits) {
+// returns ST_OK, ST_CODE (over-subscribed code) or ST_BIG (second level does not fit `cap`)
+__device__ int build_table(const uint8_t* lens, int n, int tb, uint32_t* table, int cap, int kind, uint8_t* sub_bits) {
   int count[16];
   for (int l = 0; l < 16; ++l) count[l] = 0;
   for (int s = 0; s < n; ++s) ++count[lens[s]];
   count[0] = 0;
   int left = 1;
-  for (int l = 1; l <= 15; ++l) { left = (left << 1) - count[l]; if (left < 0) return false; }
+  for (int l = 1; l <= 15; ++l) { left = (left << 1) - count[l]; if (left < 0) return ST_CODE; }
   uint32_t next[16], nx[16]; uint32_t code = 0;
   next[0] = nx[0] = 0;
   for (int l = 1; l <= 15; ++l) { code = (code + (uint32_t)count[l - 1]) << 1; next[l] = nx[l] = code; }
@@ -89,7 +93,7 @@ __device__ bool build_table(const uint8_t* lens, int n, int tb, uint32_t* table,
       uint32_t link = table[pfx];
       if (!(link & E_SUB)) {
         const int sb = sub_bits[pfx];
-        if (free_at + (1 << sb) > cap) return false;
+        if (free_at + (1 << sb) > cap) return ST_BIG;
         link = E_SUB | ((uint32_t)free_at << 8) | ((uint32_t)sb << 4) | (uint32_t)tb;
         table[pfx] = link;
         for (int k = 0; k < (1 << sb); ++k) table[free_at + k] = E_BAD | 1u;
@@ -101,17 +105,17 @@ __device__ bool build_table(const uint8_t* lens, int n, int tb, uint32_t* table,
       for (uint32_t k = rev >> tb; k < (1u << sb); k += 1u << (l - tb)) sub[k] = e;
     }
   }
-  return true;
+  return ST_OK;
 }
 
+template <int LL_SUB, int D_SUB>
 struct Smem {
+  static constexpr int LL_CAP = (1 << LL_BITS) + LL_SUB, D_CAP = (1 << D_BITS) + D_SUB;
   uint32_t ll[LL_CAP];            // literal/length table (first level with paired literals)
-  uint32_t one[1 << LL_BITS];     // its first level before pairing
   uint32_t d[D_CAP];
   uint32_t pre[1 << PRE_BITS];
   uint8_t lens[320 + 140];
   uint8_t sub_bits[1 << LL_BITS];
-  uint8_t win[WIN + 8];           // the last 32 KB of output (the DEFLATE window): match sources come from here, not from L2
 };
 
 // The bit reader.  A 64-bit shift register costs three or four instructions per shift on this machine, and a serial
@@ -136,13 +140,18 @@ struct Bits {
   __device__ __forceinline__ uint32_t byte_pos() const { return wi * 4u + ((bp + 7u) >> 3); }   // first byte not touched
 };
 
-// grid = images, block = one warp.  raw: [n][raw_stride] filtered scanlines (rows * (cols + 1) bytes used).
+// grid = images (or the images listed in `only`), block = one warp.  raw: [n][raw_stride] filtered scanlines
+// (rows * (cols + 1) bytes used).
+template <int LL_SUB, int D_SUB>
 __global__ void __launch_bounds__(32)
-png_inflate_kernel(const uint8_t* __restrict__ staging, const Job* __restrict__ jobs, uint8_t* __restrict__ raw_base,
-                   size_t raw_stride, uint32_t n_raw, int* __restrict__ status, uint32_t* __restrict__ adler_want) {
+png_inflate_kernel(const uint8_t* __restrict__ staging, const Job* __restrict__ jobs, const int* __restrict__ only,
+                   uint8_t* __restrict__ raw_base, size_t raw_stride, uint32_t n_raw, int* __restrict__ status,
+                   uint32_t* __restrict__ adler_want) {
+  using SM = Smem<LL_SUB, D_SUB>;
   extern __shared__ __align__(16) uint8_t png_smem[];
-  Smem& sm = *reinterpret_cast<Smem*>(png_smem);
-  const int img = blockIdx.x, lane = threadIdx.x;
+  SM& sm = *reinterpret_cast<SM*>(png_smem);
+  constexpr int LL_CAP = SM::LL_CAP, D_CAP = SM::D_CAP;
+  const int img = only ? only[blockIdx.x] : blockIdx.x, lane = threadIdx.x;
   const Job job = jobs[img];
   const uint8_t* in = staging + job.in_off;
   const uint32_t n_in = job.in_len;
@@ -177,7 +186,7 @@ png_inflate_kernel(const uint8_t* __restrict__ staging, const Job* __restrict__ 
             if ((len ^ 0xFFFFu) != nlen) err = ST_BLOCK;
             else if (p + len > n_in || out + len > n_raw) err = ST_OVERRUN;
             else {
-              for (uint32_t k = 0; k < len; ++k) { const uint8_t v = in[p + k]; out0[out + k] = v; sm.win[(out + k) & (WIN - 1u)] = v; }
+              for (uint32_t k = 0; k < len; ++k) out0[out + k] = in[p + k];
               out += len;
               br.seek(p + len);
             }
@@ -203,8 +212,8 @@ png_inflate_kernel(const uint8_t* __restrict__ staging, const Job* __restrict__ 
         for (int i = 256; i < 280; ++i) sm.lens[i] = 7;
         for (int i = 280; i < 288; ++i) sm.lens[i] = 8;
         for (int i = 0; i < 32; ++i) sm.lens[288 + i] = 5;
-        if (!build_table(sm.lens, 288, LL_BITS, sm.ll, LL_CAP, 0, sm.sub_bits) ||
-            !build_table(sm.lens + 288, 32, D_BITS, sm.d, D_CAP, 1, sm.sub_bits)) err = ST_CODE;
+        err = build_table(sm.lens, 288, LL_BITS, sm.ll, LL_CAP, 0, sm.sub_bits);
+        if (err == ST_OK) err = build_table(sm.lens + 288, 32, D_BITS, sm.d, D_CAP, 1, sm.sub_bits);
       } else {
         uint32_t hb = br.peek32();
         const unsigned hlit = (hb & 31u) + 257, hdist = ((hb >> 5) & 31u) + 1, hclen = ((hb >> 10) & 15u) + 4;
@@ -215,7 +224,7 @@ png_inflate_kernel(const uint8_t* __restrict__ staging, const Job* __restrict__ 
           sm.lens[320 + c_pre_order[i]] = (uint8_t)(br.peek32() & 7u); br.consume(3);
         }
         if (br.over) err = ST_TRUNC;
-        if (err == ST_OK && !build_table(sm.lens + 320, 19, PRE_BITS, sm.pre, 1 << PRE_BITS, 2, sm.sub_bits)) err = ST_CODE;
+        if (err == ST_OK) err = build_table(sm.lens + 320, 19, PRE_BITS, sm.pre, 1 << PRE_BITS, 2, sm.sub_bits);
         unsigned i = 0;
         while (err == ST_OK && i < hlit + hdist) {
           if (br.over) { err = ST_TRUNC; break; }
@@ -237,27 +246,31 @@ png_inflate_kernel(const uint8_t* __restrict__ staging, const Job* __restrict__ 
         if (err == ST_OK) {
           // the distance lengths follow the literal/length lengths: move them so both tables see their own array
           for (unsigned k = 0; k < hdist; ++k) sm.lens[320 + 32 + k] = sm.lens[hlit + k];
-          if (!build_table(sm.lens, (int)hlit, LL_BITS, sm.ll, LL_CAP, 0, sm.sub_bits) ||
-              !build_table(sm.lens + 320 + 32, (int)hdist, D_BITS, sm.d, D_CAP, 1, sm.sub_bits)) err = ST_CODE;
+          err = build_table(sm.lens, (int)hlit, LL_BITS, sm.ll, LL_CAP, 0, sm.sub_bits);
+          if (err == ST_OK) err = build_table(sm.lens + 320 + 32, (int)hdist, D_BITS, sm.d, D_CAP, 1, sm.sub_bits);
         }
       }
     }
     if (__shfl_sync(0xffffffffu, err, 0) != ST_OK) break;
     __syncwarp();
-    // pair literals (whole warp): where two consecutive literal codes fit into the first-level index
-    for (int i = lane; i < (1 << LL_BITS); i += 32) sm.one[i] = sm.ll[i];
-    __syncwarp();
-    for (uint32_t i = lane; i < (1u << LL_BITS); i += 32) {
-      const uint32_t e1 = sm.one[i];
-      if (!(e1 & E_LIT)) continue;
-      const uint32_t l1 = e1 & 15u;
-      if (l1 >= (uint32_t)LL_BITS) continue;
-      const uint32_t e2 = sm.one[i >> l1];
-      const uint32_t l2 = e2 & 15u;
-      if ((e2 & E_LIT) && l1 + l2 <= (uint32_t)LL_BITS)
-        sm.ll[i] = E_LIT | E_LIT2 | (e1 & 0xFF00u) | ((e2 & 0xFF00u) << 8) | (l1 + l2);
+    // pair literals, in place: where two consecutive literal codes fit into the first-level index, the entry decodes
+    // both.  Entry i reads entry i >> l1 (l1 >= 1), which lies in a lower 32-entry chunk for every i >= 64 and in the
+    // chunk itself or below otherwise: chunks are visited from the top by the whole warp, the two lowest by lane 0.
+    for (int base = (1 << LL_BITS) - 32; base >= 0; base -= 32) {
+      const bool serial = base < 64;
+      for (int k = serial ? 31 : lane; k >= 0 && (serial ? lane == 0 : k == lane); k = serial ? k - 1 : -1) {
+        const uint32_t i = (uint32_t)(base + k);
+        const uint32_t e1 = sm.ll[i];
+        if (!(e1 & E_LIT) || (e1 & E_LIT2)) continue;
+        const uint32_t l1 = e1 & 15u;
+        if (l1 >= (uint32_t)LL_BITS) continue;
+        const uint32_t e2 = sm.ll[i >> l1];
+        const uint32_t l2 = e2 & 15u;
+        if ((e2 & E_LIT) && !(e2 & E_LIT2) && l1 + l2 <= (uint32_t)LL_BITS)
+          sm.ll[i] = E_LIT | E_LIT2 | (e1 & 0xFF00u) | ((e2 & 0xFF00u) << 8) | (l1 + l2);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     // ---- the symbols of this block (lane 0).  A serial decoder runs at the latency of its dependent chain, and on this
     // machine a conditional branch of a lone warp costs about as much as a shared-memory load (ncu: the `wait` samples
     // sit on the branches), so the literal path is ONE loop-back branch: funnel shift, table look-up, two byte stores
@@ -272,7 +285,6 @@ png_inflate_kernel(const uint8_t* __restrict__ staging, const Job* __restrict__ 
       uint32_t w0 = br.w0, w1 = br.w1, w2 = br.w2, w3 = br.w3, bp = br.bp, wi = br.wi;
       uint32_t o = out;
       const uint32_t ll_s = smem_u32(sm.ll);
-      uint8_t* const win = sm.win;
       uint8_t* obase = out0;
       asm volatile("" : "+l"(obase));                      // one register pair: every address is a single wide add
 // consume n_ bits and form the next 32: both candidate funnel shifts (the shift count wraps mod 32) are independent of
@@ -300,7 +312,6 @@ png_inflate_kernel(const uint8_t* __restrict__ staging, const Job* __restrict__ 
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(ll_s + ((bits << 2) & (((1u << LL_BITS) - 1u) << 2))));
           uint8_t* p = obase + o;
           p[0] = (uint8_t)(ecur >> 8); p[1] = (uint8_t)(ecur >> 16);
-          win[o & (WIN - 1u)] = (uint8_t)(ecur >> 8); win[(o + 1u) & (WIN - 1u)] = (uint8_t)(ecur >> 16);
           o += 1u + ((ecur >> 27) & 1u);
           if (adv) { w0 = w1; w1 = w2; w2 = w3; ++wi; bp -= 32u; }
           asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}"
@@ -313,7 +324,6 @@ png_inflate_kernel(const uint8_t* __restrict__ staging, const Job* __restrict__ 
           e = ll[((e >> 8) & 0xFFFFFu) + ((bits >> used) & ((1u << ((e >> 4) & 15u)) - 1u))];
           if (e & E_LIT) {
             if (o >= lim) { err = ST_OVERRUN; break; }
-            win[o & (WIN - 1u)] = (uint8_t)(e >> 8);
             obase[o++] = (uint8_t)(e >> 8);
             VO_PNG_ADV(used + (e & 15u));
             e = ll[bits & ((1u << LL_BITS) - 1u)];
@@ -343,20 +353,17 @@ png_inflate_kernel(const uint8_t* __restrict__ staging, const Job* __restrict__ 
         VO_PNG_ADV(used + db);
         if (o > lim || dist > o) { err = ST_DIST; break; }
         if (length > lim - o) { err = ST_LENGTH; break; }
+        const uint8_t* src = obase + (o - dist);           // (a 32 KB window in shared memory was measured: no faster)
         uint8_t* dst = obase + o;
-        const uint32_t so = o - dist;
         if (dist >= length) {                              // no overlap: all loads first, then the stores
           uint32_t k = 0;
           for (; k + 4 <= length; k += 4) {
-            const uint8_t a0 = win[(so + k) & (WIN - 1u)], a1 = win[(so + k + 1u) & (WIN - 1u)];
-            const uint8_t a2 = win[(so + k + 2u) & (WIN - 1u)], a3 = win[(so + k + 3u) & (WIN - 1u)];
+            const uint8_t a0 = src[k], a1 = src[k + 1], a2 = src[k + 2], a3 = src[k + 3];
             dst[k] = a0; dst[k + 1] = a1; dst[k + 2] = a2; dst[k + 3] = a3;
-            win[(o + k) & (WIN - 1u)] = a0; win[(o + k + 1u) & (WIN - 1u)] = a1;
-            win[(o + k + 2u) & (WIN - 1u)] = a2; win[(o + k + 3u) & (WIN - 1u)] = a3;
           }
-          for (; k < length; ++k) { const uint8_t v = win[(so + k) & (WIN - 1u)]; dst[k] = v; win[(o + k) & (WIN - 1u)] = v; }
+          for (; k < length; ++k) dst[k] = src[k];
         } else {
-          for (uint32_t k = 0; k < length; ++k) { const uint8_t v = win[(so + k) & (WIN - 1u)]; dst[k] = v; win[(o + k) & (WIN - 1u)] = v; }
+          for (uint32_t k = 0; k < length; ++k) dst[k] = src[k];
         }
         o += length;
         e = ll[bits & ((1u << LL_BITS) - 1u)];
@@ -391,12 +398,13 @@ __device__ __forceinline__ int paeth(int a, int b, int c) {
 // grid = images, block = one warp.  out: [n][rows][cols] (image i at out + i * out_stride).
 __global__ void __launch_bounds__(32)
 png_unfilter_kernel(const uint8_t* __restrict__ raw_base, size_t raw_stride, int rows, int cols, uint8_t* __restrict__ out_base,
-                    size_t out_stride, int* __restrict__ status, const uint32_t* __restrict__ adler_want) {
+                    size_t out_stride, int* __restrict__ status, const uint32_t* __restrict__ adler_want,
+                    const int* __restrict__ only) {
   extern __shared__ __align__(16) uint8_t unf_smem[];
   uint8_t* lastrow = unf_smem;                                                   // [cols]: the finished row above the group
   uint32_t* row_a = reinterpret_cast<uint32_t*>(unf_smem + ((cols + 15) & ~15));   // [rows] per-row byte sums
   uint32_t* row_b = row_a + rows;                                                // [rows] per-row position-weighted sums
-  const int img = blockIdx.x, lane = threadIdx.x;
+  const int img = only ? only[blockIdx.x] : blockIdx.x, lane = threadIdx.x;
   if (status[img] != ST_OK) return;
   const uint8_t* raw = raw_base + (size_t)img * raw_stride;
   uint8_t* out = out_base + (size_t)img * out_stride;
@@ -458,6 +466,7 @@ static const char* status_text(int s) {
     case ST_ADLER: return "Adler-32 mismatch";
     case ST_FILTER: return "bad row filter type";
     case ST_TRUNC: return "truncated stream";
+    case ST_BIG: return "code tables exceed the decoder's capacity";
     default: return "unknown";
   }
 }
@@ -504,20 +513,36 @@ int png_decode_batch_device(vo_ctx* ctx, const uint8_t* const* files, const size
   int* hstat; VO_TRY(pin_buf(ctx, "png_hstat", (size_t)n, &hstat));
   VO_CUDA(cudaMemcpyAsync(dstage, hstage, off, cudaMemcpyHostToDevice, st));
   VO_CUDA(cudaMemcpyAsync(djobs, hjobs, (size_t)n * sizeof(Job), cudaMemcpyHostToDevice, st));
-  VO_TRY(ensure_dyn_smem_of(png_inflate_kernel, sizeof(Smem)));
+  using SmSmall = Smem<LL_SUB_SMALL, D_SUB_SMALL>;
+  using SmFull = Smem<LL_SUB_FULL, D_SUB_FULL>;
+  VO_TRY(ensure_dyn_smem_of(png_inflate_kernel<LL_SUB_FULL, D_SUB_FULL>, sizeof(SmFull)));
   const size_t unf_smem = (size_t)((cols + 15) & ~15) + (size_t)2 * rows * sizeof(uint32_t);
   VO_TRY(ensure_dyn_smem_of(png_unfilter_kernel, unf_smem));
+  uint32_t* dwant = reinterpret_cast<uint32_t*>(dstat + n);
   {
     ProfScope ps(ctx, st, "png_inflate", (double)off + (double)n * n_raw);
-    png_inflate_kernel<<<n, 32, sizeof(Smem), st>>>(dstage, djobs, draw, raw_stride, n_raw, dstat, reinterpret_cast<uint32_t*>(dstat + n));
+    png_inflate_kernel<LL_SUB_SMALL, D_SUB_SMALL><<<n, 32, sizeof(SmSmall), st>>>(dstage, djobs, nullptr, draw, raw_stride, n_raw, dstat, dwant);
   }
   {
     ProfScope ps(ctx, st, "png_unfilter", (double)n * (n_raw + (double)rows * cols));
-    png_unfilter_kernel<<<n, 32, unf_smem, st>>>(draw, raw_stride, rows, cols, out_dev, (size_t)rows * cols, dstat,
-                                                 reinterpret_cast<const uint32_t*>(dstat + n));
+    png_unfilter_kernel<<<n, 32, unf_smem, st>>>(draw, raw_stride, rows, cols, out_dev, (size_t)rows * cols, dstat, dwant, nullptr);
   }
   VO_CUDA(cudaMemcpyAsync(hstat, dstat, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
   VO_CUDA(cudaStreamSynchronize(st));
+  // streams whose code tables did not fit the small second level: once more with the full capacity
+  int n_big = 0;
+  for (int i = 0; i < n; ++i) n_big += hstat[i] == ST_BIG;
+  if (n_big) {
+    int* hbig; VO_TRY(pin_buf(ctx, "png_hbig", (size_t)n, &hbig));
+    int* dbig; VO_TRY(dev_buf(ctx, "png_dbig", (size_t)n, &dbig));
+    for (int i = 0, k = 0; i < n; ++i) if (hstat[i] == ST_BIG) hbig[k++] = i;
+    VO_CUDA(cudaMemcpyAsync(dbig, hbig, (size_t)n_big * sizeof(int), cudaMemcpyHostToDevice, st));
+    png_inflate_kernel<LL_SUB_FULL, D_SUB_FULL><<<n_big, 32, sizeof(SmFull), st>>>(dstage, djobs, dbig, draw, raw_stride, n_raw, dstat, dwant);
+    png_unfilter_kernel<<<n_big, 32, unf_smem, st>>>(draw, raw_stride, rows, cols, out_dev, (size_t)rows * cols, dstat, dwant, dbig);
+    ctx->kernel_launches += 2;
+    VO_CUDA(cudaMemcpyAsync(hstat, dstat, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    VO_CUDA(cudaStreamSynchronize(st));
+  }
   for (int i = 0; i < n; ++i)
     if (hstat[i] != ST_OK) { set_error("png %d: %s", i, status_text(hstat[i])); return VO_ERR_ARG; }
   return VO_OK;

@@ -1324,7 +1324,7 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
   constexpr int D = 4, N = 8, HLEN = (D + 2) * (D + 2) * (N + 2);
   __shared__ uint32_t s_hist[4][DESC_COPIES * HLEN];
   __shared__ unsigned s_row[4][DESC_MAX_ROWS + 3];
-  __shared__ float s_vec[4][128];
+  __shared__ __align__(16) float s_vec[4][128];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int n = min(counters[b * 4 + 2], kp_cap);
@@ -1484,15 +1484,21 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
       s_vec[wib][e] = (float)v * SIFT_INV_FIX;
     }
     __syncwarp();
+    // the two norms are sequential folds in the oracle's order (k ascending); the values come four per load
     float nrm2 = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < 128; ++k) nrm2 = fmaf(s_vec[wib][k], s_vec[wib][k], nrm2);   // oracle order
+    const float4* sv4 = reinterpret_cast<const float4*>(s_vec[wib]);
+#pragma unroll 4
+    for (int q = 0; q < 32; ++q) {
+      const float4 v = sv4[q];
+      nrm2 = fmaf(v.x, v.x, nrm2); nrm2 = fmaf(v.y, v.y, nrm2); nrm2 = fmaf(v.z, v.z, nrm2); nrm2 = fmaf(v.w, v.w, nrm2);
+    }
     const float thr = __fsqrt_rn(nrm2) * 0.2f;
     nrm2 = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < 128; ++k) {
-      const float v = fminf(s_vec[wib][k], thr);
-      nrm2 = fmaf(v, v, nrm2);
+#pragma unroll 4
+    for (int q = 0; q < 32; ++q) {
+      const float4 v = sv4[q];
+      const float a = fminf(v.x, thr), b2 = fminf(v.y, thr), c2 = fminf(v.z, thr), d2 = fminf(v.w, thr);
+      nrm2 = fmaf(a, a, nrm2); nrm2 = fmaf(b2, b2, nrm2); nrm2 = fmaf(c2, c2, nrm2); nrm2 = fmaf(d2, d2, nrm2);
     }
     const float sn = __fsqrt_rn(nrm2);
     const float sc = __fdiv_rn(512.f, fmaxf(sn, FLT_EPSILON));
