@@ -150,49 +150,87 @@ def run_sequence(left_files, right_files, P1, P2, batch=32, seed=0, threads=0, c
 
 
 class DevicePngPipeline:
-    """PNG files -> poses with the decode on the GPU (vo_png.cu) and ``depth`` batches in flight: one context, one
-    device batch buffer and one host thread per slot.  A slot reads the files of its batch (left and right together:
-    one decode launch, one warp per image), then runs vo_frames_dev on the decoded buffer.  The serial inflate of a
-    batch (tens of milliseconds of latency, a few per cent of the SMs) hides behind the SIFT kernels of the other
-    slots; the host only reads files and gathers IDAT chunks."""
+    """PNG files -> poses with the decode on the GPU (vo_png.cu).  Two pools of host threads, each thread with its
+    own context (stream): ``decoders`` slots read the files of a batch (left and right together: one decode launch, one
+    warp per image) into a device batch buffer; ``depth`` slots run vo_frames_dev on decoded buffers.  The serial
+    inflate of a batch is tens of milliseconds of latency on a few per cent of the SMs, so many batches are kept in
+    decode at once (a decode slot costs one 31 MB buffer), while three frame-loop slots (7.5 GB of pyramids each)
+    are enough to saturate the SMs.  The host only reads files and gathers IDAT chunks."""
 
-    def __init__(self, rows, cols, batch=32, depth=6, device=0, threads=2):
+    def __init__(self, rows, cols, batch=32, depth=3, decoders=10, device=0, threads=2):
         import torch
         from . import api
         self.rows, self.cols, self.batch, self.device, self.threads = rows, cols, batch, device, threads
-        self.ctxs = [api.Context(device) for _ in range(max(1, depth))]
+        self.frame_ctxs = [api.Context(device) for _ in range(max(1, depth))]
+        self.decode_ctxs = [api.Context(device) for _ in range(max(1, decoders))]
+        n_buf = len(self.frame_ctxs) + len(self.decode_ctxs) + 2
         self.bufs = [torch.empty((2 * (batch + 1), rows, cols), dtype=torch.uint8, device=torch.device("cuda", device))
-                     for _ in self.ctxs]
+                     for _ in range(n_buf)]
 
     def run(self, left_files, right_files, P1, P2, seed=0):
         """Returns (rel_pose [n,4,4], status [n], counts [n,8])."""
+        import queue
         import threading
         from . import vo
         n, batch, rows, cols = len(left_files), self.batch, self.rows, self.cols
         assert len(right_files) == n and n > 0
         chunks = [(max(b0 - 1, 0), min(b0 + batch, n)) for b0 in range(0, n, batch)]   # [lo, hi) with halo
         rel = np.tile(np.eye(4), (n, 1, 1)); status = np.zeros(n, dtype=np.int32); counts = np.zeros((n, 8), dtype=np.int32)
+        free = queue.Queue()
+        for b in self.bufs:
+            free.put(b)
+        ready = queue.Queue()
         nxt = iter(range(len(chunks)))
         lock = threading.Lock()
         err = []
 
-        def worker(ctx, buf):
+        live = [len(self.decode_ctxs)]
+
+        def decoder(ctx):
             try:
                 while not err:
                     with lock:
                         k = next(nxt, None)
                     if k is None:
-                        return
+                        break
                     lo, hi = chunks[k]
-                    m = hi - lo
-                    read_batch_dev(list(left_files[lo:hi]) + list(right_files[lo:hi]), rows, cols, buf, ctx, self.threads)
-                    r, s, c = vo.run_frames(None, None, P1, P2, seed=seed, first_frame=lo, ctx=ctx,
-                                            device_ptrs=(buf[0].data_ptr(), buf[m].data_ptr(), m, rows, cols))
-                    first = 0 if lo == 0 else 1
-                    rel[lo + first:hi] = r[first:]; status[lo + first:hi] = s[first:]; counts[lo + first:hi] = c[first:]
+                    buf = free.get()
+                    try:
+                        read_batch_dev(list(left_files[lo:hi]) + list(right_files[lo:hi]), rows, cols, buf, ctx, self.threads)
+                    except BaseException:
+                        free.put(buf)
+                        raise
+                    ready.put((k, buf))
             except BaseException as e:   # noqa: BLE001  (surfaced in the caller's thread)
                 err.append(e)
-        th = [threading.Thread(target=worker, args=(c, b)) for c, b in zip(self.ctxs, self.bufs)][:len(chunks)]
+            finally:
+                with lock:
+                    live[0] -= 1
+                    last = live[0] == 0
+                if last:                      # every batch has been queued: one end marker per frame thread
+                    for _ in self.frame_ctxs:
+                        ready.put(None)
+
+        def framer(ctx):
+            while True:
+                item = ready.get()
+                if item is None:
+                    return
+                k, buf = item
+                try:
+                    if not err:               # after a failure the queue is only drained (the decoders must not block)
+                        lo, hi = chunks[k]
+                        m = hi - lo
+                        r, s, c = vo.run_frames(None, None, P1, P2, seed=seed, first_frame=lo, ctx=ctx,
+                                                device_ptrs=(buf[0].data_ptr(), buf[m].data_ptr(), m, rows, cols))
+                        first = 0 if lo == 0 else 1
+                        rel[lo + first:hi] = r[first:]; status[lo + first:hi] = s[first:]; counts[lo + first:hi] = c[first:]
+                except BaseException as e:   # noqa: BLE001
+                    err.append(e)
+                finally:
+                    free.put(buf)
+        th = [threading.Thread(target=decoder, args=(c,)) for c in self.decode_ctxs] + \
+             [threading.Thread(target=framer, args=(c,)) for c in self.frame_ctxs]
         [t.start() for t in th]
         [t.join() for t in th]
         if err:
@@ -200,16 +238,17 @@ class DevicePngPipeline:
         return rel, status, counts
 
     def close(self):
-        for c in self.ctxs:
+        for c in self.frame_ctxs + self.decode_ctxs:
             c.close()
         self.bufs = []
 
 
-def run_sequence_device(left_files, right_files, P1, P2, batch=32, seed=0, depth=6, device=0, threads=2):
+def run_sequence_device(left_files, right_files, P1, P2, batch=32, seed=0, depth=3, decoders=10, device=0, threads=2):
     """run_sequence with the PNG decode on the GPU (DevicePngPipeline for one call)."""
     with open(left_files[0], "rb") as f:
         rows, cols, _, _ = png_info(f.read(64))
-    pipe = DevicePngPipeline(rows, cols, batch=batch, depth=min(depth, max(1, (len(left_files) + batch - 1) // batch)), device=device,
+    n_chunks = max(1, (len(left_files) + batch - 1) // batch)
+    pipe = DevicePngPipeline(rows, cols, batch=batch, depth=min(depth, n_chunks), decoders=min(decoders, n_chunks), device=device,
                              threads=threads)
     try:
         return pipe.run(left_files, right_files, P1, P2, seed=seed)

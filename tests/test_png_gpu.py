@@ -89,9 +89,28 @@ def test_device_decode_opencv_files_at_kitti_size(ctx, tmp_path):
     io.read_batch_dev(lf + rf, 376, 1241, out, ctx)
     got = out.cpu().numpy()
     assert np.array_equal(got[:5], left) and np.array_equal(got[5:], right)
-    rel, status, counts = io.run_sequence_device(lf, rf, synth.KITTI_P0, synth.KITTI_P1, batch=2, seed=5, depth=2)
+    rel, status, counts = io.run_sequence_device(lf, rf, synth.KITTI_P0, synth.KITTI_P1, batch=2, seed=5, depth=2, decoders=3)
     rel0, status0, counts0 = vo.run_frames(left, right, synth.KITTI_P0, synth.KITTI_P1, seed=5, ctx=ctx)
     assert np.array_equal(rel, rel0) and np.array_equal(status, status0) and np.array_equal(counts, counts0)
+
+
+def test_device_pipeline_surfaces_a_bad_file(ctx, tmp_path):
+    """A corrupt file in the middle of a sequence ends the pipelined run with the decoder's error (no hang, no poses
+    for a buffer that was not decoded)."""
+    cv2 = pytest.importorskip("cv2")
+    from vo_b200 import io, synth, VoError
+    left, right = synth.shift_stream(6, seed=4, h=94, w=311)
+    lf, rf = [], []
+    for i in range(6):
+        for name, arr, lst in (("l", left, lf), ("r", right, rf)):
+            p = os.path.join(tmp_path, f"{name}{i:06d}.png")
+            assert cv2.imwrite(p, arr[i]); lst.append(p)
+    data = bytearray(open(lf[3], "rb").read())
+    for k in range(200, 260):
+        data[k] ^= 0x5A
+    open(lf[3], "wb").write(bytes(data))
+    with pytest.raises(VoError, match="png"):
+        io.run_sequence_device(lf, rf, synth.KITTI_P0, synth.KITTI_P1, batch=2, seed=5, depth=2, decoders=3)
 
 
 def test_device_decode_rejects_malformed_files(ctx):
