@@ -242,3 +242,31 @@ def test_vo_frames_with_unique_matches(ctx):
             assert np.array_equal(a, rel[i]) and np.allclose(a, b, atol=1e-9)
             assert [g.log[i][k] for k in ("k0", "k1", "k2", "k3", "k4")] == counts[i, 2:7].tolist()
             assert [o.log[i][k] for k in ("k0", "k1", "k2", "k3", "k4")] == counts[i, 2:7].tolist()
+
+
+def test_column_major_frames_on_device_and_landmark_edge_cases(ctx):
+    """vo_frames_dev with MATLAB-ordered stacks already in device memory (transposed by a kernel) equals the row-major
+    run; the landmark pass on a batch with failed frames (blank images: estworldpose status 1) and on a one-frame batch
+    returns no rows for them."""
+    import torch
+    from vo_b200 import vo, synth
+    left, right = _frames(4, seed=41)
+    want = vo.run_frames(left, right, synth.KITTI_P0, synth.KITTI_P1, seed=2, ctx=ctx)
+    lt = torch.from_numpy(np.ascontiguousarray(np.transpose(left, (0, 2, 1)))).cuda()
+    rt = torch.from_numpy(np.ascontiguousarray(np.transpose(right, (0, 2, 1)))).cuda()
+    got = vo.run_frames(None, None, synth.KITTI_P0, synth.KITTI_P1, seed=2, ctx=ctx, col_major=True,
+                        device_ptrs=(lt.data_ptr(), rt.data_ptr(), 4, 188, 620))
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    l2 = left.copy(); r2 = right.copy()
+    l2[2] = 127; r2[2] = 127
+    rel, status, counts = vo.run_frames(l2, r2, synth.KITTI_P0, synth.KITTI_P1, seed=2, ctx=ctx)
+    assert status.tolist() == [0, 0, 1, 1]
+    lm = vo.frames_landmarks(np.tile(np.eye(4), (4, 1, 1)), cap=4096, ctx=ctx)
+    assert len(lm[0]) == 0 and len(lm[1]) >= 2 and len(lm[2]) == 0 and len(lm[3]) == 0
+    vo.run_frames(left[:1], right[:1], synth.KITTI_P0, synth.KITTI_P1, seed=2, ctx=ctx)
+    assert [len(a) for a in vo.frames_landmarks(np.eye(4)[None], ctx=ctx)] == [0]
+    import vo_b200
+    with pytest.raises(vo_b200.VoError, match="cap"):
+        vo.run_frames(left, right, synth.KITTI_P0, synth.KITTI_P1, seed=2, ctx=ctx)
+        vo.frames_landmarks(np.tile(np.eye(4), (4, 1, 1)), cap=1, ctx=ctx)
