@@ -54,6 +54,7 @@ struct SiftPlan {
   CUtensorMap tm_dog[MAX_OCT];     // the same view of the DoG stack, box {256, 4, 1} (extrema input via TMA)
   int cand_cap = 0, kp_cap = 0;
   uint32_t* cand = nullptr; int* counters = nullptr;   // counters[b*4 + {0:cand,1:raw kp,2:final}]
+  int* work = nullptr;                                  // work[b*2 + {0: next refined candidate, 1: next keypoint}] (dynamic scheduling)
   vo_keypoint* raw = nullptr; vo_keypoint* sorted = nullptr; vo_keypoint* final_kp = nullptr;
   float* desc = nullptr; float2* trig = nullptr; struct RefinedKp* refined = nullptr;
   size_t layer_elems(int o) const { return (size_t)batch * h[o] * pitch[o]; }
@@ -64,7 +65,7 @@ struct SiftPlan {
 void sift_plan_destroy(SiftPlan* p) {
   if (!p) return;
   cudaFree(p->gauss); cudaFree(p->dog); cudaFree(p->img); cudaFree(p->img_t); cudaFree(p->cand);
-  cudaFree(p->counters); cudaFree(p->raw); cudaFree(p->sorted); cudaFree(p->final_kp); cudaFree(p->desc); cudaFree(p->trig); cudaFree(p->refined);
+  cudaFree(p->counters); cudaFree(p->work); cudaFree(p->raw); cudaFree(p->sorted); cudaFree(p->final_kp); cudaFree(p->desc); cudaFree(p->trig); cudaFree(p->refined);
   delete p;
 }
 
@@ -1035,13 +1036,18 @@ sift_refine_kernel(const float* __restrict__ dog, const OctInfo oi, int batch, i
 // Orientation: WARP per refined keypoint.
 __global__ void __launch_bounds__(128)
 sift_orient_kernel(const float* __restrict__ gauss, const OctInfo oi, int batch, const RefinedKp* __restrict__ refined,
-                   int cand_cap, int* __restrict__ counters, vo_keypoint* __restrict__ raw, int kp_cap) {
+                   int cand_cap, int* __restrict__ counters, vo_keypoint* __restrict__ raw, int kp_cap, int* __restrict__ work) {
   __shared__ uint32_t s_hist[4][ORI_BINS];
   __shared__ float s_sm[4][ORI_BINS + 4];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int n_ref = min(counters[b * 4 + 3], cand_cap);
-  for (int ci = blockIdx.x * 4 + wib; ci < n_ref; ci += gridDim.x * 4) {
+  // candidates are handed out one at a time (their windows differ 4x in size: a fixed assignment leaves warps idle)
+  for (;;) {
+    int ci = 0;
+    if (lane == 0) ci = atomicAdd(&work[b * 2 + 0], 1);
+    ci = __shfl_sync(0xffffffffu, ci, 0);
+    if (ci >= n_ref) break;
     const RefinedKp rk = refined[(size_t)b * cand_cap + ci];
     const int o = rk.where >> 28, layer = (rk.where >> 25) & 7, r = (rk.where >> 13) & 4095, c = rk.where & 8191;
     const int rows = oi.h[o], cols = oi.w[o], pitch = oi.pitch[o];
@@ -1320,7 +1326,7 @@ __global__ void __launch_bounds__(128, 10)
 sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int batch, int nl,
                        const vo_keypoint* __restrict__ kps, const float2* __restrict__ trig, int kp_cap,
                        const int* __restrict__ counters, float loc_offset, float* __restrict__ desc,
-                       unsigned long long* __restrict__ algo_bytes) {
+                       unsigned long long* __restrict__ algo_bytes, int* __restrict__ work) {
   constexpr int D = 4, N = 8, HLEN = (D + 2) * (D + 2) * (N + 2);
   __shared__ uint32_t s_hist[4][DESC_COPIES * HLEN];
   __shared__ unsigned s_row[4][DESC_MAX_ROWS + 3];
@@ -1330,7 +1336,12 @@ sift_descriptor_kernel(const float* __restrict__ gauss, const OctInfo oi, int ba
   const int n = min(counters[b * 4 + 2], kp_cap);
   uint32_t* hist = s_hist[wib] + (lane & (DESC_COPIES - 1)) * HLEN;
   unsigned long long my_bytes = 0;
-  for (int ki = blockIdx.x * 4 + wib; ki < n; ki += gridDim.x * 4) {
+  // keypoints are handed out one at a time (dynamic scheduling: window sizes differ 4x within an octave)
+  for (;;) {
+    int ki = 0;
+    if (lane == 0) ki = atomicAdd(&work[b * 2 + 1], 1);
+    ki = __shfl_sync(0xffffffffu, ki, 0);
+    if (ki >= n) break;
     const vo_keypoint kp = kps[(size_t)b * kp_cap + ki];
     int oc = kp.octave & 255; const int layer = (kp.octave >> 8) & 255;
     oc = oc < 128 ? oc : (-128 | oc);
@@ -1654,6 +1665,7 @@ static int get_plan(vo_ctx* ctx, int rows, int cols, int batch, const vo_sift_op
   A((void**)&p->gauss, (gtot + 256) * sizeof(float)); A((void**)&p->dog, dtot * sizeof(float));
   A((void**)&p->img, (size_t)batch * rows * cols); A((void**)&p->img_t, (size_t)batch * rows * cols);
   A((void**)&p->cand, (size_t)batch * p->cand_cap * sizeof(uint32_t)); A((void**)&p->counters, (size_t)batch * 4 * sizeof(int));
+  A((void**)&p->work, (size_t)batch * 2 * sizeof(int));
   A((void**)&p->raw, (size_t)batch * kp_cap * sizeof(vo_keypoint)); A((void**)&p->sorted, (size_t)batch * kp_cap * sizeof(vo_keypoint));
   A((void**)&p->final_kp, (size_t)batch * kp_cap * sizeof(vo_keypoint)); A((void**)&p->desc, (size_t)batch * kp_cap * 128 * sizeof(float));
   A((void**)&p->trig, (size_t)batch * kp_cap * sizeof(float2));
@@ -1687,6 +1699,7 @@ static int get_plan(vo_ctx* ctx, int rows, int cols, int batch, const vo_sift_op
 int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, cudaStream_t st) {
   const int nl = p->nl;
   VO_CUDA(cudaMemsetAsync(p->counters, 0, (size_t)batch * 4 * sizeof(int), st));
+  VO_CUDA(cudaMemsetAsync(p->work, 0, (size_t)batch * 2 * sizeof(int), st));
   // pyramid
   ProfScope* ps_base = new ProfScope(ctx, st, "sift_base_upsample_blur", (double)batch * ((double)p->rows * p->cols + (double)p->h[0] * p->w[0] * 4.0));
   if (p->base_taps.r == 5 && p->h[0] >= 64) {
@@ -1778,7 +1791,7 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
     dim3 g(ctx->num_sms * 4 / (batch > 4 ? 4 : 1), batch);
     ProfScope ps(ctx, st, "sift_refine_orient", 0.0, 0.0, 2);
     sift_refine_kernel<<<dim3(div_up(p->cand_cap / 4, 128), batch), 128, 0, st>>>(p->dog, oi, p->batch, nl, contrast_cv, o.edge_threshold, o.sigma, p->cand, p->cand_cap, p->counters, p->refined);
-    sift_orient_kernel<<<g, 128, 0, st>>>(p->gauss, oi, p->batch, p->refined, p->cand_cap, p->counters, p->raw, p->kp_cap);
+    sift_orient_kernel<<<g, 128, 0, st>>>(p->gauss, oi, p->batch, p->refined, p->cand_cap, p->counters, p->raw, p->kp_cap, p->work);
   }
   {
     dim3 g(p->kp_cap / 256, batch);
@@ -1804,7 +1817,7 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
     }
     ProfScope ps(ctx, st, "sift_descriptor", 0.0, 0.0, 2);
     sift_trig_kernel<<<dim3(8, batch), 256, 0, st>>>(p->final_kp, p->kp_cap, p->counters, p->trig);
-    sift_descriptor_kernel<<<g, 128, 0, st>>>(p->gauss, oi, p->batch, nl, p->final_kp, p->trig, p->kp_cap, p->counters, (float)o.index_base, p->desc, ab);
+    sift_descriptor_kernel<<<g, 128, 0, st>>>(p->gauss, oi, p->batch, nl, p->final_kp, p->trig, p->kp_cap, p->counters, (float)o.index_base, p->desc, ab, p->work);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
