@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--out", default="poses_b200.txt")
+    ap.add_argument("--decode", default="host", choices=["host", "device"],
+                    help="host: the library's PNG decoder on every core; device: inflate + un-filter kernels on the GPU")
     a = ap.parse_args()
     import vo_b200
     from vo_b200 import io, vo, kitti_eval
@@ -33,7 +35,10 @@ def main():
         k, v = line.split(":", 1)
         P[k.strip()] = np.array(v.split(), dtype=np.float64).reshape(3, 4)
     t0 = time.time()
-    rel, status, counts = io.run_sequence(left, right, P["P0"], P["P1"], batch=a.batch, seed=a.seed)
+    if a.decode == "device":
+        rel, status, counts = io.run_sequence_device(left, right, P["P0"], P["P1"], batch=a.batch, seed=a.seed)
+    else:
+        rel, status, counts = io.run_sequence(left, right, P["P0"], P["P1"], batch=a.batch, seed=a.seed)
     dt = time.time() - t0
     bad = np.nonzero(status[1:] != 0)[0] + 1
     for i in bad:
