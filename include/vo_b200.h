@@ -138,6 +138,19 @@ int vo_match_top2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_
 int vo_match_best2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, int n2, int dim,
                        const vo_match_opts* opts, void* records_dev, void* stream);
 
+/* The same shard with the all-gather fused into the match epilogue (one process per GPU, NVLink / NVSwitch peer
+ * stores): peer_bufs[r] is rank r's gathered-record buffer (n_total x 16 bytes, this rank's own one included), each
+ * made with vo_peer_alloc by its owner and mapped here with vo_peer_open (CUDA IPC; the 64-byte handles travel over any
+ * host channel, e.g. torch.distributed.all_gather_object).  The kernel writes record i of this shard to row
+ * first_row + i of EVERY buffer; afterwards one barrier across the ranks (no data) makes all slices visible. */
+int vo_match_best2_gather_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, int n2, int dim,
+                              const vo_match_opts* opts, void* const* peer_bufs, int n_peers, size_t first_row,
+                              void* stream);
+int vo_peer_alloc(vo_ctx* ctx, size_t bytes, void** dev_ptr, uint8_t handle[64]);
+int vo_peer_open(vo_ctx* ctx, const uint8_t handle[64], void** dev_ptr);
+int vo_peer_close(vo_ctx* ctx, void* dev_ptr);
+int vo_peer_free(vo_ctx* ctx, void* dev_ptr);
+
 /* counters of the last vo_match / vo_match_top2 call on this ctx (after synchronisation):
  * stats[0] = 1 if the exact-integer u8 path ran (0: split-bf16 general path),
  * stats[1] = rows re-evaluated by the exact FP32 row scan, stats[2] = GEMM kernel launches,

@@ -1671,6 +1671,22 @@ match_records_kernel(const uint32_t* __restrict__ j1, const float* __restrict__ 
   rec[i] = make_uint4(keep ? j1[i] + (uint32_t)index_base : 0xFFFFFFFFu, __float_as_uint(s1[i]), __float_as_uint(s2[i]), keep ? 1u : 0u);
 }
 
+// The same record written straight into the gathered array of EVERY rank: peers.p[r] is rank r's buffer (this rank's
+// own one included), mapped into this process with CUDA IPC, so the stores to the other GPUs travel over NVLink /
+// NVSwitch while the kernel runs -- the all-gather of the relocalisation shard is the epilogue's own stores and no
+// collective moves data afterwards (one barrier tells the ranks that every slice has landed).
+struct PeerTable { uint4* p[16]; int n; };
+__global__ void __launch_bounds__(256)
+match_records_gather_kernel(const uint32_t* __restrict__ j1, const float* __restrict__ s1, const float* __restrict__ s2,
+                            int n1, int n2, float thr, float max_ratio, int index_base, const PeerTable peers, size_t row0) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n1) return;
+  const bool keep = n2 > 0 && keep_row(s1[i], s2[i], n2, thr, max_ratio);
+  const uint4 rec = make_uint4(keep ? j1[i] + (uint32_t)index_base : 0xFFFFFFFFu, __float_as_uint(s1[i]), __float_as_uint(s2[i]), keep ? 1u : 0u);
+#pragma unroll 4
+  for (int r = 0; r < peers.n; ++r) peers.p[r][row0 + i] = rec;
+}
+
 // --------------------------------------------------------------------------- host plumbing
 static int make_operand_map(CUtensorMap* map, const __nv_bfloat16* base, int rows_alloc, int kp, int n_prob, int box_rows) {
   EncodeTiledFn enc = get_encode_tiled();
@@ -2079,6 +2095,62 @@ int vo_match_best2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2
                                                         o.index_base, static_cast<uint4*>(records_dev));
   ctx->kernel_launches += 1;
   VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+int vo_match_best2_gather_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2_dev, int n2, int dim,
+                              const vo_match_opts* opts, void* const* peer_bufs, int n_peers, size_t first_row, void* stream) {
+  VO_CHECK_ARG(ctx && peer_bufs, "ctx/peer_bufs is null");
+  VO_CHECK_ARG(n1 >= 0 && n2 >= 0, "negative size");
+  VO_CHECK_ARG(n_peers >= 1 && n_peers <= 16, "n_peers must be in 1..16");
+  VO_CHECK_ARG(dim > 0 && dim <= 128, "dim must be in 1..128 (SIFT descriptors are 128-d)");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n1 == 0) return VO_OK;
+  vo_match_opts o; fill_match_opts(opts, &o);
+  Single s; VO_TRY(single_operands(ctx, f1_dev, n1, f2_dev, n2, 0, "f", st, &s));
+  MatchTop2 t;
+  const MatchFilter flt = make_match_filter(o);
+  VO_TRY(match_batch_top2(ctx, s.A, s.B, 1, dim, "f", nullptr, st, &t, &flt));
+  PeerTable pt; pt.n = n_peers;
+  for (int r = 0; r < 16; ++r) pt.p[r] = r < n_peers ? static_cast<uint4*>(peer_bufs[r]) : nullptr;
+  for (int r = 0; r < n_peers; ++r) VO_CHECK_ARG(pt.p[r] != nullptr, "a peer buffer is null");
+  match_records_gather_kernel<<<div_up(n1, 256), 256, 0, st>>>(t.j1, t.s1, t.s2, n1, n2, o.match_threshold * 0.04f, o.max_ratio,
+                                                               o.index_base, pt, first_row);
+  ctx->kernel_launches += 1;
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+// Buffers that other processes (one per GPU) can write into: cudaMalloc + CUDA IPC.
+int vo_peer_alloc(vo_ctx* ctx, size_t bytes, void** dev_ptr, uint8_t handle[64]) {
+  VO_CHECK_ARG(ctx && dev_ptr && handle && bytes > 0, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  VO_CUDA(cudaMalloc(dev_ptr, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *dev_ptr);
+  if (e != cudaSuccess) { cudaFree(*dev_ptr); *dev_ptr = nullptr; set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); return VO_ERR_CUDA; }
+  memcpy(handle, &h, 64);
+  return VO_OK;
+}
+int vo_peer_open(vo_ctx* ctx, const uint8_t handle[64], void** dev_ptr) {
+  VO_CHECK_ARG(ctx && dev_ptr && handle, "bad argument");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h; memcpy(&h, handle, 64);
+  VO_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return VO_OK;
+}
+int vo_peer_close(vo_ctx* ctx, void* dev_ptr) {
+  VO_CHECK_ARG(ctx && dev_ptr, "bad argument");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  VO_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return VO_OK;
+}
+int vo_peer_free(vo_ctx* ctx, void* dev_ptr) {
+  VO_CHECK_ARG(ctx && dev_ptr, "bad argument");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  VO_CUDA(cudaFree(dev_ptr));
   return VO_OK;
 }
 

@@ -68,6 +68,41 @@ def run(ctx, rank, world, dist, queries_per_rank=131072, landmarks=1048576, hyps
         dist.all_gather(per_rank, ms)
     ms_call = max(float(t[0]) for t in per_rank)
     ms_gemm = max(float(t[1]) for t in per_rank)
+    # the same shard with the all-gather fused into the match epilogue: peer stores over NVLink, no data collective
+    fused = None
+    try:
+        pg = shard.PeerGather(ctx, n1, rank, world, dist)
+        stream = torch.cuda.ExternalStream(ctx.stream)
+        for _ in range(2):
+            rec_f = pg.run(q, land)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        # timed like the all-gather form above: one call at a time, the caller waits for the records of each call
+        # (back-to-back launches without that wait run into the board's power cap and are not comparable)
+        ctx.profile_enable(True)
+        f0, f1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(reps):
+            rec_f = pg.run(q, land)
+            ctx.sync()
+        f1e.record(stream)
+        torch.cuda.synchronize()
+        pf = ctx.profile(); ctx.profile_enable(False)
+        gf = pf["match_gemm_topk"]
+        msf = torch.tensor([f0.elapsed_time(f1e) / reps, gf["ms"] / gf["launches"]], device=dev, dtype=torch.float64)
+        same = torch.tensor([1.0 if torch.equal(rec_f, rec) else 0.0], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(msf, op=dist.ReduceOp.MAX)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        fused = dict(ms_per_call_max_over_ranks=float(msf[0]), ms_match_gemm_max_over_ranks=float(msf[1]),
+                     ms_beside_the_gemm=float(msf[0] - msf[1]), allgather_form_ms_beside_the_gemm=ms_call - ms_gemm,
+                     equals_allgather_form_on_every_rank=bool(same[0] > 0.5),
+                     note="vo_match_best2_gather_dev: the records kernel stores every 16-byte record into all ranks' buffers (CUDA IPC, "
+                          "NVLink peer stores); one barrier on the launching stream, no count exchange, no host synchronisation")
+        pg.close()
+    except Exception as e:   # noqa: BLE001
+        fused = dict(error=f"{type(e).__name__}: {e}")
     # the sampled query rows live on different ranks: gather them to rank 0 (tiny)
     rows = np.sort(np.random.default_rng(5).permutation(n1)[:n_check])
     mine = torch.zeros((n_check, 128), device=dev)
@@ -122,6 +157,6 @@ def run(ctx, rank, world, dist, queries_per_rank=131072, landmarks=1048576, hyps
                 aggregate_tops_call=ops / ms_call / 1e9, aggregate_tops_gemm=ops / ms_gemm / 1e9,
                 allgather_bytes_per_rank=16 * max(counts), kept_rows=int(keep.sum()), kept_correct=correct,
                 copied_rows=int(cp.sum()), parity_rows_checked=int(n_check) if parity is not None else 0,
-                parity_rows_bit_exact=parity,
+                parity_rows_bit_exact=parity, fused_peer_gather=fused,
                 p3p=dict(points=int(len(idx)), hypotheses=hyps, status=int(status), inliers=int(np.sum(inl)),
                          ms_host_call=1e3 * t_p3p, pose_err_t=err_t, pose_err_R=err_R))

@@ -126,3 +126,91 @@ def relocalise_row_sharded_dev(ctx, queries_dev, landmarks_dev, rank, world, dis
     dist.all_gather_into_tensor(out, rec[:width].contiguous())
     parts = [out[r * width: r * width + counts[r]] for r in range(world)]
     return torch.cat(parts, 0), counts
+
+
+class PeerGather:
+    """Relocalisation shard with the all-gather fused into the match epilogue (vo_match_best2_gather_dev).
+
+    Every rank owns a device buffer for the gathered records of ALL query rows ([n_total, 4] int32 = 16 bytes per row),
+    allocated by the library and exported through CUDA IPC; every rank maps every peer's buffer.  ``run`` then launches
+    the match on this rank's rows: the records kernel stores each 16-byte record into all ``world`` buffers directly
+    (NVLink / NVSwitch peer stores, issued while the kernel runs), so no collective moves data afterwards -- one
+    barrier on the launching stream tells the ranks that every slice has landed.  Slices are the equal ``row_chunks``
+    of the total, so no counts are exchanged and nothing synchronises with the host."""
+
+    def __init__(self, ctx, n_total, rank, world, dist):
+        import ctypes as C
+        import torch
+        from . import _lib
+        self.ctx, self.rank, self.world, self.dist, self.n_total = ctx, rank, world, dist, n_total
+        L = _lib.lib()
+        self._L = L
+        own = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        _lib.check(L.vo_peer_alloc(ctx.handle, C.c_size_t(n_total * 16), C.byref(own), handle))
+        self.own = own.value
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, bytes(handle))
+        else:
+            handles[0] = bytes(handle)
+        self.ptrs = []
+        for r in range(world):
+            if r == rank:
+                self.ptrs.append(self.own)
+            else:
+                p = C.c_void_p()
+                hb = (C.c_uint8 * 64).from_buffer_copy(handles[r])
+                _lib.check(L.vo_peer_open(ctx.handle, hb, C.byref(p)))
+                self.ptrs.append(p.value)
+        self._table = (C.c_void_p * world)(*self.ptrs)
+        self.chunks = row_chunks(n_total, world)
+        self._flag = torch.zeros(1, device=torch.device("cuda", torch.cuda.current_device()))
+        self._stream = torch.cuda.ExternalStream(ctx.stream)
+
+    def records(self):
+        """This rank's gathered buffer as an [n_total, 4] int32 CUDA tensor (columns 1, 2 are float32 bit patterns)."""
+        import torch
+
+        class _Arr:
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = dict(shape=(self.n_total, 4), typestr="<i4", data=(self.own, False), version=3)
+        return torch.as_tensor(a, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def run(self, queries_dev, landmarks_dev, opts=None):
+        """queries_dev: this rank's slice (row_chunks(n_total, world)[rank]) [n1, 128] float32 CUDA; landmarks replicated.
+        Asynchronous: the records are complete on every rank once the launching stream (ctx.stream) has passed the
+        barrier enqueued here."""
+        import ctypes as C
+        import torch
+        from . import _lib
+        lo, hi = self.chunks[self.rank]
+        n1, n2 = int(queries_dev.shape[0]), int(landmarks_dev.shape[0])
+        assert n1 == hi - lo, "the query slice must be this rank's row_chunks share"
+        mo = _lib.MatchOpts(*opts) if opts is not None else None
+        _lib.check(self._L.vo_match_best2_gather_dev(self.ctx.handle, C.c_void_p(queries_dev.data_ptr()), n1,
+                                                     C.c_void_p(landmarks_dev.data_ptr()), n2, int(queries_dev.shape[1]),
+                                                     C.byref(mo) if mo is not None else None, self._table, self.world,
+                                                     C.c_size_t(lo), C.c_void_p(self.ctx.stream)))
+        if self.world > 1:
+            with torch.cuda.stream(self._stream):          # the barrier follows the kernel in stream order
+                self.dist.all_reduce(self._flag)
+        return self.records()
+
+    def close(self):
+        import ctypes as C
+        from . import _lib
+        if self.world > 1:
+            import torch
+            torch.cuda.synchronize()
+            self.dist.barrier()                            # nobody unmaps while a peer may still be writing
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank and p:
+                self._L.vo_peer_close(self.ctx.handle, C.c_void_p(p))
+        if self.world > 1:
+            self.dist.barrier()
+        if self.own:
+            self._L.vo_peer_free(self.ctx.handle, C.c_void_p(self.own))
+            self.own = None
+        self.ptrs = []

@@ -157,6 +157,33 @@ def test_best2_records_row_sharded_equals_unsharded(ctx):
     assert np.array_equal(full[keep, 1].view(np.uint32), ometric.view(np.uint32))
 
 
+def test_peer_gather_records_equal_the_allgather_form(ctx):
+    """vo_match_best2_gather_dev (the all-gather fused into the epilogue: records stored into every rank's CUDA-IPC
+    buffer) on one rank, with the slices of a 3-way sharding written one after the other into the same gathered buffer,
+    equals the plain records of the unsharded match; bench.py --gpus N checks the multi-process form on every rank."""
+    import ctypes as C
+    import torch
+    from vo_b200 import _lib, shard
+    f1, f2 = correlated_pair(1500, 2300, seed=43)
+    q = torch.from_numpy(f1).cuda(); l = torch.from_numpy(f2).cuda()
+    full, _ = shard.relocalise_row_sharded_dev(ctx, q, l, 0, 1)
+    pg = shard.PeerGather(ctx, len(f1), 0, 1, None)
+    got = pg.run(q, l)
+    ctx.sync()
+    assert torch.equal(got, full)
+    L = _lib.lib()
+    got.zero_()
+    for lo, hi in shard.row_chunks(len(f1), 3):          # what three ranks would each store into this rank's buffer
+        qs = q[lo:hi].contiguous()
+        _lib.check(L.vo_match_best2_gather_dev(ctx.handle, C.c_void_p(qs.data_ptr()), hi - lo, C.c_void_p(l.data_ptr()), len(f2), 128,
+                                               None, pg._table, 1, C.c_size_t(lo), C.c_void_p(ctx.stream)))
+    ctx.sync()
+    a, b = got.cpu().numpy(), full.cpu().numpy()
+    keep = b[:, 3] == 1
+    assert np.array_equal(a[:, 3] == 1, keep) and np.array_equal(a[keep], b[keep]) and keep.sum() > 100
+    pg.close()
+
+
 def test_cta_pair_kernel_bit_exact():
     """The experimental variants of the exact-integer kernel -- cta_group::2 CTA pairs (VO_MATCH_PAIRS=1) and
     A operand in TMEM (VO_MATCH_TS=1); switches are read once per process, hence the subprocess -- must
