@@ -166,7 +166,9 @@ def bench_dropin(sleft, sright, n_percall=24, n_batched=129, batch=32):
     dt = time.perf_counter() - t0
     out["percall"] = dict(value=(n_percall - 1) / dt, unit="frames/s", frames=n_percall - 1, ms_per_frame=1e3 * dt / (n_percall - 1),
                           calls_per_frame=9, note="vo_sift_mex x2, vo_match_mex x5, vo_triangulate_mex, vo_p3p_mex per frame; "
-                                                  "MATLAB-side indexing done in NumPy; includes building every mxArray input")
+                                                  "MATLAB-side indexing done in NumPy; includes the stand-in host's own copies of every "
+                                                  "input into a fresh mxArray and of every output back (0.7 ms per 3 k x 128 descriptor "
+                                                  "matrix: tools/mex_percall_probe.py), which a MATLAB session does not make")
     # (b) batched gateway: stacks of batch+1 frames (one-frame halo), the stacks already MATLAB arrays
     nb = (min(n_batched, len(sleft)) - 1) // batch
     hs = [stack_handles(host, sleft[b * batch: b * batch + batch + 1], sright[b * batch: b * batch + batch + 1]) for b in range(nb)]

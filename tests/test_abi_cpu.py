@@ -51,3 +51,27 @@ def test_mex_gateways_export_mexfunction():
         assert os.path.exists(so), f"{so} missing: run python __graft_entry__.py"
         lib = C.CDLL(so, mode=os.RTLD_LAZY)
         assert hasattr(lib, "mexFunction")
+
+
+def test_gateways_fail_loudly_without_a_gpu_and_check_their_arguments():
+    """The MEX gateways through the stand-in MATLAB host on a CPU-only box: argument errors are raised before any
+    device work, and a valid call ends in mexErrMsgIdAndTxt("vo:ctx:create", ... no CPU fallback), never in a result."""
+    import numpy as np
+    import torch
+    from vo_b200 import mexhost, reloc, shard, io   # noqa: F401  (the host-side modules import without a GPU)
+    h = mexhost.Host()
+    f = np.zeros((4, 128), dtype=np.float32)
+    with pytest.raises(mexhost.MexError, match="vo:match:class"):
+        h.call("vo_match_mex", 1, f.astype(np.float64), f.astype(np.float64))
+    with pytest.raises(mexhost.MexError, match="vo:frames:class"):
+        h.call("vo_frames_mex", 1, np.zeros((8, 8, 2), np.float32), np.zeros((8, 8, 2), np.float32), np.eye(3, 4), np.eye(3, 4))
+    with pytest.raises(mexhost.MexError, match="vo:frames:size"):
+        h.call("vo_frames_mex", 1, np.zeros((8, 8, 2), np.uint8), np.zeros((8, 8, 3), np.uint8), np.eye(3, 4), np.eye(3, 4))
+    with pytest.raises(mexhost.MexError, match="vo:sift:nargin"):
+        h.call("vo_sift_mex", 1)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mexhost.MexError, match="no CPU fallback"):
+        h.call("vo_match_mex", 1, f, f)
+    with pytest.raises(mexhost.MexError, match="no CPU fallback"):
+        h.call("vo_frames_mex", 1, np.zeros((8, 8, 2), np.uint8), np.zeros((8, 8, 2), np.uint8), np.eye(3, 4), np.eye(3, 4))
