@@ -297,6 +297,8 @@ __device__ __forceinline__ u64 f2_bcast(float k) { const float2 v = make_float2(
 // leaves a single __syncthreads per chunk.
 // Box rows hold 164 floats (x0 - 16 .. x0 + 147) and ring rows 132: both strides are 4 (mod 32) banks, so eight lanes
 // that read or write 16 bytes in eight different rows / row-column combinations touch 32 different banks (MODE 2).
+// next octave's seed, written by the blur that produces layer nl: G[o+1][0](y, x) = G[o][nl](2y, 2x)
+struct DsOut { float* dst; int pitch, h, w; };
 constexpr int TS_W = 128, TS_G = 16, TS_HALO = 16, TS_BOXW = TS_W + 2 * TS_HALO + 4, TS_RS = TS_W + 4;
 __host__ __device__ constexpr int TS_MIRROR(int r) { return 3 + 2 * r; }
 // PACK: the row pass runs on packed f32x2 too.  A lane's four outputs are the pairs (c, c+1) and (c+2, c+3); the tap
@@ -308,11 +310,11 @@ __host__ __device__ constexpr int TS_MIRROR(int r) { return 3 + 2 * r; }
 // MODE 2: a lane computes EIGHT consecutive outputs of one row, and a warp covers two rows (lane = segment * 2 + row):
 // 8 + 2R taps are loaded for 8 outputs instead of 4 + 2R for 4, i.e. 20 instead of 36 bytes of shared memory per pixel at
 // R = 13 -- the kernel is bound by shared-memory traffic, not by its arithmetic.
-template <int R, int MODE>
+template <int R, int MODE, bool DS>
 __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3)
 sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* __restrict__ dst,
                      float* __restrict__ dog, const float* __restrict__ src, int h, int w, int pitch,
-                     int seg_rows, const Taps taps) {
+                     int seg_rows, const Taps taps, const DsOut ds) {
   static_assert(R <= TS_HALO, "halo too small");
   // ring slots 0..MIRROR-1 are kept a second time at RING + slot, so the 4 + 2R consecutive rows a
   // column window reads are always contiguous in shared memory (one base address, immediate offsets)
@@ -517,6 +519,9 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
           const float2 v = *reinterpret_cast<const float2*>(&acc[o]);
           *reinterpret_cast<float2*>(dst_i + g) = v;
           *reinterpret_cast<float2*>(dog_i + g) = make_float2(v.x - cc[o].x, v.y - cc[o].y);
+          if constexpr (DS) {                                                         // x is even: v.x is column 2 * (x / 2)
+            if (!(y & 1) && (y >> 1) < ds.h && (x >> 1) < ds.w) ds.dst[((size_t)b * ds.h + (y >> 1)) * ds.pitch + (x >> 1)] = v.x;
+          }
         }
       }
     }
@@ -1560,7 +1565,7 @@ static int launch_blur_t(const float* src, const uint8_t* src8, float* dst, floa
 
 template <int R, int MODE>
 static int launch_tma_t2(const CUtensorMap& tm, int z_base, const float* src, float* dst, float* dog, int h, int w, int pitch,
-                        int batch, const Taps& t, int num_sms, cudaStream_t st) {
+                         int batch, const Taps& t, int num_sms, cudaStream_t st, const DsOut& ds) {
   const int strips = div_up(w, TS_W);
   int n_seg = 1;
   const int target = num_sms * 6;
@@ -1570,31 +1575,38 @@ static int launch_tma_t2(const CUtensorMap& tm, int z_base, const float* src, fl
   n_seg = div_up(h, seg_rows);
   dim3 grid(strips, n_seg, batch);
   constexpr int smem = 2 * TS_G * TS_BOXW * 4 + (MODE == 1 ? 8 * TS_BOXW * 4 : 0) + (64 + TS_MIRROR(R)) * TS_RS * 4 + 64;
-  VO_TRY(ensure_dyn_smem_of(sift_blur_tma_kernel<R, MODE>, smem));
-  sift_blur_tma_kernel<R, MODE><<<grid, 256, smem, st>>>(tm, z_base, dst, dog, src, h, w, pitch, seg_rows, t);
+  if (ds.dst != nullptr) {
+    VO_TRY(ensure_dyn_smem_of(sift_blur_tma_kernel<R, MODE, true>, smem));
+    sift_blur_tma_kernel<R, MODE, true><<<grid, 256, smem, st>>>(tm, z_base, dst, dog, src, h, w, pitch, seg_rows, t, ds);
+  } else {
+    VO_TRY(ensure_dyn_smem_of(sift_blur_tma_kernel<R, MODE, false>, smem));
+    sift_blur_tma_kernel<R, MODE, false><<<grid, 256, smem, st>>>(tm, z_base, dst, dog, src, h, w, pitch, seg_rows, t, ds);
+  }
   return VO_OK;
 }
 // VO_BLUR_ROW selects the row pass: 2 (default) = eight outputs per lane, 0 = four outputs per lane (round 1),
 // 1 = packed f32x2 (measured slower: 3.27 vs 2.45 ms per step, it reads more shared memory per pixel; kept for A/B runs)
 template <int R>
 static int launch_tma_t(const CUtensorMap& tm, int z_base, const float* src, float* dst, float* dog, int h, int w, int pitch,
-                        int batch, const Taps& t, int num_sms, cudaStream_t st) {
+                        int batch, const Taps& t, int num_sms, cudaStream_t st, const DsOut& ds) {
   static const int mode = [] { const char* e = getenv("VO_BLUR_ROW"); return e ? atoi(e) : 2; }();
-  if (mode == 1) return launch_tma_t2<R, 1>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
-  if (mode == 0) return launch_tma_t2<R, 0>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
-  return launch_tma_t2<R, 2>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
+  if (mode == 1) return launch_tma_t2<R, 1>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st, ds);
+  if (mode == 0) return launch_tma_t2<R, 0>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st, ds);
+  return launch_tma_t2<R, 2>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st, ds);
 }
 
 // tm/z_base: tensor map of the octave's Gaussian stack and the z index of image 0 of the source layer
+// *ds_done is set when the launched kernel also wrote the next octave's seed (ds.dst != nullptr on the TMA path)
 static int launch_blur(const CUtensorMap& tm, int z_base, const float* src, float* dst, float* dog, int h, int w, int pitch,
-                       int batch, const Taps& t, int num_sms, cudaStream_t st) {
+                       int batch, const Taps& t, int num_sms, cudaStream_t st, const DsOut& ds = DsOut{nullptr, 0, 0, 0},
+                       bool* ds_done = nullptr) {
   if (h >= 64 && w >= 96) {
     switch (t.r) {
-      case 5: return launch_tma_t<5>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
-      case 6: return launch_tma_t<6>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
-      case 8: return launch_tma_t<8>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
-      case 10: return launch_tma_t<10>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
-      case 13: return launch_tma_t<13>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st);
+      case 5: if (ds_done) *ds_done = ds.dst != nullptr; return launch_tma_t<5>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st, ds);
+      case 6: if (ds_done) *ds_done = ds.dst != nullptr; return launch_tma_t<6>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st, ds);
+      case 8: if (ds_done) *ds_done = ds.dst != nullptr; return launch_tma_t<8>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st, ds);
+      case 10: if (ds_done) *ds_done = ds.dst != nullptr; return launch_tma_t<10>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st, ds);
+      case 13: if (ds_done) *ds_done = ds.dst != nullptr; return launch_tma_t<13>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st, ds);
       default: break;
     }
   }
@@ -1726,18 +1738,27 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
     if (!(p->h[oc] >= 64 && p->w[oc] >= 96)) { first_small = oc; break; }
   const int small_cap = first_small < p->n_oct ? p->h[first_small] * p->w[first_small] : 0;
   const bool fuse_small = first_small < p->n_oct && (size_t)small_cap * 12 <= 200 * 1024;
+  bool seeded = false;   // layer 0 of the octave about to be processed was written by the previous octave's blur
   for (int oc = 0; oc < (fuse_small ? first_small : p->n_oct); ++oc) {
     const double px = (double)batch * p->h[oc] * p->w[oc];
-    if (oc > 0) {
+    if (oc > 0 && !seeded) {
       ProfScope ps(ctx, st, "sift_downsample", px * 8.0);
       dim3 g(div_up(p->w[oc], 256), p->h[oc], batch);
       sift_downsample_kernel<<<g, 256, 0, st>>>(p->G(oc - 1, nl), p->G(oc, 0), p->h[oc - 1], p->pitch[oc - 1], p->h[oc], p->w[oc], p->pitch[oc]);
     }
+    seeded = false;
     const bool tma = p->h[oc] >= 64 && p->w[oc] >= 96;   // same test as launch_blur
     const char* nm = tma ? (oc == 0 ? "sift_blur_dog_tma_oct0" : "sift_blur_dog_tma_oct1+") : "sift_blur_dog_small";
+    // the next octave's layer 0 is the 2x decimation of this octave's layer nl: the blur that produces that layer writes it
+    // too (unless the next octave belongs to the shared-memory kernel below, which decimates for itself)
+    const bool next_here = oc + 1 < (fuse_small ? first_small : p->n_oct);
     for (int i = 1; i < nl + 3; ++i) {
       ProfScope ps(ctx, st, nm, px * 12.0);   // read G[l], write G[l+1], write D[l]
-      VO_TRY(launch_blur(p->tm_gauss[oc], (i - 1) * p->batch, p->G(oc, i - 1), p->G(oc, i), p->D(oc, i - 1), p->h[oc], p->w[oc], p->pitch[oc], batch, p->taps[i], ctx->num_sms, st));
+      DsOut ds{nullptr, 0, 0, 0};
+      if (i == nl && next_here) ds = DsOut{p->G(oc + 1, 0), p->pitch[oc + 1], p->h[oc + 1], p->w[oc + 1]};
+      bool done = false;
+      VO_TRY(launch_blur(p->tm_gauss[oc], (i - 1) * p->batch, p->G(oc, i - 1), p->G(oc, i), p->D(oc, i - 1), p->h[oc], p->w[oc], p->pitch[oc], batch, p->taps[i], ctx->num_sms, st, ds, &done));
+      if (i == nl) seeded = done;
     }
   }
   if (fuse_small) {
