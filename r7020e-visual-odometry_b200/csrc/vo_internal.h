@@ -63,6 +63,7 @@ struct vo_ctx {
   std::map<std::string, vo::Scratch> scratch;
   int match_stats[4] = {0, 0, 0, 0};
   long long kernel_launches = 0;   // kernels launched by this context (bench.py's gpu_launches)
+  int landmarks_prepared = 0;      // rows of the landmark set converted by vo_landmarks_prepare (0: none)
   bool prof_enabled = false;
   std::vector<vo::ProfStage> prof_stages;
   std::vector<vo::ProfRec> prof_pending;

@@ -1406,6 +1406,10 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
   // exact-integer path: the tensor-core dot is the oracle's dot, so the epilogue key is already exact;
   // split path: re-score the candidates with the oracle's sequential FP32 dot
   const bool general = (*nonint_flag) != 0;
+  if (general && rb.base == nullptr) {   // non-integer queries against a prepared (u8-only) landmark set: no float rows to re-score with
+    j1_out[orow] = 0xFFFFFFFFu; s1_out[orow] = INFINITY; s2_out[orow] = INFINITY;
+    return;
+  }
   float s[3]; int nc = 0;
   for (int q = 0; q < 3; ++q) {
     if (j[q] == 0xFFFFFFFFu) { s[q] = INFINITY; continue; }
@@ -1732,6 +1736,33 @@ MatchFilter make_match_filter(const vo_match_opts& o) {
   return f;
 }
 
+// Converts the landmark rows of ONE problem once (u8 operand rows, 1/||row||, their maximum) into the scratch buffers
+// that match_batch_top2 uses under `tag`, and keeps the maximum aside: later calls under the same tag with
+// B.prepared = 1 skip the conversion (the float rows are then not read at all).  Integer-valued rows only.
+int match_prepare_landmarks(vo_ctx* ctx, const MatchOperand& B, int dim, const char* tag, cudaStream_t st) {
+  auto nm = [&](const char* base) { return std::string(base) + "_" + tag; };
+  if (dim != 128) { set_error("vo_landmarks_prepare: dim must be 128"); return VO_ERR_ARG; }
+  const int b_alloc = div_up(B.cap > 0 ? B.cap : 1, BN) * BN;
+  int* ctl; VO_TRY(dev_buf(ctx, nm("m_ctl").c_str(), 8 + (size_t)1, &ctl));
+  VO_CUDA(cudaMemsetAsync(ctl, 0, 9 * sizeof(int), st));
+  int* keep_b; VO_TRY(dev_buf(ctx, nm("m_keepB").c_str(), (size_t)1, &keep_b));
+  uint8_t* u8B; VO_TRY(dev_buf(ctx, nm("m_u8B").c_str(), (size_t)b_alloc * 128, &u8B));
+  float* invB; VO_TRY(dev_buf(ctx, nm("m_invB").c_str(), (size_t)b_alloc, &invB));
+  if ((reinterpret_cast<uintptr_t>(B.base) & 15) == 0)
+    match_prep_rows128_kernel<<<dim3(b_alloc / PREP_ROWS, 1), 256, 0, st>>>(B, b_alloc, u8B, invB, ctl, ctl + 8);
+  else {
+    const size_t prep_smem = (size_t)PREP_ROWS * (dim + 1) * sizeof(float);
+    match_prep_kernel<<<dim3(b_alloc / PREP_ROWS, 1), 256, prep_smem, st>>>(B, b_alloc, dim, u8B, invB, ctl, ctl + 8);
+  }
+  ctx->kernel_launches += 1;
+  VO_CUDA(cudaMemcpyAsync(keep_b, ctl + 8, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  int* h; VO_TRY(pin_buf(ctx, "m_prep_flag", 4, &h));
+  VO_CUDA(cudaMemcpyAsync(h, ctl, sizeof(int), cudaMemcpyDeviceToHost, st));
+  VO_CUDA(cudaStreamSynchronize(st));
+  if (h[0] != 0) { set_error("vo_landmarks_prepare: the rows are not integers in 0..255 (prepared landmark sets use the exact-integer path)"); return VO_ERR_ARG; }
+  return VO_OK;
+}
+
 int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, int n_prob, int dim,
                      const char* tag, float* dbg_c, cudaStream_t st, MatchTop2* out, const MatchFilter* filter) {
   const MatchFilter flt = filter ? *filter : MatchFilter{0.f, 0.f, 0.f};
@@ -1745,6 +1776,8 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   int* ctl; VO_TRY(dev_buf(ctx, nm("m_ctl").c_str(), 8 + (size_t)(n_prob > 0 ? n_prob : 1), &ctl));
   VO_CUDA(cudaMemsetAsync(ctl, 0, (8 + (size_t)(n_prob > 0 ? n_prob : 1)) * sizeof(int), st));
   int* invb_max = ctl + 8;   // [n_prob] bit pattern of max_j 1/||b_j||
+  int* keep_b; VO_TRY(dev_buf(ctx, nm("m_keepB").c_str(), (size_t)(n_prob > 0 ? n_prob : 1), &keep_b));   // invb_max of a prepared B
+  if (B.prepared) VO_CUDA(cudaMemcpyAsync(invb_max, keep_b, (size_t)n_prob * sizeof(int), cudaMemcpyDeviceToDevice, st));
   uint8_t *u8A, *u8B;
   VO_TRY(dev_buf(ctx, nm("m_u8A").c_str(), (size_t)(n_prob > 0 ? n_prob : 1) * a_alloc * 128, &u8A));
   __nv_bfloat16 *opA, *opB; float *invA, *invB, *rawA = nullptr, *rawB = nullptr;
@@ -1777,13 +1810,15 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
       match_prep_rows128_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, 0, st>>>(A, a_alloc, u8A, invA, ctl, nullptr);
     else
       match_prep_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, u8A, invA, ctl, nullptr);
-    if (dim == 128 && !B.col_major && (reinterpret_cast<uintptr_t>(B.base) & 15) == 0 && B.prob_stride % 4 == 0)
+    if (B.prepared) {
+      // the landmark rows were converted once (vo_landmarks_prepare): nothing to read, nothing to write
+    } else if (dim == 128 && !B.col_major && (reinterpret_cast<uintptr_t>(B.base) & 15) == 0 && B.prob_stride % 4 == 0)
       match_prep_rows128_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, 0, st>>>(B, b_alloc, u8B, invB, ctl, invb_max);
     else
       match_prep_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, u8B, invB, ctl, invb_max);
     // general float descriptors only (both return at once when every value is an integer 0..255)
     match_prep_split_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, kp, 0, opA, rawA, ctl);
-    match_prep_split_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, kp, 1, opB, rawB, ctl);
+    if (!B.prepared) match_prep_split_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, kp, 1, opB, rawB, ctl);
   }
   VO_CUDA(cudaGetLastError());
 
@@ -2087,14 +2122,28 @@ int vo_match_best2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2
   cudaStream_t st = (cudaStream_t)stream;
   if (n1 == 0) return VO_OK;
   vo_match_opts o; fill_match_opts(opts, &o);
-  Single s; VO_TRY(single_operands(ctx, f1_dev, n1, f2_dev, n2, 0, "f", st, &s));
+  const bool prepared = f2_dev == nullptr;
+  VO_CHECK_ARG(!prepared || (ctx->landmarks_prepared == n2 && dim == 128), "f2_dev is null but no landmark set of this size was prepared (vo_landmarks_prepare)");
+  const char* tag = prepared ? "lm" : "f";
+  Single s; VO_TRY(single_operands(ctx, f1_dev, n1, f2_dev, n2, 0, tag, st, &s));
+  s.B.prepared = prepared ? 1 : 0;
   MatchTop2 t;
   const MatchFilter flt = make_match_filter(o);
-  VO_TRY(match_batch_top2(ctx, s.A, s.B, 1, dim, "f", nullptr, st, &t, &flt));
+  VO_TRY(match_batch_top2(ctx, s.A, s.B, 1, dim, tag, nullptr, st, &t, &flt));
   match_records_kernel<<<div_up(n1, 256), 256, 0, st>>>(t.j1, t.s1, t.s2, n1, n2, o.match_threshold * 0.04f, o.max_ratio,
                                                         o.index_base, static_cast<uint4*>(records_dev));
   ctx->kernel_launches += 1;
   VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+int vo_landmarks_prepare(vo_ctx* ctx, const float* f2_dev, int n2, int dim, void* stream) {
+  VO_CHECK_ARG(ctx && f2_dev && n2 > 0, "null or empty landmark set");
+  VO_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  Single s; VO_TRY(single_operands(ctx, f2_dev, 0, f2_dev, n2, 0, "lm", st, &s));
+  VO_TRY(match_prepare_landmarks(ctx, s.B, dim, "lm", st));
+  ctx->landmarks_prepared = n2;
   return VO_OK;
 }
 
@@ -2108,10 +2157,14 @@ int vo_match_best2_gather_dev(vo_ctx* ctx, const float* f1_dev, int n1, const fl
   cudaStream_t st = (cudaStream_t)stream;
   if (n1 == 0) return VO_OK;
   vo_match_opts o; fill_match_opts(opts, &o);
-  Single s; VO_TRY(single_operands(ctx, f1_dev, n1, f2_dev, n2, 0, "f", st, &s));
+  const bool prepared = f2_dev == nullptr;
+  VO_CHECK_ARG(!prepared || (ctx->landmarks_prepared == n2 && dim == 128), "f2_dev is null but no landmark set of this size was prepared (vo_landmarks_prepare)");
+  const char* tag = prepared ? "lm" : "f";
+  Single s; VO_TRY(single_operands(ctx, f1_dev, n1, f2_dev, n2, 0, tag, st, &s));
+  s.B.prepared = prepared ? 1 : 0;
   MatchTop2 t;
   const MatchFilter flt = make_match_filter(o);
-  VO_TRY(match_batch_top2(ctx, s.A, s.B, 1, dim, "f", nullptr, st, &t, &flt));
+  VO_TRY(match_batch_top2(ctx, s.A, s.B, 1, dim, tag, nullptr, st, &t, &flt));
   PeerTable pt; pt.n = n_peers;
   for (int r = 0; r < 16; ++r) pt.p[r] = r < n_peers ? static_cast<uint4*>(peer_bufs[r]) : nullptr;
   for (int r = 0; r < n_peers; ++r) VO_CHECK_ARG(pt.p[r] != nullptr, "a peer buffer is null");

@@ -128,6 +128,18 @@ def relocalise_row_sharded_dev(ctx, queries_dev, landmarks_dev, rank, world, dis
     return torch.cat(parts, 0), counts
 
 
+def prepare_landmarks(ctx, landmarks_dev):
+    """vo_landmarks_prepare: convert a replicated landmark set ([n2, 128] float32 CUDA tensor of integer-valued SIFT rows)
+    once into the match operand form held by ``ctx``; afterwards the float tensor may be freed and the shard calls take
+    ``landmarks_dev=None``.  Returns n2."""
+    import ctypes as C
+    from . import _lib
+    n2 = int(landmarks_dev.shape[0])
+    _lib.check(_lib.lib().vo_landmarks_prepare(ctx.handle, C.c_void_p(landmarks_dev.data_ptr()), n2, int(landmarks_dev.shape[1]),
+                                              C.c_void_p(ctx.stream)))
+    return n2
+
+
 class PeerGather:
     """Relocalisation shard with the all-gather fused into the match epilogue (vo_match_best2_gather_dev).
 
@@ -178,19 +190,22 @@ class PeerGather:
         a.__cuda_array_interface__ = dict(shape=(self.n_total, 4), typestr="<i4", data=(self.own, False), version=3)
         return torch.as_tensor(a, device=torch.device("cuda", torch.cuda.current_device()))
 
-    def run(self, queries_dev, landmarks_dev, opts=None):
-        """queries_dev: this rank's slice (row_chunks(n_total, world)[rank]) [n1, 128] float32 CUDA; landmarks replicated.
+    def run(self, queries_dev, landmarks_dev, opts=None, n_landmarks=None):
+        """queries_dev: this rank's slice (row_chunks(n_total, world)[rank]) [n1, 128] float32 CUDA; landmarks replicated
+        (``landmarks_dev=None`` with ``n_landmarks`` = the count given to prepare_landmarks: the prepared set is used).
         Asynchronous: the records are complete on every rank once the launching stream (ctx.stream) has passed the
         barrier enqueued here."""
         import ctypes as C
         import torch
         from . import _lib
         lo, hi = self.chunks[self.rank]
-        n1, n2 = int(queries_dev.shape[0]), int(landmarks_dev.shape[0])
+        n1 = int(queries_dev.shape[0])
+        n2 = int(landmarks_dev.shape[0]) if landmarks_dev is not None else int(n_landmarks)
         assert n1 == hi - lo, "the query slice must be this rank's row_chunks share"
         mo = _lib.MatchOpts(*opts) if opts is not None else None
         _lib.check(self._L.vo_match_best2_gather_dev(self.ctx.handle, C.c_void_p(queries_dev.data_ptr()), n1,
-                                                     C.c_void_p(landmarks_dev.data_ptr()), n2, int(queries_dev.shape[1]),
+                                                     C.c_void_p(landmarks_dev.data_ptr()) if landmarks_dev is not None else None, n2,
+                                                     int(queries_dev.shape[1]),
                                                      C.byref(mo) if mo is not None else None, self._table, self.world,
                                                      C.c_size_t(lo), C.c_void_p(self.ctx.stream)))
         if self.world > 1:

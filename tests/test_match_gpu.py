@@ -181,6 +181,18 @@ def test_peer_gather_records_equal_the_allgather_form(ctx):
     a, b = got.cpu().numpy(), full.cpu().numpy()
     keep = b[:, 3] == 1
     assert np.array_equal(a[:, 3] == 1, keep) and np.array_equal(a[keep], b[keep]) and keep.sum() > 100
+    # a prepared landmark set (converted once, float rows no longer needed) gives the same records
+    n2 = shard.prepare_landmarks(ctx, l)
+    del l
+    got.zero_()
+    again = pg.run(q, None, n_landmarks=n2)
+    ctx.sync()
+    assert torch.equal(again, full)
+    import vo_b200
+    with pytest.raises(vo_b200.VoError, match="prepared"):
+        pg.run(q, None, n_landmarks=n2 + 1)
+    with pytest.raises(vo_b200.VoError, match="not integers"):
+        shard.prepare_landmarks(ctx, q * 0.5)
     pg.close()
 
 
