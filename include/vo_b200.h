@@ -149,7 +149,7 @@ int vo_match_best2_gather_dev(vo_ctx* ctx, const float* f1_dev, int n1, const fl
 /* A landmark set that stays on the device (the relocalisation map): converted ONCE into the match operand form
  * (128-byte u8 rows, 1/||row||; 134 MB per million landmarks instead of 512 MB of float rows, which may be freed
  * afterwards).  vo_match_best2_dev / vo_match_best2_gather_dev then take f2_dev = NULL with n2 = the prepared count and
- * skip the conversion on every call.  Rows must be integers 0..255 (SIFT descriptors), dim 128; synchronises once. */
+ * skip the conversion on every call (n2 = 0 with a NULL pointer is the empty set, not the prepared one).  Rows must be integers 0..255 (SIFT descriptors), dim 128; synchronises once. */
 int vo_landmarks_prepare(vo_ctx* ctx, const float* f2_dev, int n2, int dim, void* stream);
 int vo_peer_alloc(vo_ctx* ctx, size_t bytes, void** dev_ptr, uint8_t handle[64]);
 int vo_peer_open(vo_ctx* ctx, const uint8_t handle[64], void** dev_ptr);

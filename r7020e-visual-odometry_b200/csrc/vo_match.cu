@@ -2122,7 +2122,7 @@ int vo_match_best2_dev(vo_ctx* ctx, const float* f1_dev, int n1, const float* f2
   cudaStream_t st = (cudaStream_t)stream;
   if (n1 == 0) return VO_OK;
   vo_match_opts o; fill_match_opts(opts, &o);
-  const bool prepared = f2_dev == nullptr;
+  const bool prepared = f2_dev == nullptr && n2 > 0;    // an empty landmark set has a null pointer too
   VO_CHECK_ARG(!prepared || (ctx->landmarks_prepared == n2 && dim == 128), "f2_dev is null but no landmark set of this size was prepared (vo_landmarks_prepare)");
   const char* tag = prepared ? "lm" : "f";
   Single s; VO_TRY(single_operands(ctx, f1_dev, n1, f2_dev, n2, 0, tag, st, &s));
@@ -2157,7 +2157,7 @@ int vo_match_best2_gather_dev(vo_ctx* ctx, const float* f1_dev, int n1, const fl
   cudaStream_t st = (cudaStream_t)stream;
   if (n1 == 0) return VO_OK;
   vo_match_opts o; fill_match_opts(opts, &o);
-  const bool prepared = f2_dev == nullptr;
+  const bool prepared = f2_dev == nullptr && n2 > 0;    // an empty landmark set has a null pointer too
   VO_CHECK_ARG(!prepared || (ctx->landmarks_prepared == n2 && dim == 128), "f2_dev is null but no landmark set of this size was prepared (vo_landmarks_prepare)");
   const char* tag = prepared ? "lm" : "f";
   Single s; VO_TRY(single_operands(ctx, f1_dev, n1, f2_dev, n2, 0, tag, st, &s));
