@@ -159,7 +159,7 @@ int vo_peer_free(vo_ctx* ctx, void* dev_ptr);
 /* counters of the last vo_match / vo_match_top2 call on this ctx (after synchronisation):
  * stats[0] = 1 if the exact-integer u8 path ran (0: split-bf16 general path),
  * stats[1] = rows re-evaluated by the exact FP32 row scan, stats[2] = GEMM kernel launches,
- * stats[3] = K extent of the GEMM. */
+ * stats[3] = K extent of the GEMM (general path: 128 per bf16 term; one term with a score bound, three without). */
 int vo_match_stats(vo_ctx* ctx, int stats[4]);
 
 /* Debug/unit-test hook: raw tensor-core dot products C = f1 * f2^T (n1 x n2 float32, row-major

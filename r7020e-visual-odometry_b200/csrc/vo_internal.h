@@ -62,6 +62,7 @@ struct vo_ctx {
   cudaStream_t stream = nullptr;
   std::map<std::string, vo::Scratch> scratch;
   int match_stats[4] = {0, 0, 0, 0};
+  int match_float_terms = 3;   // bf16 terms the general-float GEMM of the last call contracted (1 with a score bound)
   long long kernel_launches = 0;   // kernels launched by this context (bench.py's gpu_launches)
   int landmarks_prepared = 0;      // rows of the landmark set converted by vo_landmarks_prepare (0: none)
   bool prof_enabled = false;

@@ -20,6 +20,9 @@
 //                              match_topk_u8x2_kernel (cta_group::2 pairs), match_topk_u8ts_kernel (A in TMEM).
 //      match_topk_kernel       the same structure with kind::f16 on the split-bf16 operands; both kernels
 //                              are launched and one returns at once on the device flag (no host sync).
+//                              With the caller's score bound (matchFeatures) it contracts the hi x hi term
+//                              alone (K = 128 instead of 384, six B stages instead of four) and the certificate
+//                              carries the one-term margin; the exact top-2 mode contracts all three terms.
 //   3. match_finalize_kernel   merges the per-segment candidates, recomputes the oracle's exact FP32 score
 //                              of the candidates and certifies the row from the monotone key -> score map
 //                              (nearest neighbour with lowest index on ties, s2 or a proof that the
@@ -46,12 +49,24 @@ constexpr int UMMA_K = 16;
 constexpr int A_KBLOCK_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;    // 32 KB
 constexpr int MAX_KBLOCKS = 6;                // K' <= 384  (dim <= 128 split, or dim <= 384 exact)
-constexpr int B_STAGES = 4;
+constexpr int B_STAGES = 4;                   // B ring stages beside the 6 A K blocks of the three-term form ...
+constexpr int B_STAGES_MAX = 6;               // ... and what the same shared memory holds when A is shorter (one term: 2 K blocks)
 constexpr int NUM_EPI_WARPS = 16;              // 4 TMEM lane quarters x 4 column quarters of 64
 constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
 constexpr int NCAND = 3;
-constexpr int SMEM_BYTES = MAX_KBLOCKS * A_KBLOCK_BYTES + B_STAGES * B_STAGE_BYTES + 128 + 2 * BN * 4 + BM * 4;   // 232,064 <= 232,448
-constexpr float SPLIT_EPS = 1.0f / 8192.0f;   // |approx key - oracle key| <= 2^-13 * ||a||
+constexpr int SMEM_BYTES = MAX_KBLOCKS * A_KBLOCK_BYTES + B_STAGES * B_STAGE_BYTES + 256 + 2 * BN * 4 + BM * 4;   // 232,192 <= 232,448
+constexpr float SPLIT_EPS = 1.0f / 8192.0f;   // three-term split: |approx key - oracle key| <= 2^-13 * ||a||
+// One-term form (hi x hi only, used when the caller's score bound decides the rows): bf16 keeps 8 significant bits, so
+// |x - hi(x)| <= 2^-8 |x| and |sum a_k b_k - sum hi(a_k) hi(b_k)| <= (2^-7 + 2^-16) sum |a_k b_k| <= 2^-7 (1 + 2^-9) ||a|| ||b||
+// (Cauchy-Schwarz); FP32 accumulation and the sequential oracle dot add < 2^-16 each.  1/128 + 1/2048 leaves room to spare.
+constexpr float ONE_TERM_EPS = 1.0f / 128.0f + 1.0f / 2048.0f;
+// General-float path with a score bound: a column can only matter if its oracle key exceeds key_floor / inva, i.e. if
+// its approximate key exceeds that minus eps * ||a||.  The same expression seeds the epilogue's bound and the
+// certificate in match_finalize_kernel (1.0625: the subtraction itself is rounded).
+__device__ __forceinline__ float general_key_floor(float key_floor, float ia, float eps) {
+  const float na = __fdiv_rn(1.0f, ia);
+  return __fdiv_rn(key_floor, ia) - 1.0625f * eps * na;
+}
 
 // generic mbarrier / TMA wrappers live in vo_ptx.cuh
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -153,9 +168,11 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const float* __restrict__ invb_base, int invb_stride, const int* __restrict__ n1p,
                   int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
                   const int* __restrict__ nonint_flag, int kp_blocks, int n_splits,
-                  uint2* __restrict__ cand_base, size_t cand_stride, float* __restrict__ dbg_c, int dbg_ld) {
+                  uint2* __restrict__ cand_base, size_t cand_stride, float* __restrict__ dbg_c, int dbg_ld,
+                  const float* __restrict__ inva_base, int inva_stride, float key_floor, int terms, float eps,
+                  const int* __restrict__ invb_max_bits) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B-swizzled operand tiles need 1024-byte alignment
-  if (*nonint_flag == 0) return;   // exact-integer inputs are handled by match_topk_fat_kernel
+  if (*nonint_flag == 0) return;   // exact-integer inputs are handled by match_topk_u8_kernel
   const int prob = blockIdx.z;
   const int n1 = min(n1p[prob * n1_stride], cap1), n2 = min(n2p[prob * n2_stride], cap2);
   const int m0 = blockIdx.x * BM;
@@ -180,21 +197,24 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     return;
   }
-  const int kblocks = 3 * kp_blocks;
+  // operands are A' = [hi | hi | lo], B' = [hi | lo | hi]: the first kp_blocks K blocks are the hi x hi term alone
+  const int kblocks = terms * kp_blocks;
 
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();
   const uint32_t sA = base;
-  const uint32_t sB = sA + MAX_KBLOCKS * A_KBLOCK_BYTES;
-  const uint32_t bars = sB + B_STAGES * B_STAGE_BYTES;
+  // the B ring starts right after the A K blocks this launch uses: 4 stages of 32 KB with three terms, 6 with one
+  const uint32_t sB = sA + kblocks * A_KBLOCK_BYTES;
+  const int n_stages = min(B_STAGES_MAX, (MAX_KBLOCKS * A_KBLOCK_BYTES + B_STAGES * B_STAGE_BYTES - kblocks * A_KBLOCK_BYTES) / B_STAGE_BYTES);
+  const uint32_t bars = sA + MAX_KBLOCKS * A_KBLOCK_BYTES + B_STAGES * B_STAGE_BYTES;
   const uint32_t bar_a_full = bars;
-  const uint32_t bar_b_full = bars + 8;                    // [B_STAGES]
-  const uint32_t bar_b_empty = bar_b_full + 8 * B_STAGES;  // [B_STAGES]
-  const uint32_t bar_t_full = bar_b_empty + 8 * B_STAGES;  // [2]
+  const uint32_t bar_b_full = bars + 8;                        // [B_STAGES_MAX]
+  const uint32_t bar_b_empty = bar_b_full + 8 * B_STAGES_MAX;  // [B_STAGES_MAX]
+  const uint32_t bar_t_full = bar_b_empty + 8 * B_STAGES_MAX;  // [2]
   const uint32_t bar_t_empty = bar_t_full + 16;            // [2]
   const uint32_t bar_i_full = bar_t_empty + 16;            // [2]  1/||b|| slice of the tile has landed
   const uint32_t tmem_slot = bar_i_full + 16;
-  const uint32_t s_invb_addr = bars + 128;                 // [2][BN] floats, filled by bulk TMA copies
+  const uint32_t s_invb_addr = bars + 256;                 // [2][BN] floats, filled by bulk TMA copies
   float* s_invb = reinterpret_cast<float*>(smem_raw + (s_invb_addr - smem_u32(smem_raw)));
   float* s_thr = s_invb + 2 * BN;                          // [BM] per-row lower bound of the third-best key
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -203,11 +223,19 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     mbar_init(bar_a_full, 1);
-    for (int s = 0; s < B_STAGES; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
+    for (int s = 0; s < B_STAGES_MAX; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, NUM_EPI_WARPS); mbar_init(bar_i_full + 8 * s, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + BM) s_thr[threadIdx.x - 64] = -INFINITY;
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + BM) {
+    float t0 = -INFINITY;
+    const int r = m0 + (int)threadIdx.x - 64;
+    if (key_floor > 0.f && r < n1) {   // score bound (matchFeatures mode): keys at or below it cannot change the row's outcome
+      const float ia = inva_base[(size_t)prob * inva_stride + r];
+      if (ia > 0.f) t0 = general_key_floor(key_floor, ia, eps);
+    }
+    s_thr[threadIdx.x - 64] = t0;
+  }
   if (warp == 1) {  // whole warp: allocate all 512 TMEM columns (2 accumulator stages x 256)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -227,7 +255,7 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
           mbar_expect_tx(bar_b_full + 8 * stage, B_STAGE_BYTES);
           tma_load_3d(sB + stage * B_STAGE_BYTES, &tmB, bar_b_full + 8 * stage, kb * BK, t * BN, prob);
-          if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
     }
   } else if (warp == 1) {
@@ -262,7 +290,7 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (kb + 1 == kblocks) tc_commit(bar_t_full + 8 * acc);
           }
           __syncwarp();
-          if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
@@ -279,11 +307,16 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int row = m0 + row_in_cta;
     Top3 top; top.init();
     int acc = 0; uint32_t acc_phase = 0;
+    // Prefilter on the raw accumulators (the float counterpart of the u8 kernel's integer test): with a positive bound,
+    //   dot <= thr_raw = RD(thr / max_j 1/||b_j||) * (1 - 2^-20)   implies   fl(dot * 1/||b_j||) <= thr   for every column,
+    // so a chunk whose largest accumulator stays at or below thr_raw needs no key at all: one max tree and one compare.
+    const float ibm = __int_as_float(invb_max_bits[prob]);
     for (int t = t_begin; t < t_end; ++t) {
       mbar_wait(bar_i_full + 8 * acc, acc_phase);
       mbar_wait(bar_t_full + 8 * acc, acc_phase);
       tc_fence_after();
       float thr = fmaxf(top.k3, s_thr[row_in_cta]);
+      const float thr_raw = (thr > 0.f && ibm > 0.f) ? __fdiv_rd(thr, ibm) * 0.99999905f : -INFINITY;
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + cq * 64);
       uint32_t r0[32], r1[32];
       tmem_ld32(tbase, r0);
@@ -300,6 +333,12 @@ match_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int c = 0; c < 32; ++c)
               if (j0 + c < n2) dbg_c[(size_t)row * dbg_ld + j0 + c] = __uint_as_float(r[c]);
           }
+          float rm[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            rm[q] = fmaxf(fmaxf(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), fmaxf(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
+          const float rmax = fmaxf(fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])), fmaxf(fmaxf(rm[4], rm[5]), fmaxf(rm[6], rm[7])));
+          if (!(rmax > thr_raw)) continue;            // nothing in this chunk can beat the row's bound
           float v[32];
           const float4* ibp = reinterpret_cast<const float4*>(s_invb + acc * BN + col_in_tile);
 #pragma unroll
@@ -1369,7 +1408,7 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
                       const float* __restrict__ invb_base, int invb_stride, const int* __restrict__ n1p,
                       int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
                       const int* __restrict__ nonint_flag, int all_slots, int sched_L, int sched_T, MatchFilter flt,
-                      uint32_t* __restrict__ j1_out,
+                      float gen_eps, uint32_t* __restrict__ j1_out,
                       float* __restrict__ s1_out, float* __restrict__ s2_out, int row_stride,
                       int* __restrict__ scan_list, int* __restrict__ scan_count) {
   const int prob = blockIdx.y;
@@ -1428,15 +1467,17 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
   // thread only skipped keys at or below a lower bound of it) or, on the exact-integer path with a
   // score bound, the row's initial key bound.  The score is a monotone function of the key, so every
   // such column has score >= sb.
+  // General floats: the candidate keys are approximate (|approx - oracle| <= gen_eps * ||a||), the candidates' scores
+  // above are exact; a skipped column's oracle key is at most the bound plus that margin.
   float kb = (nc >= 3) ? k[2] : -INFINITY;
-  const bool bounded = !general && flt.key_floor > 0.f && ia > 0.f;
-  if (bounded) kb = fmaxf(kb, __fdiv_rn(flt.key_floor, ia));
+  const bool bounded = flt.key_floor > 0.f && ia > 0.f;
+  if (bounded) kb = fmaxf(kb, general ? general_key_floor(flt.key_floor, ia, gen_eps) : __fdiv_rn(flt.key_floor, ia));
   bool certified;
   float s2v = (n2 >= 2) ? s[1] : INFINITY;
   if (kb == -INFINITY) {
     certified = (nc == n2);            // nothing was skipped: the candidates are all the columns
   } else {
-    if (general) kb = kb + SPLIT_EPS * ((ia > 0.f) ? __fdiv_rn(1.0f, ia) : 0.f);
+    if (general) kb = kb + gen_eps * ((ia > 0.f) ? __fdiv_rn(1.0f, ia) : 0.f);
     const float sb = score_from_key(kb, ia);
     if (!bounded) {
       certified = (nc >= 2) && (sb > s[0]) && (sb >= s[1]);     // (j1, s1, s2) are exactly the oracle's
@@ -1867,8 +1908,25 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
       sched_L = (int)share;
       const int s_max = (T + sched_L - 1) / sched_L + 1;          // segments a panel can be cut into
       n_splits = std::max(n_splits, div_up(2 * s_max, 4));        // candidate row stride (4 slots per split)
+      // the persistent kernel does not use the split count beyond that stride, so it is free to suit the grid of the
+      // general-float kernel (128-row panels x splits, waves of num_sms; about three tile times of prologue per CTA)
+      const int panels = a_alloc / BM;
+      long long best = -1; int best_sp = n_splits;
+      for (int sp = n_splits; sp <= 8 && sp <= b_tiles; ++sp) {
+        const long long ctas = (long long)panels * sp;
+        const long long cost = ((ctas + ctx->num_sms - 1) / ctx->num_sms) * (div_up(b_tiles, sp) + 3);
+        if (best < 0 || cost < best) { best = cost; best_sp = sp; }
+      }
+      n_splits = best_sp;
     }
   }
+  // general-float path: with a score bound (matchFeatures) the hi x hi term alone decides almost every row and the
+  // certificate carries the larger margin; without one (exact top-2 of every row) all three terms are contracted.
+  // The debug GEMM always contracts the three terms.  VO_MATCH_FLOAT_TERMS=3 forces the three-term form.
+  static const int terms_env = [] { const char* e = getenv("VO_MATCH_FLOAT_TERMS"); return e ? atoi(e) : 0; }();
+  const int gen_terms = (flt.key_floor > 0.f && dbg_c == nullptr && terms_env != 3) ? 1 : 3;
+  const float gen_eps = gen_terms == 1 ? ONE_TERM_EPS : SPLIT_EPS;
+  ctx->match_float_terms = gen_terms;
   const int n_slots = n_splits * 4;
   const size_t cand_stride = (size_t)a_alloc * n_slots * NCAND;
   uint2* cand; VO_TRY(dev_buf(ctx, nm("m_cand").c_str(), (size_t)n_prob * cand_stride, &cand));
@@ -1890,7 +1948,7 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
     ProfScope ps(ctx, st, "match_gemm_topk", 0.0, exact_sizes ? 2.0 * A.cap * B.cap * dim : 0.0, 2);
     match_topk_kernel<<<dim3(a_alloc / BM, n_splits, n_prob), NUM_THREADS, SMEM_BYTES, st>>>(
         tmA, tmB, invB, b_alloc, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap, ctl, kp / BK, n_splits, cand,
-        cand_stride, dbg_c, B.cap);
+        cand_stride, dbg_c, B.cap, invA, a_alloc, flt.key_floor, gen_terms, gen_eps, invb_max);
     if (use_ts) {
       CUtensorMap tmB96;
       VO_TRY(make_u8_map(&tmB96, u8B, b_alloc, n_prob, TN));
@@ -1941,7 +1999,7 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   }
   match_finalize_kernel<<<dim3(div_up(A.cap, 128), n_prob), 128, 0, st>>>(
       cand, cand_stride, n_slots, ra, rb, dim, invA, a_alloc, invB, b_alloc, A.count, A.count_stride, A.cap, B.count,
-      B.count_stride, B.cap, ctl, (use_pairs || use_ts) ? 1 : 0, sched_L, sched_T, flt, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
+      B.count_stride, B.cap, ctl, (use_pairs || use_ts) ? 1 : 0, sched_L, sched_T, flt, gen_eps, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
   if (B.cap > 0) {
     int scan_grid = ctx->num_sms * 2;
     match_rowscan_kernel<<<scan_grid, 256, 0, st>>>(scan_list, ctl + 1, ra, rb, u8A, u8B, a_alloc, b_alloc, ctl, dim, invA, a_alloc, invB, b_alloc, B.count,
@@ -2041,7 +2099,7 @@ static int read_stats(vo_ctx* ctx, cudaStream_t st) {
   VO_CUDA(cudaStreamSynchronize(st));
   ctx->match_stats[0] = h[0] ? 0 : 1;
   ctx->match_stats[1] = h[1];
-  if (h[0]) ctx->match_stats[3] *= 3;
+  if (h[0]) ctx->match_stats[3] *= ctx->match_float_terms;
   return VO_OK;
 }
 

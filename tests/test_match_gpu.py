@@ -104,8 +104,18 @@ def test_general_float_path(ctx):
     assert np.array_equal(j1, oj1)
     assert np.array_equal(s1.view(np.uint32), os1.view(np.uint32))
     assert np.array_equal(s2.view(np.uint32), os2.view(np.uint32))
-    assert st["rowscan_rows"] < 0.2 * len(f1)
+    assert st["rowscan_rows"] < 0.2 * len(f1) and st["k_extent"] == 384      # exact top-2 of every row: three bf16 terms
     _check(ctx, f1, f2)
+    st = ctx.match_stats()                       # matchFeatures: the score bound decides the rows, one bf16 term suffices
+    assert not st["exact_integer_path"] and st["k_extent"] == 128 and st["rowscan_rows"] < 0.05 * len(f1)
+    # unit-norm float copies of SIFT-like rows at a size with several column tiles and row panels
+    from vo_b200 import synth
+    h1, h2 = synth.descriptor_sets("float", 3000, 5000, seed=3)
+    _check(ctx, h1, h2)
+    st = ctx.match_stats()
+    assert st["k_extent"] == 128 and st["rowscan_rows"] < 0.05 * len(h1)
+    _check(ctx, h1, h2, Unique=True)
+    _check(ctx, h1, h2, MatchThreshold=10.0, MaxRatio=0.9)       # a loose bound: more candidates per row
     # signed, non-normalised general floats
     g1 = rng.standard_normal((333, 128)).astype(np.float32) * 3.0
     g2 = rng.standard_normal((555, 128)).astype(np.float32) * 0.5
