@@ -122,6 +122,32 @@ def test_general_float_path(ctx):
     _check(ctx, g1, g2, MatchThreshold=100.0, MaxRatio=1.0)
 
 
+def test_general_float_decisions_near_the_thresholds(ctx):
+    """Unit-norm float rows whose best scores are spread over 0 .. 0.1 (threshold 0.04) and whose landmark set holds
+    near-duplicates (ratios around 0.6): the one-term general path has to prove every keep / reject or fall back to the
+    exact scan -- pairs and metric bits equal the oracle's either way."""
+    rng = np.random.default_rng(21)
+    def unit(x):
+        return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+    def jitter(x, t):       # rows at squared distance ~t from the rows of x
+        d = rng.standard_normal(x.shape)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        return unit(x + d * np.sqrt(t)[:, None])
+    base = unit(np.abs(rng.standard_normal((1500, 128))))
+    sib = jitter(base[:700], rng.uniform(0.0, 0.1, 700))
+    f2 = np.concatenate([base, sib]).astype(np.float32)
+    src = rng.permutation(len(f2))[:1800]
+    f1 = jitter(f2[src], rng.uniform(0.0, 0.1, len(src)))
+    pairs = _check(ctx, f1, f2)
+    st = ctx.match_stats()
+    assert not st["exact_integer_path"] and st["k_extent"] == 128
+    assert 100 < len(pairs) < len(f1)
+    assert st["rowscan_rows"] < 0.25 * len(f1), st
+    _check(ctx, f1, f2, Unique=True)
+    _check(ctx, f1, f2, MaxRatio=0.9)
+    _check(ctx, f1, f2, MatchThreshold=2.0, MaxRatio=0.8)
+
+
 def test_col_major_inputs(ctx):
     f1, f2 = correlated_pair(400, 500, seed=77)
     import vo_b200
