@@ -745,7 +745,7 @@ constexpr int EX_COLS = 30, EX_ROWS = 32;
 template <int NL>
 __global__ void __launch_bounds__(128)
 sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int batch, int h, int w, int pitch,
-                    float threshold, uint32_t* __restrict__ cand, int cand_cap, int* __restrict__ counters, int pf_rows) {
+                    float threshold, uint32_t* __restrict__ cand, int cand_cap, int* __restrict__ counters) {
   constexpr int L = NL + 2;
   const int lane = threadIdx.x & 31;
   const int strip = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -755,20 +755,27 @@ sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int batch, int h
   const int y0 = blockIdx.y * EX_ROWS;
   const int b = blockIdx.z;
   const size_t layer_stride = (size_t)batch * h * pitch;
-  const float* img = dog_oct + (size_t)b * h * pitch + xc;
+  // one 64-bit base per layer stays in registers; a pixel address is then ONE wide multiply-add of the 32-bit element
+  // offset row * pitch + column (the row part is warp-uniform), instead of a 64-bit add chain per layer and row
+  const float* lp[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    lp[l] = dog_oct + (size_t)b * h * pitch + (size_t)l * layer_stride;
+    asm volatile("" : "+l"(lp[l]));
+  }
   float hxA[L], hxB[L], hxC[L], hnA[L], hnB[L], hnC[L], cB[L], cC[L];
 #pragma unroll
   for (int l = 0; l < L; ++l) { hxA[l] = hxB[l] = hxC[l] = hnA[l] = hnB[l] = hnC[l] = cB[l] = cC[l] = 0.f; }
   const bool col_ok = lane >= 1 && lane <= EX_COLS && x >= SIFT_BORDER && x < w - SIFT_BORDER;
   const int y_end = min(y0 + EX_ROWS, h - SIFT_BORDER);    // last row (exclusive) that can hold a keypoint
   // the next row's values are loaded one iteration ahead, so the shuffles never wait on HBM (two rows
-  // ahead was measured slower: more registers, no gain).  Unrolling by 3 lets the compiler rename the
+  // ahead and L2 prefetches further down were measured slower).  Unrolling by 3 lets the compiler rename the
   // rolling 3-row window instead of moving registers every row.
   float nxt[L];
   {
-    const size_t off = (size_t)min(max(y0 - 1, 0), h - 1) * pitch;
+    const unsigned off = (unsigned)(min(max(y0 - 1, 0), h - 1) * pitch) + (unsigned)xc;
 #pragma unroll
-    for (int l = 0; l < L; ++l) nxt[l] = __ldg(img + (size_t)l * layer_stride + off);
+    for (int l = 0; l < L; ++l) nxt[l] = __ldg(lp[l] + off);
   }
 #pragma unroll 3
   for (int r = y0 - 1; r <= y_end; ++r) {
@@ -776,16 +783,9 @@ sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int batch, int h
 #pragma unroll
     for (int l = 0; l < L; ++l) v[l] = nxt[l];
     if (r < y_end) {
-      const size_t off = (size_t)min(max(r + 1, 0), h - 1) * pitch;
+      const unsigned off = (unsigned)(min(max(r + 1, 0), h - 1) * pitch) + (unsigned)xc;
 #pragma unroll
-      for (int l = 0; l < L; ++l) nxt[l] = __ldg(img + (size_t)l * layer_stride + off);
-      // the rows further down are pulled into L2 now (no registers held): the loads above then see L2 latency, not HBM's.
-      // Lanes 0 and 31 touch the two 128-byte lines a warp's row segment can straddle.
-      if (pf_rows > 0 && (lane == 0 || lane == 31) && r + 1 + pf_rows < y_end + 1) {
-        const size_t offp = (size_t)min(r + 1 + pf_rows, h - 1) * pitch;
-#pragma unroll
-        for (int l = 0; l < L; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(img + (size_t)l * layer_stride + offp));
-      }
+      for (int l = 0; l < L; ++l) nxt[l] = __ldg(lp[l] + off);
     }
 #pragma unroll
     for (int l = 0; l < L; ++l) {
@@ -803,14 +803,22 @@ sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int batch, int h
       mx[l] = fmaxf(fmaxf(hxA[l], hxB[l]), hxC[l]);
       mn[l] = fminf(fminf(hnA[l], hnB[l]), hnC[l]);
     }
+    // branch-free tests (a maximum needs val > threshold > 0, a minimum val < -threshold); candidates are rare, so one
+    // vote over the three layers decides whether the compaction below runs at all
+    bool ext_l[NL + 1];
+    bool any_ext = false;
 #pragma unroll
     for (int layer = 1; layer <= NL; ++layer) {
       const float val = cB[layer];
-      bool ext = false;
-      if (col_ok && fabsf(val) > threshold) {
-        if (val > 0) ext = val >= mx[layer - 1] && val >= mx[layer] && val >= mx[layer + 1];
-        else ext = val <= mn[layer - 1] && val <= mn[layer] && val <= mn[layer + 1];
-      }
+      const float m27 = fmaxf(fmaxf(mx[layer - 1], mx[layer]), mx[layer + 1]);
+      const float n27 = fminf(fminf(mn[layer - 1], mn[layer]), mn[layer + 1]);
+      ext_l[layer] = col_ok & (((val > threshold) & (val >= m27)) | ((val < -threshold) & (val <= n27)));
+      any_ext |= ext_l[layer];
+    }
+    if (!__any_sync(0xffffffffu, any_ext)) continue;       // warp-uniform
+#pragma unroll
+    for (int layer = 1; layer <= NL; ++layer) {
+      const bool ext = ext_l[layer];
       const unsigned mask = __ballot_sync(0xffffffffu, ext);
       if (mask) {
         const int leader = __ffs(mask) - 1;
@@ -827,6 +835,8 @@ sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int batch, int h
   }
 }
 
+// (Two columns per lane -- one 8-byte load and two shuffles per layer and row for two pixels -- was built and measured in
+// round 2: 96-103 registers, 16-20 warps per SM instead of 36, 0.96 ms per step against 0.92: removed again.)
 // TMA-fed form for the wide octaves (an experiment kept behind VO_EXT_TMA=1, bit-identical results).  The register
 // form above keeps only one row per layer in flight per warp (about 20 KB per SM) and runs at 48 % of the HBM
 // roofline, so the question was whether it starves for bytes in flight.  Here a block of 8 warps walks a strip of 240
@@ -834,7 +844,7 @@ sift_extrema_kernel(const float* __restrict__ dog_oct, int oct, int batch, int h
 // layers x 256 columns (20 KB), three groups deep: 40 KB per block and 120 KB per SM in flight without holding a
 // register.  Measured: 1.26 ms per step against 1.03 ms (ncu: same 1.5e8 warp instructions, issue-active 63 % against
 // 71 %, top stalls wait + barrier instead of long_scoreboard): the test is bound by instruction issue, not by memory
-// parallelism -- as were a second row in registers, per-lane cp.async rings (round 1) and L2 prefetches (VO_EXT_PF).
+// parallelism -- as were a second row in registers, per-lane cp.async rings (round 1) and L2 prefetches (round 2, removed again).
 // Out-of-image halo columns / rows are zero-filled by TMA and only ever feed windows of border pixels, which cannot
 // be keypoints.
 constexpr int XT_WARPS = 8, XT_COLS = XT_WARPS * EX_COLS, XT_BOXW = 256, XT_G = 4, XT_NST = 3;
@@ -1797,8 +1807,7 @@ int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, 
                                                                                        threshold, p->cand, p->cand_cap, p->counters);
       continue;
     }
-    static const int ext_pf = [] { const char* e = getenv("VO_EXT_PF"); return e ? atoi(e) : 0; }();
-#define VO_EXTREMA(NLV) sift_extrema_kernel<NLV><<<g, 128, 0, st>>>(p->D(oc, 0), oc, p->batch, p->h[oc], p->w[oc], p->pitch[oc], threshold, p->cand, p->cand_cap, p->counters, ext_pf)
+#define VO_EXTREMA(NLV) sift_extrema_kernel<NLV><<<g, 128, 0, st>>>(p->D(oc, 0), oc, p->batch, p->h[oc], p->w[oc], p->pitch[oc], threshold, p->cand, p->cand_cap, p->counters)
     switch (nl) {
       case 1: VO_EXTREMA(1); break;
       case 2: VO_EXTREMA(2); break;
