@@ -123,9 +123,12 @@ if __name__ == "__main__":
     launches()
     bench_launches()
     full(RP + "_sift.ncu-rep", RP + "_ncu_full_sift.md", "Round " + RN + " -- ncu `--set full`: SIFT, sort, prep and geometry kernels of one frame-loop step (18 images of 1241x376)",
-         'ncu --set full --clock-control none --import-source on -k regex:"sift_descriptor_kernel|sift_refine_kernel|sift_orient_kernel|sift_extrema|sift_blur_tma_kernel|sift_base_stream|sift_small_oct|sift_rank_bucket|landmark" -c 40 python tools/prof_targets.py 8')
+         'ncu --set full --clock-control none --import-source on -k regex:"sift_descriptor_kernel|sift_refine_kernel|sift_orient_kernel|sift_extrema|sift_blur_tma_kernel|sift_base_stream|sift_small_oct|sift_rank_bucket|landmark" -c 33 python tools/prof_targets.py 8')
     full(RP + "_match_u8.ncu-rep", RP + "_ncu_full_match.md", "Round " + RN + " -- ncu `--set full`: match_topk_u8_kernel, 32768 x 32768 x 128, matchFeatures mode",
          "ncu --set full --clock-control none --import-source on -k regex:match_topk_u8 -s 2 -c 1 python tools/prof_match.py 32768 match")
+    full(RP + "_match_float.ncu-rep", RP + "_ncu_full_match_float.md", "Round " + RN + " -- ncu `--set full`: match_topk_kernel (general-float path, one bf16 term), 32768 x 32768 x 128 unit-norm float rows, matchFeatures mode",
+         "ncu --set full --clock-control none --import-source on -k regex:match_topk_kernel -s 1 -c 1 python tools/prof_float.py 32768")
+    opmix(RP + "_match_float.ncu-rep", "match_topk_kernel", RP + "_opmix_match_float.txt")
     opmix(RP + "_match_u8.ncu-rep", "match_topk_u8", RP + "_opmix_match_u8.txt")
     opmix(RP + "_sift.ncu-rep", "sift_descriptor", RP + "_opmix_descriptor.txt")
     opmix(RP + "_sift.ncu-rep", "sift_blur_tma", RP + "_opmix_blur_tma_r13.txt", "4")

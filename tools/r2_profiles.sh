@@ -8,3 +8,5 @@ ncu --set full --clock-control none --import-source on -k regex:"sift_descriptor
 python tools/prof_match.py 32768 match > gpurun_out/prof_match_plain.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:match_topk_u8 -s 2 -c 1 -o gpurun_out/r2_match_u8 -f python tools/prof_match.py 32768 match > gpurun_out/ncu_match.log 2>&1
 ls -la gpurun_out/
+python tools/prof_float.py 32768 > gpurun_out/prof_float_plain.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:"match_topk_kernel" -s 1 -c 1 -o gpurun_out/r2_match_float -f python tools/prof_float.py 32768 > gpurun_out/ncu_float.log 2>&1
