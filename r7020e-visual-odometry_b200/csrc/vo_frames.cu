@@ -107,6 +107,7 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
 
   auto raw_op = [&](int first_img) {   // raw descriptor set of image (first_img + 2p)
     MatchOperand o; o.base = desc + (size_t)first_img * img_stride; o.prob_stride = 2 * img_stride;
+    o.integer_rows = 1;   // written by sift_descriptor_kernel: saturated, rounded to 0..255
     o.count = cnt + first_img * 4 + 2; o.count_stride = 8; o.cap = kc; return o;
   };
   auto gath_op = [&](int first_img, const uint32_t* g, const int* c) {

@@ -1408,7 +1408,7 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
                       const float* __restrict__ invb_base, int invb_stride, const int* __restrict__ n1p,
                       int n1_stride, int cap1, const int* __restrict__ n2p, int n2_stride, int cap2,
                       const int* __restrict__ nonint_flag, int all_slots, int sched_L, int sched_T, MatchFilter flt,
-                      float gen_eps, uint32_t* __restrict__ j1_out,
+                      float gen_eps, int general_skipped, uint32_t* __restrict__ j1_out,
                       float* __restrict__ s1_out, float* __restrict__ s2_out, int row_stride,
                       int* __restrict__ scan_list, int* __restrict__ scan_count) {
   const int prob = blockIdx.y;
@@ -1445,7 +1445,8 @@ match_finalize_kernel(const uint2* __restrict__ cand_base, size_t cand_stride, i
   // exact-integer path: the tensor-core dot is the oracle's dot, so the epilogue key is already exact;
   // split path: re-score the candidates with the oracle's sequential FP32 dot
   const bool general = (*nonint_flag) != 0;
-  if (general && rb.base == nullptr) {   // non-integer queries against a prepared (u8-only) landmark set: no float rows to re-score with
+  if (general && (rb.base == nullptr || general_skipped)) {   // non-integer rows where the caller promised integers (general kernels not launched), or
+                                                              // non-integer queries against a prepared (u8-only) landmark set: nothing to re-score with
     j1_out[orow] = 0xFFFFFFFFu; s1_out[orow] = INFINITY; s2_out[orow] = INFINITY;
     return;
   }
@@ -1844,9 +1845,10 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   if (A.cap <= 0 || n_prob <= 0) return VO_OK;
 
   const size_t prep_smem = (size_t)PREP_ROWS * (dim + 1) * sizeof(float);
+  const bool skip_general = A.integer_rows && B.integer_rows && dbg_c == nullptr;
   const bool exact_sizes = (n_prob == 1 && !A.gather && !B.gather);   // caps are the live sizes
   {
-    ProfScope ps(ctx, st, "match_prep", exact_sizes ? ((double)A.cap + B.cap) * (dim * 4.0 + 132.0) : 0.0, 0.0, 4);
+    ProfScope ps(ctx, st, "match_prep", exact_sizes ? ((double)A.cap + B.cap) * (dim * 4.0 + 132.0) : 0.0, 0.0, (skip_general ? 2 : 4) - (B.prepared ? (skip_general ? 1 : 2) : 0));
     if (dim == 128 && !A.col_major && (reinterpret_cast<uintptr_t>(A.base) & 15) == 0 && A.prob_stride % 4 == 0)
       match_prep_rows128_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, 0, st>>>(A, a_alloc, u8A, invA, ctl, nullptr);
     else
@@ -1857,9 +1859,12 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
       match_prep_rows128_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, 0, st>>>(B, b_alloc, u8B, invB, ctl, invb_max);
     else
       match_prep_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, u8B, invB, ctl, invb_max);
-    // general float descriptors only (both return at once when every value is an integer 0..255)
-    match_prep_split_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, kp, 0, opA, rawA, ctl);
-    if (!B.prepared) match_prep_split_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, kp, 1, opB, rawB, ctl);
+    // general float descriptors only (both return at once when every value is an integer 0..255; not launched at all
+    // when the caller vouches for integer rows: the frame loop matches descriptors its own SIFT kernel has just written)
+    if (!skip_general) {
+      match_prep_split_kernel<<<dim3(a_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(A, a_alloc, dim, kp, 0, opA, rawA, ctl);
+      if (!B.prepared) match_prep_split_kernel<<<dim3(b_alloc / PREP_ROWS, n_prob), 256, prep_smem, st>>>(B, b_alloc, dim, kp, 1, opB, rawB, ctl);
+    }
   }
   VO_CUDA(cudaGetLastError());
 
@@ -1945,8 +1950,8 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
     VO_TRY(ensure_dyn_smem_of(match_topk_u8_kernel, U_SMEM_BYTES));
     // both variants are launched; each reads the device-side "non-integer input" flag and one of them
     // returns at once (no host synchronisation to pick the path)
-    ProfScope ps(ctx, st, "match_gemm_topk", 0.0, exact_sizes ? 2.0 * A.cap * B.cap * dim : 0.0, 2);
-    match_topk_kernel<<<dim3(a_alloc / BM, n_splits, n_prob), NUM_THREADS, SMEM_BYTES, st>>>(
+    ProfScope ps(ctx, st, "match_gemm_topk", 0.0, exact_sizes ? 2.0 * A.cap * B.cap * dim : 0.0, skip_general ? 1 : 2);
+    if (!skip_general) match_topk_kernel<<<dim3(a_alloc / BM, n_splits, n_prob), NUM_THREADS, SMEM_BYTES, st>>>(
         tmA, tmB, invB, b_alloc, A.count, A.count_stride, A.cap, B.count, B.count_stride, B.cap, ctl, kp / BK, n_splits, cand,
         cand_stride, dbg_c, B.cap, invA, a_alloc, flt.key_floor, gen_terms, gen_eps, invb_max);
     if (use_ts) {
@@ -1999,7 +2004,7 @@ int match_batch_top2(vo_ctx* ctx, const MatchOperand& A, const MatchOperand& B, 
   }
   match_finalize_kernel<<<dim3(div_up(A.cap, 128), n_prob), 128, 0, st>>>(
       cand, cand_stride, n_slots, ra, rb, dim, invA, a_alloc, invB, b_alloc, A.count, A.count_stride, A.cap, B.count,
-      B.count_stride, B.cap, ctl, (use_pairs || use_ts) ? 1 : 0, sched_L, sched_T, flt, gen_eps, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
+      B.count_stride, B.cap, ctl, (use_pairs || use_ts) ? 1 : 0, sched_L, sched_T, flt, gen_eps, skip_general ? 1 : 0, out->j1, out->s1, out->s2, a_alloc, scan_list, ctl + 1);
   if (B.cap > 0) {
     int scan_grid = ctx->num_sms * 2;
     match_rowscan_kernel<<<scan_grid, 256, 0, st>>>(scan_list, ctl + 1, ra, rb, u8A, u8B, a_alloc, b_alloc, ctl, dim, invA, a_alloc, invB, b_alloc, B.count,

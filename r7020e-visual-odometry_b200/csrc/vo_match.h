@@ -18,6 +18,8 @@ struct MatchOperand {
   int cap = 0;
   int col_major = 0;   // single problem only: element (i,k) at base[k*ld + i]
   int ld = 0;
+  int integer_rows = 0;   // the caller vouches that every row holds integers 0..255 (descriptors written by sift_descriptor_kernel):
+                          // with both sides vouched for, the general-float kernels are not even launched
   int prepared = 0;    // B side only: its u8 rows / 1/||row|| / max were written by an earlier call under the same tag
                        // (vo_landmarks_prepare: integer-valued rows) and are still there; base may be null
 };
