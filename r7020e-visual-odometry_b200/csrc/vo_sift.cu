@@ -318,7 +318,7 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
   static_assert(R <= TS_HALO, "halo too small");
   // ring slots 0..MIRROR-1 are kept a second time at RING + slot, so the 4 + 2R consecutive rows a
   // column window reads are always contiguous in shared memory (one base address, immediate offsets)
-  constexpr int RING = 64, MIRROR = TS_MIRROR(R);
+  constexpr int RING = 64, MIRROR = TS_MIRROR(R) + (MODE == 3 ? 4 : 0);   // MODE 3 reads 8 + 2R consecutive rows
   extern __shared__ __align__(128) uint8_t tsm[];      // > 48 KB: dynamic shared memory (opt-in)
   constexpr bool PACK = MODE == 1;
   constexpr int SROW_BYTES = PACK ? 8 * TS_BOXW * 4 : 0;   // PACK: one shifted row per warp
@@ -371,7 +371,7 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
       }
       __syncthreads();
     }
-    if constexpr (MODE == 2) {
+    if constexpr (MODE >= 2) {
       const int seg = lane >> 1, rr = 2 * wrp + (lane & 1);
       const int row = row0 + rr;
       if (!(row < 0 || row >= h || row < ys - R)) {
@@ -482,6 +482,49 @@ sift_blur_tma_kernel(const __grid_constant__ CUtensorMap tm, int z_base, float* 
     row_pass_group(c + 2);
     __syncthreads();
     if (tid == 0 && c + 4 < n_groups) issue(c + 4);
+    if constexpr (MODE == 3) {
+      // column pass with EIGHT rows and ONE column per thread: 8 + 2R ring values are loaded for 8 outputs (17 bytes of
+      // shared memory per pixel at R = 13 instead of 30), scalar arithmetic (the same IEEE operations as the packed form)
+      const int col = tid & 127, rg8 = tid >> 7;
+      const int xs = x0 + col;
+      const int y8 = ys + c * TS_G + rg8 * 8;
+      if (y8 < ye && xs < w) {
+        float cc1[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) cc1[o] = (y8 + o < ye) ? __ldg(img + (unsigned)((y8 + o) * pitch + xs)) : 0.f;
+        float win1[8 + 2 * R];
+        const int s8 = (y8 - R) & (RING - 1);
+        if (y8 - R >= 0 && y8 + 7 + R < h) {
+          const float* base = &ring[s8][col];       // s8 + q <= RING - 1 + MIRROR
+#pragma unroll
+          for (int q = 0; q < 8 + 2 * R; ++q) win1[q] = base[q * TS_RS];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8 + 2 * R; ++q) win1[q] = ring[reflect101(y8 - R + q, h) & (RING - 1)][col];
+        }
+        float a8[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) a8[o] = taps.k[0] * win1[R + o];
+#pragma unroll
+        for (int i = 1; i <= R; ++i) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) a8[o] = fmaf(taps.k[i], win1[R + o - i] + win1[R + o + i], a8[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          const int y = y8 + o;
+          if (y < ye) {
+            const unsigned g = (unsigned)(y * pitch + xs);
+            dst_i[g] = a8[o];
+            dog_i[g] = a8[o] - cc1[o];
+            if constexpr (DS) {
+              if (!((y | xs) & 1) && (y >> 1) < ds.h && (xs >> 1) < ds.w) ds.dst[((size_t)b * ds.h + (y >> 1)) * ds.pitch + (xs >> 1)] = a8[o];
+            }
+          }
+        }
+      }
+      continue;
+    }
     const int yf = ys + c * TS_G + rg * 4;
     if (yf < ye && x < w) {
       // centre pixels of G[l] for the fused DoG: issued first so their latency hides behind the filter
@@ -1584,7 +1627,7 @@ static int launch_tma_t2(const CUtensorMap& tm, int z_base, const float* src, fl
   if (seg_rows < 4 * TS_G) seg_rows = 4 * TS_G;
   n_seg = div_up(h, seg_rows);
   dim3 grid(strips, n_seg, batch);
-  constexpr int smem = 2 * TS_G * TS_BOXW * 4 + (MODE == 1 ? 8 * TS_BOXW * 4 : 0) + (64 + TS_MIRROR(R)) * TS_RS * 4 + 64;
+  constexpr int smem = 2 * TS_G * TS_BOXW * 4 + (MODE == 1 ? 8 * TS_BOXW * 4 : 0) + (64 + TS_MIRROR(R) + (MODE == 3 ? 4 : 0)) * TS_RS * 4 + 64;
   if (ds.dst != nullptr) {
     VO_TRY(ensure_dyn_smem_of(sift_blur_tma_kernel<R, MODE, true>, smem));
     sift_blur_tma_kernel<R, MODE, true><<<grid, 256, smem, st>>>(tm, z_base, dst, dog, src, h, w, pitch, seg_rows, t, ds);
@@ -1596,12 +1639,14 @@ static int launch_tma_t2(const CUtensorMap& tm, int z_base, const float* src, fl
 }
 // VO_BLUR_ROW selects the row pass: 2 (default) = eight outputs per lane, 0 = four outputs per lane (round 1),
 // 1 = packed f32x2 (measured slower: 3.27 vs 2.45 ms per step, it reads more shared memory per pixel; kept for A/B runs)
+// 3 = as 2 with a column pass of eight rows x one column per thread (scalar; fewer shared bytes, more issue slots: 2.47 vs 2.36)
 template <int R>
 static int launch_tma_t(const CUtensorMap& tm, int z_base, const float* src, float* dst, float* dog, int h, int w, int pitch,
                         int batch, const Taps& t, int num_sms, cudaStream_t st, const DsOut& ds) {
   static const int mode = [] { const char* e = getenv("VO_BLUR_ROW"); return e ? atoi(e) : 2; }();
   if (mode == 1) return launch_tma_t2<R, 1>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st, ds);
   if (mode == 0) return launch_tma_t2<R, 0>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st, ds);
+  if (mode == 3) return launch_tma_t2<R, 3>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st, ds);
   return launch_tma_t2<R, 2>(tm, z_base, src, dst, dog, h, w, pitch, batch, t, num_sms, st, ds);
 }
 
