@@ -539,6 +539,7 @@ def run_ours(args, rank, world, local_rank):
     t_dev = timed(step_dev, profile=False, use=n_ctx, sampler=sampler)
     clocks = sampler.stop(*t_dev["marks"])
     t_host = timed(step_host, profile=False, use=n_ctx)
+    graph_states = [c.frames_graph_state() for c in ctxs]   # 2 = the timed passes replayed a captured CUDA graph (VO_FRAMES_GRAPH=1)
     # roofline pass: the same steps, one batch at a time on one stream, with the library's per-stage CUDA
     # events switched on (they cost a few % of a step, and overlapping batches would smear the stages)
     t_prof = timed(step_dev, profile=True, use=1)
@@ -650,7 +651,7 @@ def run_ours(args, rank, world, local_rank):
                 run=dict(frames_per_step_per_gpu=B, distinct_batches=n_batches, sequence_frames=n_seq,
                          l2="per-step working set ~%.1f GB of pyramids >> 126 MB L2; %d distinct input batches"
                             % ((B + 1) * 2 * 110e6 / 1e9, n_batches),
-                         batches_in_flight=n_ctx,
+                         batches_in_flight=n_ctx, frames_graph_state=graph_states,
                          timing="value / e2e: exactly `steps` steps with `batches_in_flight` batches in flight (one stream "
                                 "and host thread per batch slot), CUDA events on the launching streams, max over ranks; "
                                 "roofline / stage_share / ms_per_step_profiled_serial: the same steps run one batch at a time "

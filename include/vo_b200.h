@@ -258,6 +258,15 @@ int vo_frames_dev(vo_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev
  * estworldpose failed).  VO_ERR_STATE without a preceding vo_frames call, VO_ERR_CAPACITY if cap is too small. */
 int vo_frames_landmarks(vo_ctx* ctx, const double* poses, int n_frames, int cap, double* landmarks, int* rows);
 
+/* CUDA graph for the frame loop.  With enable != 0, vo_frames / vo_frames_dev capture their launch
+ * sequence (SIFT ... P3P and the result copies; shapes depend on capacities only) the second time a (batch shape, option
+ * set) is seen and replay it afterwards: a call then uploads its images and per-call parameters and launches ONE graph.
+ * Results are bit-identical to the plain path.  The environment variable VO_FRAMES_GRAPH=1 enables it for every new
+ * context.  vo_frames_graph_state: 0 = off, 1 = on (nothing captured yet), 2 = a captured graph is being replayed,
+ * -1 = capture failed on this driver and the context fell back to plain launches. */
+int vo_frames_use_graph(vo_ctx* ctx, int enable);
+int vo_frames_graph_state(vo_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,7 +46,7 @@ EXPORTS = [
     "vo_version", "vo_last_error", "vo_ctx_create", "vo_ctx_destroy", "vo_ctx_sync",
     "vo_ctx_stream", "vo_profile_enable", "vo_kernel_launches", "vo_profile_count", "vo_profile_get", "vo_frames_dev", "vo_sift", "vo_sift_batch", "vo_sift_stack", "vo_match", "vo_match_top2", "vo_match_dev",
     "vo_match_top2_dev", "vo_match_best2_dev", "vo_match_best2_gather_dev", "vo_landmarks_prepare", "vo_peer_alloc", "vo_peer_open", "vo_peer_close", "vo_peer_free", "vo_match_stats", "vo_match_debug_gemm", "vo_triangulate", "vo_p3p",
-    "vo_frames", "vo_frames_landmarks", "vo_png_info", "vo_png_decode_gray8", "vo_png_read_batch", "vo_inflate_zlib", "vo_png_decode_batch_dev", "vo_png_read_batch_dev",
+    "vo_frames", "vo_frames_landmarks", "vo_frames_use_graph", "vo_frames_graph_state", "vo_png_info", "vo_png_decode_gray8", "vo_png_read_batch", "vo_inflate_zlib", "vo_png_decode_batch_dev", "vo_png_read_batch_dev",
 ]
 
 

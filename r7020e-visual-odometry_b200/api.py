@@ -79,6 +79,15 @@ class Context:
     def kernel_launches(self):
         return int(_lib.lib().vo_kernel_launches(self._h))
 
+    def use_frames_graph(self, enable=True):
+        """vo_frames_use_graph: replay the frame loop's launch sequence as a CUDA graph (captured at the second call with
+        the same batch shape and options)."""
+        check(_lib.lib().vo_frames_use_graph(self._h, 1 if enable else 0))
+
+    def frames_graph_state(self):
+        """0 = off, 1 = on (nothing captured yet), 2 = a captured graph is being replayed, -1 = capture failed (plain launches)."""
+        return int(_lib.lib().vo_frames_graph_state(self._h))
+
     @property
     def stream(self):
         """cudaStream_t (int) the host-pointer entry points launch on."""

@@ -102,6 +102,7 @@ int vo_ctx::dev(const char* name, size_t bytes, void** out) {
     VO_CUDA(cudaMalloc(&s.ptr, want));
     s.bytes = want;
     s.host = false;
+    ++alloc_generation;
   }
   *out = s.ptr;
   return VO_OK;
@@ -119,6 +120,7 @@ int vo_ctx::pinned(const char* name, size_t bytes, void** out) {
     VO_CUDA(cudaMallocHost(&s.ptr, want));
     s.bytes = want;
     s.host = true;
+    ++alloc_generation;
   }
   *out = s.ptr;
   return VO_OK;
@@ -157,6 +159,7 @@ int vo_ctx_create(int device, vo_ctx** out) {
     vo::set_error("cudaStreamCreate failed");
     return VO_ERR_CUDA;
   }
+  { const char* e = getenv("VO_FRAMES_GRAPH"); c->frames_graph = (e && atoi(e) != 0) ? 1 : 0; }   // see vo_frames_use_graph
   *out = c;
   return VO_OK;
 }

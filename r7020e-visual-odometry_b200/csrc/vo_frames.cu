@@ -20,8 +20,17 @@ struct FramePlan {
   const int* K = nullptr;                // K[s*n + p]
   const double *old_l = nullptr, *old_r = nullptr, *dP = nullptr;
   const int* dstat = nullptr;
+  // vo_frames_use_graph: the launch sequence of one call (SIFT ... P3P and the result copies), captured once per
+  // (shape, options, buffer generation) and replayed; the image upload and the per-call parameters stay outside
+  std::vector<unsigned char> g_key;
+  long long g_gen = -1;
+  cudaGraphExec_t g_exec = nullptr;
+  long long g_launches = 0;
 };
-void frame_plan_destroy(FramePlan* p) { delete p; }
+void frame_plan_destroy(FramePlan* p) {
+  if (p && p->g_exec) cudaGraphExecDestroy(p->g_exec);
+  delete p;
+}
 
 // out_k[p][k] = src_k[p][idx[p][k]] for k < cnt[p]   (up to two arrays share one index list)
 __global__ void __launch_bounds__(256)
@@ -72,12 +81,12 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
   VO_CHECK_ARG(n >= 1 && rows > 0 && cols > 0, "bad size");
   VO_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  vo_match_opts mo; fill_match_opts(opts ? &opts->match : nullptr, &mo);
+  vo_match_opts mo; memset(&mo, 0, sizeof(mo)); fill_match_opts(opts ? &opts->match : nullptr, &mo);   // (zeroed: the option structs are part of the graph key)
   mo.index_base = 0;
-  vo_p3p_opts po; fill_p3p_opts(opts ? &opts->p3p : nullptr, &po);
+  vo_p3p_opts po; memset(&po, 0, sizeof(po)); fill_p3p_opts(opts ? &opts->p3p : nullptr, &po);
   const int want_cap = (opts && opts->max_keypoints > 0) ? opts->max_keypoints : 8192;
   const int first_frame = opts ? opts->first_frame : 0;
-  SiftPlan* plan; vo_sift_opts so;
+  SiftPlan* plan; vo_sift_opts so; memset(&so, 0, sizeof(so));
   VO_TRY(sift_prepare(ctx, rows, cols, 2 * n, opts ? &opts->sift : nullptr, want_cap, &plan, &so));
   const int kc = sift_plan_kp_cap(plan);
   const size_t img_bytes = (size_t)rows * cols;
@@ -91,18 +100,46 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
     VO_CUDA(cudaMemcpy2DAsync(dimg, 2 * img_bytes, left, img_bytes, img_bytes, n, kind, st));
     VO_CUDA(cudaMemcpy2DAsync(dimg + img_bytes, 2 * img_bytes, right, img_bytes, img_bytes, n, kind, st));
   }
-  VO_TRY(sift_run_device(ctx, plan, 2 * n, so, st));
   const float* desc = sift_plan_desc(plan);
   const vo_keypoint* kps = sift_plan_keypoints(plan);
   const int* cnt = sift_plan_counters(plan);
   const size_t img_stride = (size_t)kc * 128;   // floats per image's descriptor block
+  const int np = n - 1;
 
+  // ---- buffers (no launches here: a replayed graph needs the same addresses and nothing else)
   // index / count arrays, [n][kc] each
   uint32_t *l0, *r0, *a1, *b1, *oL1, *oR1, *a2, *b2, *oL2, *oR2, *a3, *b3, *cL3, *cR3, *a4, *b4;
   uint32_t** arrs[] = {&l0, &r0, &a1, &b1, &oL1, &oR1, &a2, &b2, &oL2, &oR2, &a3, &b3, &cL3, &cR3, &a4, &b4};
   uint32_t* pool; VO_TRY(dev_buf(ctx, "fr_idx", (size_t)16 * n * kc, &pool));
   for (int i = 0; i < 16; ++i) *arrs[i] = pool + (size_t)i * n * kc;
   int* K; VO_TRY(dev_buf(ctx, "fr_K", (size_t)5 * n + 8, &K));   // K[s*n + p], s = 0..4
+  double *old_l, *old_r, *cur_l, *world, *dA, *dP;
+  VO_TRY(dev_buf(ctx, "fr_oldl", (size_t)n * kc * 2, &old_l));
+  VO_TRY(dev_buf(ctx, "fr_oldr", (size_t)n * kc * 2, &old_r));
+  VO_TRY(dev_buf(ctx, "fr_curl", (size_t)n * kc * 2, &cur_l));
+  VO_TRY(dev_buf(ctx, "fr_world", (size_t)n * kc * 3, &world));
+  VO_TRY(dev_buf(ctx, "fr_A", (size_t)n * 16, &dA));
+  VO_TRY(dev_buf(ctx, "fr_P", 32, &dP));
+  int* dstat; VO_TRY(dev_buf(ctx, "fr_stat", (size_t)n * 4, &dstat));
+  double* hA; VO_TRY(pin_buf(ctx, "fr_hA", (size_t)n * 16, &hA));
+  int* hI; VO_TRY(pin_buf(ctx, "fr_hI", (size_t)n * 4 + (size_t)5 * n + (size_t)2 * n * 4 + 16, &hI));
+  int* hK = hI + (size_t)n * 4;
+  int* hC = hK + (size_t)5 * n;
+
+  // ---- per-call parameters (outside the replayed part): projection matrices, intrinsics and the call's share of the
+  // P3P seed, which the hypothesis kernel adds on the device
+  double* hP; VO_TRY(pin_buf(ctx, "fr_hP", 32, &hP));
+  for (int k = 0; k < 12; ++k) { hP[k] = P1[k]; hP[12 + k] = P2[k]; }
+  hP[24] = P1[0]; hP[25] = P1[5]; hP[26] = P1[2]; hP[27] = P1[6];   // fx fy cx cy (VO.m:35-38)
+  const uint64_t seed_add = (uint64_t)(first_frame + 1) * 0x9E3779B97F4A7C15ull;
+  memcpy(hP + 28, &seed_add, sizeof(seed_add));
+  VO_CUDA(cudaMemcpyAsync(dP, hP, 29 * sizeof(double), cudaMemcpyHostToDevice, st));
+  const uint64_t* seed_add_dev = reinterpret_cast<const uint64_t*>(dP + 28);
+
+  const MatchFilter mflt = make_match_filter(mo);
+  // ---- the launch sequence of one call
+  auto enqueue = [&]() -> int {
+  VO_TRY(sift_run_device(ctx, plan, 2 * n, so, st));
   VO_CUDA(cudaMemsetAsync(K, 0, ((size_t)5 * n + 8) * sizeof(int), st));
 
   auto raw_op = [&](int first_img) {   // raw descriptor set of image (first_img + 2p)
@@ -114,7 +151,6 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
     MatchOperand o = raw_op(first_img); o.gather = g; o.gather_stride = kc; o.count = c; o.count_stride = 1; return o;
   };
   MatchTop2 t, tb;
-  const MatchFilter mflt = make_match_filter(mo);
   // matchFeatures(A, B) of VO.m for a batch of problems; with Unique also the reversed problems (B, A)
   auto match = [&](const MatchOperand& A, const MatchOperand& B, int nprob, uint32_t* i1, uint32_t* i2, int* npairs) -> int {
     VO_TRY(match_batch_top2(ctx, A, B, nprob, 128, "fr", nullptr, st, &t, &mflt));
@@ -126,7 +162,6 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
     MatchOperand A = raw_op(0), B = raw_op(1);
     VO_TRY(match(A, B, n, l0, r0, K));
   }
-  const int np = n - 1;
   const dim3 cg(8, np > 0 ? np : 1);
   if (np > 0) {
     // M1 = matchFeatures(cur.l_desc, old.l_desc)                                 VO.m:283
@@ -154,48 +189,68 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
       MatchOperand A = gath_op(2, cL3, K + 3 * n), B = gath_op(0, oL2, K + 2 * n);
       VO_TRY(match(A, B, np, a4, b4, K + 4 * n));
     }
-  }
-  // triangulate the old pair (VO.m:114) and estimate the pose (VO.m:123-127)
-  double *old_l, *old_r, *cur_l, *world, *dA, *dP;
-  VO_TRY(dev_buf(ctx, "fr_oldl", (size_t)n * kc * 2, &old_l));
-  VO_TRY(dev_buf(ctx, "fr_oldr", (size_t)n * kc * 2, &old_r));
-  VO_TRY(dev_buf(ctx, "fr_curl", (size_t)n * kc * 2, &cur_l));
-  VO_TRY(dev_buf(ctx, "fr_world", (size_t)n * kc * 3, &world));
-  VO_TRY(dev_buf(ctx, "fr_A", (size_t)n * 16, &dA));
-  VO_TRY(dev_buf(ctx, "fr_P", 32, &dP));
-  int* dstat; VO_TRY(dev_buf(ctx, "fr_stat", (size_t)n * 4, &dstat));
-  double hP[28];
-  for (int k = 0; k < 12; ++k) { hP[k] = P1[k]; hP[12 + k] = P2[k]; }
-  hP[24] = P1[0]; hP[25] = P1[5]; hP[26] = P1[2]; hP[27] = P1[6];   // fx fy cx cy (VO.m:35-38)
-  VO_CUDA(cudaMemcpyAsync(dP, hP, sizeof(hP), cudaMemcpyHostToDevice, st));
-  if (np > 0) {
+    // triangulate the old pair (VO.m:114) and estimate the pose (VO.m:123-127)
     gather_points_kernel<<<cg, 256, 0, st>>>(kps, kc, oL2, oR2, cL3, a4, b4, K + 4 * n, old_l, old_r, cur_l);
     {
       ProfScope ps(ctx, st, "triangulate");
       VO_TRY(triangulate_batch_device(old_l, old_r, K + 4 * n, 1, kc, np, dP, world, st));
     }
     ProfScope ps(ctx, st, "p3p_msac", 0.0, 0.0, 4);
-    vo_p3p_opts pp = po;
-    pp.seed = po.seed + (uint64_t)(first_frame + 1) * 0x9E3779B97F4A7C15ull;
-    VO_TRY(p3p_batch_device(ctx, cur_l, world, K + 4 * n, kc, np, dP + 24, pp, dA, nullptr, dstat, dstat + n, st));
-  }
-  if (!ctx->frame_plan) ctx->frame_plan = new FramePlan();
-  {
-    FramePlan* fp = ctx->frame_plan;
-    fp->n = n; fp->kc = kc; fp->kps = kps; fp->l0 = l0; fp->r0 = r0; fp->K = K; fp->old_l = old_l; fp->old_r = old_r; fp->dP = dP;
-    fp->dstat = dstat;
+    VO_TRY(p3p_batch_device(ctx, cur_l, world, K + 4 * n, kc, np, dP + 24, po, dA, nullptr, dstat, dstat + n, st, seed_add_dev));
   }
   // results
-  double* hA; VO_TRY(pin_buf(ctx, "fr_hA", (size_t)n * 16, &hA));
-  int* hI; VO_TRY(pin_buf(ctx, "fr_hI", (size_t)n * 4 + (size_t)5 * n + (size_t)2 * n * 4 + 16, &hI));
-  int* hK = hI + (size_t)n * 4;
-  int* hC = hK + (size_t)5 * n;
   if (np > 0) {
     VO_CUDA(cudaMemcpyAsync(hA, dA, (size_t)np * 16 * sizeof(double), cudaMemcpyDeviceToHost, st));
     VO_CUDA(cudaMemcpyAsync(hI, dstat, (size_t)n * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   VO_CUDA(cudaMemcpyAsync(hK, K, (size_t)5 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
   VO_CUDA(cudaMemcpyAsync(hC, cnt, (size_t)2 * n * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  return VO_OK;
+  };
+
+  if (!ctx->frame_plan) ctx->frame_plan = new FramePlan();
+  FramePlan* fp = ctx->frame_plan;
+  fp->n = n; fp->kc = kc; fp->kps = kps; fp->l0 = l0; fp->r0 = r0; fp->K = K; fp->old_l = old_l; fp->old_r = old_r; fp->dP = dP;
+  fp->dstat = dstat;
+
+  // CUDA graph (vo_frames_use_graph): the first call with a given shape and option set runs as it is (it allocates);
+  // the second one is captured, every later one only uploads its inputs and replays
+  std::vector<unsigned char> key;
+  auto put = [&](const void* q, size_t bytes) { const unsigned char* c = static_cast<const unsigned char*>(q); key.insert(key.end(), c, c + bytes); };
+  const bool want_graph = ctx->frames_graph > 0 && !ctx->prof_enabled;
+  if (want_graph) {
+    const int dims[5] = {n, rows, cols, kc, want_cap};
+    put(dims, sizeof(dims)); put(&so, sizeof(so)); put(&mo, sizeof(mo)); put(&po, sizeof(po)); put(&plan, sizeof(plan));
+  }
+  const bool same = want_graph && fp->g_key == key && fp->g_gen == ctx->alloc_generation;
+  if (same && fp->g_exec != nullptr) {
+    VO_CUDA(cudaGraphLaunch(fp->g_exec, st));
+    ctx->kernel_launches += fp->g_launches;
+  } else if (same) {
+    const long long l0c = ctx->kernel_launches;
+    VO_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    const int rc_cap = enqueue();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e_end = cudaStreamEndCapture(st, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc_cap == VO_OK && e_end == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+      fp->g_exec = exec;
+      fp->g_launches = ctx->kernel_launches - l0c;
+      cudaGraphDestroy(graph);
+      VO_CUDA(cudaGraphLaunch(fp->g_exec, st));
+    } else {   // something in the sequence cannot be captured on this driver: run it the plain way from now on
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+      ctx->frames_graph = -1;
+      ctx->kernel_launches = l0c;
+      VO_TRY(enqueue());
+    }
+  } else {
+    VO_TRY(enqueue());
+    if (fp->g_exec) { cudaGraphExecDestroy(fp->g_exec); fp->g_exec = nullptr; }
+    fp->g_key = key;                       // empty when graphs are off
+    fp->g_gen = ctx->alloc_generation;     // after the allocations of this call
+  }
   VO_CUDA(cudaStreamSynchronize(st));
   for (int k = 0; k < 16; ++k) rel_pose[k] = (k % 5 == 0) ? 1.0 : 0.0;
   status[0] = 0;
@@ -267,6 +322,16 @@ static int frames_landmarks(vo_ctx* ctx, const double* poses, int n, int cap, do
 }
 
 extern "C" {
+int vo_frames_use_graph(vo_ctx* ctx, int enable) {
+  VO_CHECK_ARG(ctx, "ctx is null");
+  ctx->frames_graph = enable ? 1 : 0;
+  return VO_OK;
+}
+int vo_frames_graph_state(vo_ctx* ctx) {
+  if (!ctx) return 0;
+  if (ctx->frames_graph <= 0) return ctx->frames_graph;
+  return (ctx->frame_plan && ctx->frame_plan->g_exec) ? 2 : 1;
+}
 int vo_frames_landmarks(vo_ctx* ctx, const double* poses, int n_frames, int cap, double* landmarks, int* rows) {
   return frames_landmarks(ctx, poses, n_frames, cap, landmarks, rows);
 }

@@ -295,7 +295,7 @@ p3p_hypothesis_kernel(const double* __restrict__ img_base, const double* __restr
                       const int* __restrict__ n_ptr, int cap, const double* __restrict__ K4,
                       uint64_t seed, int max_trials, double tau, double* __restrict__ hyp_cost,
                       int* __restrict__ hyp_ninl, double* __restrict__ hyp_rt, int trial0,
-                      const int* __restrict__ trial_bound) {
+                      const int* __restrict__ trial_bound, const uint64_t* __restrict__ seed_add) {
   const int prob = blockIdx.y;
   const int trial = trial0 + blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -308,7 +308,8 @@ p3p_hypothesis_kernel(const double* __restrict__ img_base, const double* __restr
   const double* world = world_base + (size_t)prob * cap * 3;
   const double K[4] = {K4[0], K4[1], K4[2], K4[3]};
   uint32_t id[4];
-  sample4(seed + (uint64_t)prob * 0x9E3779B97F4A7C15ull, (uint32_t)trial, (uint32_t)n, id);
+  // seed_add: a per-call part of the seed kept in device memory, so a captured launch sequence can be replayed with another one
+  sample4(seed + (seed_add != nullptr ? *seed_add : 0ull) + (uint64_t)prob * 0x9E3779B97F4A7C15ull, (uint32_t)trial, (uint32_t)n, id);
   double f[9], X[9];
   for (int k = 0; k < 3; ++k) {
     const double bx = (img[2 * id[k]] - K[2]) / K[0], by = (img[2 * id[k] + 1] - K[3]) / K[1];
@@ -456,7 +457,7 @@ void fill_p3p_opts(const vo_p3p_opts* in, vo_p3p_opts* o) {
 // Batched device-resident P3P-MSAC.  img: [n_prob][cap][2], world: [n_prob][cap][3], n_dev[n_prob].
 int p3p_batch_device(vo_ctx* ctx, const double* img, const double* world, const int* n_dev, int cap,
                      int n_prob, const double* K4_dev, const vo_p3p_opts& o, double* A_dev,
-                     uint8_t* inliers_dev, int* status_dev, int* info_dev, cudaStream_t st) {
+                     uint8_t* inliers_dev, int* status_dev, int* info_dev, cudaStream_t st, const uint64_t* seed_add_dev) {
   double *hc, *hrt; int* hn;
   VO_TRY(dev_buf(ctx, "p3p_cost", (size_t)n_prob * o.max_num_trials, &hc));
   VO_TRY(dev_buf(ctx, "p3p_ninl", (size_t)n_prob * o.max_num_trials, &hn));
@@ -468,11 +469,11 @@ int p3p_batch_device(vo_ctx* ctx, const double* img, const double* world, const 
   int* bound; VO_TRY(dev_buf(ctx, "p3p_bound", (size_t)n_prob, &bound));
   const int head = o.max_num_trials < P3P_HEAD ? o.max_num_trials : P3P_HEAD;
   p3p_hypothesis_kernel<<<dim3(div_up(head, 4), n_prob), 128, 0, st>>>(img, world, n_dev, cap, K4_dev, o.seed, o.max_num_trials, tau,
-                                                                      hc, hn, hrt, 0, nullptr);
+                                                                      hc, hn, hrt, 0, nullptr, seed_add_dev);
   if (o.max_num_trials > head) {
     p3p_bound_kernel<<<div_up(n_prob, 64), 64, 0, st>>>(n_dev, n_prob, cap, o.max_num_trials, head, o.adaptive, o.confidence, hc, hn, bound);
     p3p_hypothesis_kernel<<<dim3(div_up(o.max_num_trials - head, 4), n_prob), 128, 0, st>>>(
-        img, world, n_dev, cap, K4_dev, o.seed, o.max_num_trials, tau, hc, hn, hrt, head, bound);
+        img, world, n_dev, cap, K4_dev, o.seed, o.max_num_trials, tau, hc, hn, hrt, head, bound, seed_add_dev);
   }
   p3p_select_kernel<<<n_prob, 32, 0, st>>>(img, world, n_dev, cap, K4_dev, o.max_num_trials, tau, o.confidence, o.adaptive,
                                            hc, hn, hrt, A_dev, inliers_dev, status_dev, info_dev);
@@ -649,7 +650,7 @@ int vo_p3p(vo_ctx* ctx, const double* img, const double* world, int n, int col_m
   VO_TRY(dev_buf(ctx, "p3p_inl", (size_t)cap, &dinl));
   VO_TRY(dev_buf(ctx, "p3p_status", 8, &dst));
   const double* dK = d + (size_t)cap * 5;
-  VO_TRY(p3p_batch_device(ctx, d, d + (size_t)2 * cap, (const int*)(dK + 4), cap, 1, dK, o, dA, dinl, dst, dst + 1, st));
+  VO_TRY(p3p_batch_device(ctx, d, d + (size_t)2 * cap, (const int*)(dK + 4), cap, 1, dK, o, dA, dinl, dst, dst + 1, st, nullptr));
   double hA[16]; int hst[4];
   VO_CUDA(cudaMemcpyAsync(hA, dA, sizeof(hA), cudaMemcpyDeviceToHost, st));
   VO_CUDA(cudaMemcpyAsync(hst, dst, sizeof(hst), cudaMemcpyDeviceToHost, st));

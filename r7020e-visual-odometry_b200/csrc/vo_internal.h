@@ -65,6 +65,8 @@ struct vo_ctx {
   int match_float_terms = 3;   // bf16 terms the general-float GEMM of the last call contracted (1 with a score bound)
   long long kernel_launches = 0;   // kernels launched by this context (bench.py's gpu_launches)
   int landmarks_prepared = 0;      // rows of the landmark set converted by vo_landmarks_prepare (0: none)
+  long long alloc_generation = 0;  // bumped whenever a scratch buffer or the SIFT plan is (re)allocated: captured graphs hold the old addresses
+  int frames_graph = 0;            // vo_frames_use_graph: replay the frame loop's launch sequence as a CUDA graph (1: on; -1: capture failed, off)
   bool prof_enabled = false;
   std::vector<vo::ProfStage> prof_stages;
   std::vector<vo::ProfRec> prof_pending;

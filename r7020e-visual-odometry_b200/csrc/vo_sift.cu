@@ -1697,6 +1697,7 @@ static int get_plan(vo_ctx* ctx, int rows, int cols, int batch, const vo_sift_op
     *out = p; return VO_OK;
   }
   if (p) { VO_CUDA(cudaStreamSynchronize(ctx->stream)); sift_plan_destroy(p); ctx->sift_plan = nullptr; }
+  ++ctx->alloc_generation;   // a new plan: new buffer addresses and tensor maps
   if (nl > 5) { set_error("vo_sift: NumLayersInOctave > 5 is not supported"); return VO_ERR_ARG; }
   p = new SiftPlan();
   p->rows = rows; p->cols = cols; p->batch = batch; p->nl = nl; p->sigma = o.sigma;

@@ -18,7 +18,7 @@ int sift_plan_kp_cap(SiftPlan* p);
 void fill_p3p_opts(const vo_p3p_opts* in, vo_p3p_opts* o);
 int p3p_batch_device(vo_ctx* ctx, const double* img, const double* world, const int* n_dev, int cap, int n_prob,
                      const double* K4_dev, const vo_p3p_opts& o, double* A_dev, uint8_t* inliers_dev, int* status_dev,
-                     int* info_dev, cudaStream_t st);
+                     int* info_dev, cudaStream_t st, const uint64_t* seed_add_dev = nullptr);   // seed_add_dev: added to o.seed on the device
 int triangulate_batch_device(const double* pts1, const double* pts2, const int* n_dev, int n_stride, int cap, int n_prob,
                              const double* P_dev, double* xyz, cudaStream_t st);
 int landmarks_device(const vo_keypoint* kps, int kc, const uint32_t* l0, const uint32_t* r0, const int* K0, const double* old_l,

@@ -51,6 +51,36 @@ def test_vo_frames_equals_loop(ctx):
     assert np.array_equal(rel2[1:], rel[3:])
 
 
+def test_frames_graph_replay_is_bit_identical():
+    """vo_frames_use_graph: plain call, captured call, replayed calls (other frames, another first_frame, host and
+    device-resident input, a different batch length in between) return exactly what the plain path returns."""
+    import torch
+    import vo_b200
+    from vo_b200 import vo, synth
+    left, right = _frames(9, seed=21)
+    plain = vo_b200.Context(0)
+    g = vo_b200.Context(0)
+    g.use_frames_graph(True)
+    assert g.frames_graph_state() == 1
+    cases = [(0, 5, 0), (2, 7, 2), (4, 9, 4), (1, 6, 11), (0, 3, 0), (3, 8, 3), (4, 9, 4)]   # (lo, hi, first_frame)
+    states = []
+    for k, (lo, hi, ff) in enumerate(cases):
+        a = vo.run_frames(left[lo:hi], right[lo:hi], synth.KITTI_P0, synth.KITTI_P1, seed=5, first_frame=ff, ctx=plain)
+        if k % 2 == 0:
+            b = vo.run_frames(left[lo:hi], right[lo:hi], synth.KITTI_P0, synth.KITTI_P1, seed=5, first_frame=ff, ctx=g)
+        else:
+            dl, dr = torch.from_numpy(left[lo:hi].copy()).cuda(), torch.from_numpy(right[lo:hi].copy()).cuda()
+            b = vo.run_frames(None, None, synth.KITTI_P0, synth.KITTI_P1, seed=5, first_frame=ff, ctx=g,
+                              device_ptrs=(dl.data_ptr(), dr.data_ptr(), hi - lo, left.shape[1], left.shape[2]))
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), (k, lo, hi)
+        states.append(g.frames_graph_state())
+    # call 0 runs plain, call 1 captures, calls 2-3 replay; the 3-frame batch drops the graph, and the shape has to be
+    # seen twice again before it is replayed
+    assert states[:4] == [1, 2, 2, 2] and states[4] == 1 and states[5] == 1 and states[6] == 2, states
+    assert plain.frames_graph_state() == 0
+
+
 def test_landmark_map_and_png_sequence(ctx, tmp_path):
     """Rows N1 + N3 of SURVEY 8f: the landmark map of VO.m:145-161 (view_3D) built with the GPU
     triangulator equals the oracle-operator run; a PNG sequence decoded by the native reader and run
