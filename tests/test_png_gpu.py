@@ -148,4 +148,14 @@ def test_device_decode_rejects_malformed_files(ctx):
         _decode([wrap(zlib.compress(raw + b"abc", 6))], 40, 64, ctx)
     with pytest.raises(VoError, match="filter"):
         _decode([wrap(zlib.compress(bytes([9]) + raw[1:], 6))], 40, 64, ctx)
+    # a paired-literal entry that straddles the end of the image (odd raw size, two zero literals per table entry), then
+    # end of block and a 60000-byte stored block: the overrun has to be caught at the block end, not after the copy
+    raw0 = bytes(39 * 65)
+    co = zlib.compressobj(6, zlib.DEFLATED, 15, 9, zlib.Z_HUFFMAN_ONLY)
+    zz = co.compress(raw0 + b"\0") + co.flush(zlib.Z_SYNC_FLUSH)
+    zz += bytes([1]) + struct.pack("<HH", 60000, 60000 ^ 0xFFFF) + bytes(60000) + struct.pack(">I", zlib.adler32(raw0))
+    ihdr2 = struct.pack(">IIBBBBB", 64, 39, 8, 0, 0, 0, 0)
+    bad = b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", ihdr2) + _chunk(b"IDAT", zz) + _chunk(b"IEND", b"")
+    with pytest.raises(VoError, match="png 0:"):
+        _decode([bad], 39, 64, ctx)
     assert np.array_equal(_decode([good], 40, 64, ctx)[0], img)     # the context is still healthy
