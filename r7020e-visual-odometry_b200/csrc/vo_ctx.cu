@@ -2,6 +2,10 @@
 #include "vo_internal.h"
 #include <atomic>
 #include <mutex>
+#include <thread>
+#include <vector>
+#include <algorithm>
+#include <cstring>
 #include <utility>
 
 namespace vo {
@@ -56,6 +60,57 @@ ProfScope::~ProfScope() {
   if (!on) return;
   cudaEventRecord(rec.e1, st);
   c->prof_pending.push_back(rec);
+}
+
+
+int upload_2d(vo_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaStream_t st) {
+  if (width == 0 || height == 0) return VO_OK;
+  static const int n_thr_env = [] { const char* e = getenv("VO_UPLOAD_THREADS"); return e ? atoi(e) : 4; }();
+  constexpr size_t SLOT = 2u << 20;
+  cudaPointerAttributes at;
+  bool pageable = false;
+  if (cudaPointerGetAttributes(&at, src) == cudaSuccess) pageable = at.type == cudaMemoryTypeUnregistered;
+  else (void)cudaGetLastError();
+  int n_thr = n_thr_env;
+  const unsigned hw = std::thread::hardware_concurrency();
+  if (hw > 0 && (unsigned)n_thr > hw) n_thr = (int)hw;
+  if ((size_t)n_thr > height) n_thr = (int)height;
+  if (!pageable || n_thr < 2 || width * height < (8u << 20) || width > SLOT) {
+    VO_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice, st));
+    return VO_OK;
+  }
+  uint8_t* stage; VO_TRY(pin_buf(ctx, "upload_stage", (size_t)n_thr * 2 * SLOT, &stage));
+  while (ctx->upload_events.size() < (size_t)n_thr * 2) {
+    cudaEvent_t e; VO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->upload_events.push_back(e);
+    ctx->upload_pending.push_back(0);
+  }
+  const size_t rows_per_slot = SLOT / width;       // >= 1
+  std::vector<int> rc(n_thr, (int)cudaSuccess);
+  std::vector<std::thread> pool;
+  const int device = ctx->device;
+  for (int t = 0; t < n_thr; ++t) {
+    pool.emplace_back([&, t]() {
+      cudaSetDevice(device);
+      const size_t r0 = height * t / n_thr, r1 = height * (t + 1) / n_thr;
+      int k = 0;
+      for (size_t r = r0; r < r1; r += rows_per_slot, k ^= 1) {
+        const size_t nr = std::min(rows_per_slot, r1 - r);
+        uint8_t* slot = stage + ((size_t)t * 2 + k) * SLOT;
+        cudaEvent_t ev = ctx->upload_events[(size_t)t * 2 + k];
+        char& pending = ctx->upload_pending[(size_t)t * 2 + k];   // (also set by an earlier call: left, then right images)
+        if (pending) { const cudaError_t e = cudaEventSynchronize(ev); if (e != cudaSuccess) { rc[t] = (int)e; return; } }
+        for (size_t q = 0; q < nr; ++q) memcpy(slot + q * width, static_cast<const uint8_t*>(src) + (r + q) * spitch, width);
+        cudaError_t e = cudaMemcpy2DAsync(static_cast<uint8_t*>(dst) + r * dpitch, dpitch, slot, width, width, nr, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ev, st);
+        if (e != cudaSuccess) { rc[t] = (int)e; return; }
+        pending = 1;
+      }
+    });
+  }
+  for (auto& th : pool) th.join();
+  for (int t = 0; t < n_thr; ++t) VO_CUDA((cudaError_t)rc[t]);
+  return VO_OK;
 }
 
 }  // namespace vo
@@ -172,6 +227,7 @@ void vo_ctx_destroy(vo_ctx* c) {
   if (c->frame_plan) vo::frame_plan_destroy(c->frame_plan);
   c->prof_collect();
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->upload_events) cudaEventDestroy(e);
   for (auto& kv : c->scratch) {
     if (!kv.second.ptr) continue;
     if (kv.second.host) cudaFreeHost(kv.second.ptr);

@@ -93,12 +93,17 @@ static int frames_core(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, i
   uint8_t* dimg = sift_plan_images(plan);
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   if (opts && opts->col_major) {   // MATLAB H x W x N stacks: staged as they are, transposed on the device
-    VO_TRY(sift_load_col_major(plan, 0, 2, left, n, on_device != 0, st));
-    VO_TRY(sift_load_col_major(plan, 1, 2, right, n, on_device != 0, st));
+    VO_TRY(sift_load_col_major(ctx, plan, 0, 2, left, n, on_device != 0, st));
+    VO_TRY(sift_load_col_major(ctx, plan, 1, 2, right, n, on_device != 0, st));
     ctx->kernel_launches += 2;
   } else {
-    VO_CUDA(cudaMemcpy2DAsync(dimg, 2 * img_bytes, left, img_bytes, img_bytes, n, kind, st));
-    VO_CUDA(cudaMemcpy2DAsync(dimg + img_bytes, 2 * img_bytes, right, img_bytes, img_bytes, n, kind, st));
+    if (on_device) {
+      VO_CUDA(cudaMemcpy2DAsync(dimg, 2 * img_bytes, left, img_bytes, img_bytes, n, kind, st));
+      VO_CUDA(cudaMemcpy2DAsync(dimg + img_bytes, 2 * img_bytes, right, img_bytes, img_bytes, n, kind, st));
+    } else {   // pageable stacks go through threaded pinned staging
+      VO_TRY(upload_2d(ctx, dimg, 2 * img_bytes, left, img_bytes, img_bytes, n, st));
+      VO_TRY(upload_2d(ctx, dimg + img_bytes, 2 * img_bytes, right, img_bytes, img_bytes, n, st));
+    }
   }
   const float* desc = sift_plan_desc(plan);
   const vo_keypoint* kps = sift_plan_keypoints(plan);

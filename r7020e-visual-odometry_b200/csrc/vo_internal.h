@@ -66,6 +66,8 @@ struct vo_ctx {
   long long kernel_launches = 0;   // kernels launched by this context (bench.py's gpu_launches)
   int landmarks_prepared = 0;      // rows of the landmark set converted by vo_landmarks_prepare (0: none)
   long long alloc_generation = 0;  // bumped whenever a scratch buffer or the SIFT plan is (re)allocated: captured graphs hold the old addresses
+  std::vector<cudaEvent_t> upload_events;   // upload_2d: two staging slots per worker thread, one event each ...
+  std::vector<char> upload_pending;         // ... and whether a DMA out of the slot has been queued (it must finish before the slot is refilled)
   int frames_graph = 0;            // vo_frames_use_graph: replay the frame loop's launch sequence as a CUDA graph (1: on; -1: capture failed, off)
   bool prof_enabled = false;
   std::vector<vo::ProfStage> prof_stages;
@@ -115,6 +117,12 @@ static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 int ensure_dyn_smem(const void* func, size_t bytes);
 template <typename F>
 inline int ensure_dyn_smem_of(F* func, size_t bytes) { return ensure_dyn_smem(reinterpret_cast<const void*>(func), bytes); }
+
+// cudaMemcpy2DAsync(host -> device) for big inputs in PAGEABLE host memory (a MATLAB array, a NumPy array): a few host
+// threads copy row groups into pinned staging slots and queue the DMA of each slot behind them, so the copy runs at the
+// speed of several cores' memcpy instead of one staged stream.  Pinned or small sources go straight to
+// cudaMemcpy2DAsync.  On return the source has been read completely (as with a pageable cudaMemcpyAsync).
+int upload_2d(vo_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaStream_t st);
 
 // RAII bracket around one or more launches of a stage
 struct ProfScope {

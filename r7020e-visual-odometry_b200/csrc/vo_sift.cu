@@ -1906,11 +1906,11 @@ int sift_prepare(vo_ctx* ctx, int rows, int cols, int batch, const vo_sift_opts*
 }
 uint8_t* sift_plan_images(SiftPlan* p) { return p->img; }
 // n MATLAB-ordered images (contiguous, rows*cols bytes each) -> plan images first_img, first_img + img_step, ...
-int sift_load_col_major(SiftPlan* p, int first_img, int img_step, const uint8_t* src, int n, bool on_device, cudaStream_t st) {
+int sift_load_col_major(vo_ctx* ctx, SiftPlan* p, int first_img, int img_step, const uint8_t* src, int n, bool on_device, cudaStream_t st) {
   const size_t ib = (size_t)p->rows * p->cols;
   const uint8_t* stage = src;
   if (!on_device) {
-    VO_CUDA(cudaMemcpy2DAsync(p->img_t + (size_t)first_img * ib, (size_t)img_step * ib, src, ib, ib, n, cudaMemcpyHostToDevice, st));
+    VO_TRY(upload_2d(ctx, p->img_t + (size_t)first_img * ib, (size_t)img_step * ib, src, ib, ib, n, st));
     stage = p->img_t + (size_t)first_img * ib;
   }
   const size_t sstep = on_device ? ib : (size_t)img_step * ib;

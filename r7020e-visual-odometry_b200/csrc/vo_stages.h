@@ -9,7 +9,7 @@ int sift_prepare(vo_ctx* ctx, int rows, int cols, int batch, const vo_sift_opts*
 int sift_run_device(vo_ctx* ctx, SiftPlan* p, int batch, const vo_sift_opts& o, cudaStream_t st);
 uint8_t* sift_plan_images(SiftPlan* p);
 // MATLAB-ordered images (element (r,c) at src[c*rows + r]) staged in the plan -> the plan's row-major image buffer
-int sift_load_col_major(SiftPlan* p, int first_img, int img_step, const uint8_t* src, int n, bool on_device, cudaStream_t st);
+int sift_load_col_major(vo_ctx* ctx, SiftPlan* p, int first_img, int img_step, const uint8_t* src, int n, bool on_device, cudaStream_t st);
 vo_keypoint* sift_plan_keypoints(SiftPlan* p);
 float* sift_plan_desc(SiftPlan* p);
 int* sift_plan_counters(SiftPlan* p);   // counters[img*4 + 2] = keypoints of image img

@@ -81,6 +81,26 @@ def test_frames_graph_replay_is_bit_identical():
     assert plain.frames_graph_state() == 0
 
 
+def test_pageable_stacks_take_the_staged_upload(ctx):
+    """Host stacks of 8 MB and more in pageable memory (a MATLAB or NumPy array) are uploaded through threaded pinned
+    staging (upload_2d); row-major and column-major stacks give what the device-resident call gives."""
+    import torch
+    from vo_b200 import vo, synth
+    left, right = _frames(20, h=376, w=1241, seed=31)          # 9.3 MB per side
+    dl, dr = torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()
+    ref = vo.run_frames(None, None, synth.KITTI_P0, synth.KITTI_P1, seed=3, ctx=ctx,
+                        device_ptrs=(dl.data_ptr(), dr.data_ptr(), 20, 376, 1241))
+    for rep in range(2):                                       # the second call re-uses staging slots that were in flight
+        got = vo.run_frames(left, right, synth.KITTI_P0, synth.KITTI_P1, seed=3, ctx=ctx)
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b)
+    lt = np.ascontiguousarray(left.transpose(0, 2, 1)); rt = np.ascontiguousarray(right.transpose(0, 2, 1))
+    got = vo.run_frames(lt, rt, synth.KITTI_P0, synth.KITTI_P1, seed=3, ctx=ctx, col_major=True)
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+    assert (ref[1][1:] == 0).all()
+
+
 def test_landmark_map_and_png_sequence(ctx, tmp_path):
     """Rows N1 + N3 of SURVEY 8f: the landmark map of VO.m:145-161 (view_3D) built with the GPU
     triangulator equals the oracle-operator run; a PNG sequence decoded by the native reader and run
