@@ -10,6 +10,7 @@
 // To stream a sequence call with overlapping stacks: frames [i0-1, i0+B) and 'FirstFrame', i0-1.
 // One H2D copy of the stacks (transposed on the device), one synchronisation, no CPU fallback.
 #include "mex_common.h"
+#include <stdlib.h>
 
 static void read_P(const mxArray* a, double P[12], const char* nm) {
   if (mxGetClassID(a) != mxDOUBLE_CLASS) mexErrMsgIdAndTxt("vo:frames:class", "%s must be double", nm);
@@ -57,7 +58,13 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   mxArray* st = mxCreateNumericMatrix(n, 1, mxINT32_CLASS, mxREAL);
   mxArray* cn = mxCreateNumericMatrix(8, n, mxINT32_CLASS, mxREAL);
   double* A = mxGetPr(plhs[0]);
-  vo_mex_check(vo_frames(vo_mex_ctx("vo_frames_mex"), (const uint8_t*)mxGetData(prhs[0]), (const uint8_t*)mxGetData(prhs[1]), n,
+  vo_ctx* ctx = vo_mex_ctx("vo_frames_mex");
+  {   // a MATLAB loop feeds one stack at a time on one stream: replay the launch sequence as a CUDA graph (bit-identical;
+      // VO_FRAMES_GRAPH=0 in the environment keeps plain launches)
+    static const bool graph = [] { const char* e = getenv("VO_FRAMES_GRAPH"); return !(e && atoi(e) == 0); }();
+    if (graph && vo_frames_graph_state(ctx) == 0) vo_frames_use_graph(ctx, 1);
+  }
+  vo_mex_check(vo_frames(ctx, (const uint8_t*)mxGetData(prhs[0]), (const uint8_t*)mxGetData(prhs[1]), n,
                          rows, cols, P1, P2, &o, A, (int*)mxGetData(st), (int*)mxGetData(cn)), "vo:frames:cuda");
   for (int k = 0; k < n; ++k) {           // row-major 4x4 -> MATLAB column-major
     double* a = A + 16 * k;
