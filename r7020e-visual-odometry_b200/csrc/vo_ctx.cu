@@ -89,7 +89,9 @@ int upload_2d(vo_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spi
   std::vector<int> rc(n_thr, (int)cudaSuccess);
   std::vector<std::thread> pool;
   const int device = ctx->device;
-  for (int t = 0; t < n_thr; ++t) {
+  bool spawn_failed = false;
+  for (int t = 0; t < n_thr && !spawn_failed; ++t) {
+    try {
     pool.emplace_back([&, t]() {
       cudaSetDevice(device);
       const size_t r0 = height * t / n_thr, r1 = height * (t + 1) / n_thr;
@@ -107,9 +109,11 @@ int upload_2d(vo_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spi
         pending = 1;
       }
     });
+    } catch (...) { spawn_failed = true; }   // no thread to be had (resource limits): the rows are copied the plain way below
   }
   for (auto& th : pool) th.join();
   for (int t = 0; t < n_thr; ++t) VO_CUDA((cudaError_t)rc[t]);
+  if (spawn_failed) VO_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice, st));
   return VO_OK;
 }
 
