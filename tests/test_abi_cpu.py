@@ -35,6 +35,17 @@ def test_no_cpu_fallback():
         vo_b200.Context(0)
 
 
+def test_null_context_is_rejected_by_the_state_entry_points():
+    """Entry points that only touch context state answer a null context with an error, not a crash."""
+    import ctypes as C
+    from vo_b200 import _lib
+    L = _lib.lib()
+    assert L.vo_frames_use_graph(None, 1) != 0 and b"null" in L.vo_last_error()
+    assert L.vo_frames_graph_state(None) == 0
+    stats = (C.c_int * 4)()
+    assert L.vo_match_stats(None, stats) != 0
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "r7020e-visual-odometry_b200")
     for dp, _, files in os.walk(pkg):
