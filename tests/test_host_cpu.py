@@ -271,3 +271,25 @@ def test_bench_oracle_row_checker_equals_the_oracle():
     finally:
         if bench._POOL is not None:
             bench._POOL.terminate(); bench._POOL = None
+
+
+def test_one_term_match_margin_covers_the_worst_bf16_rounding():
+    """The general-float match contracts the bf16 high halves alone when a score bound decides the rows and certifies with
+    |approx - exact| <= (1/128 + 1/2048) ||a|| ||b|| (csrc/vo_match.cu: ONE_TERM_EPS).  The worst case -- every element just
+    below a bf16 rounding midpoint, all products of one sign -- stays inside it, as do random and scaled inputs."""
+    def bf16(x):
+        u = x.astype(np.float32).view(np.uint32).astype(np.uint64)
+        return (((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16).astype(np.uint32).view(np.float32)
+    eps = 1.0 / 128 + 1.0 / 2048
+    rng = np.random.default_rng(0)
+    m = np.float32(1 + 2.0 ** -8 * (1 - 1e-4))
+    sets = [(np.full((4, 128), m, np.float32), np.full((4, 128), m, np.float32)),
+            (np.abs(rng.standard_normal((500, 128))).astype(np.float32), np.abs(rng.standard_normal((500, 128))).astype(np.float32)),
+            ((rng.standard_normal((500, 128)) * 300).astype(np.float32), (rng.standard_normal((500, 128)) * 0.01).astype(np.float32))]
+    worst = 0.0
+    for a, b in sets:
+        exact = np.einsum("ik,ik->i", a.astype(np.float64), b.astype(np.float64))
+        approx = np.einsum("ik,ik->i", bf16(a).astype(np.float64), bf16(b).astype(np.float64))
+        rel = np.abs(approx - exact) / (np.linalg.norm(a.astype(np.float64), axis=1) * np.linalg.norm(b.astype(np.float64), axis=1))
+        worst = max(worst, float(rel.max()))
+    assert 0.0077 < worst < eps, worst      # the adversarial rows reach 2^-7; the margin keeps 6 % of room
