@@ -102,6 +102,35 @@ def test_match_vs_float64_bruteforce():
     assert pairs.dtype == np.uint32 and metric.dtype == np.float32
 
 
+def test_match_vs_opencv_bfmatcher():
+    """An independent implementation of the exhaustive matcher: cv2.BFMatcher (L2, k = 2) on unit-normalised rows, with the
+    matchFeatures rules applied to its distances (SSD = d^2 <= 0.04, SSD ratio <= 0.6).  Same pairs as the oracle, except
+    rows whose decision sits within rounding of a threshold; the metrics agree to float precision."""
+    cv2 = pytest.importorskip("cv2")
+    from conftest import correlated_pair
+    f1, f2 = correlated_pair(1500, 1800, seed=5)
+    pairs, metric = oracle.match(f1, f2)
+    u1 = (f1 / np.linalg.norm(f1, axis=1, keepdims=True)).astype(np.float32)
+    u2 = (f2 / np.linalg.norm(f2, axis=1, keepdims=True)).astype(np.float32)
+    knn = cv2.BFMatcher(cv2.NORM_L2).knnMatch(u1, u2, k=2)
+    cv_pairs, cv_metric, near = [], [], set()
+    for i, (a, b) in enumerate(knn):
+        s1, s2 = a.distance ** 2, b.distance ** 2
+        if min(abs(s1 - 0.04), abs(s1 / max(s2, 1e-6) - 0.6)) < 1e-4:
+            near.add(i)
+        if s1 <= 0.04 and s1 / max(s2, 1e-6) <= 0.6:
+            cv_pairs.append((i, a.trainIdx)); cv_metric.append(s1)
+    mine = {int(i): (int(j), float(m)) for (i, j), m in zip(pairs, metric)}
+    theirs = {i: (j, m) for (i, j), m in zip(cv_pairs, cv_metric)}
+    assert len(theirs) > 300
+    for i in set(mine) | set(theirs):
+        if i in near:
+            continue
+        assert i in mine and i in theirs, i
+        assert mine[i][0] == theirs[i][0]
+        assert abs(mine[i][1] - theirs[i][1]) < 2e-5
+
+
 def test_match_semantics_edge_cases():
     rng = np.random.default_rng(1)
     f = np.rint(np.abs(rng.normal(0, 40, (6, 128)))).astype(np.float32)
