@@ -211,6 +211,36 @@ def test_p3p_and_msac():
     assert same["best_trial"] == r["best_trial"] and np.array_equal(same["A"], r["A"])   # seeded => reproducible
 
 
+def test_msac_pose_vs_opencv_solvepnpransac():
+    """estworldpose end to end against an independent robust estimator: cv2.solvePnPRansac (P3P minimal solver, 1 px
+    reprojection threshold) on KITTI-like data with 30 % outliers.  Different samplers and scorings, so the comparison is
+    what a user sees: the same pose (to the noise level) and the same inlier set (up to borderline points)."""
+    cv2 = pytest.importorskip("cv2")
+    K4 = np.array([718.856, 718.856, 607.1928, 185.2157])
+    Km = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1.0]])
+    rng = np.random.default_rng(12)
+    for trial in range(5):
+        n = 400
+        R = cv2.Rodrigues(rng.normal(0, 0.03, 3))[0]; t = np.array([rng.normal(0, 0.1), rng.normal(0, 0.05), -rng.uniform(0.3, 1.5)])
+        Xw = np.c_[rng.uniform(-15, 15, n), rng.uniform(-3, 2, n), rng.uniform(5, 60, n)]
+        Xc = Xw @ R.T + t
+        uv = np.c_[K4[0] * Xc[:, 0] / Xc[:, 2] + K4[2], K4[1] * Xc[:, 1] / Xc[:, 2] + K4[3]] + rng.normal(0, 0.15, (n, 2))
+        out = rng.random(n) < 0.3
+        uv[out] += rng.normal(0, 40, (int(out.sum()), 2))
+        r = oracle.p3p(uv, Xw, K4, seed=trial)
+        ok, rv, tv, inl = cv2.solvePnPRansac(Xw, uv, Km, None, iterationsCount=1000, reprojectionError=1.0, confidence=0.99,
+                                             flags=cv2.SOLVEPNP_P3P)
+        assert ok and r["status"] == 0
+        Rc = cv2.Rodrigues(rv)[0]
+        A_cv = np.eye(4); A_cv[:3, :3] = Rc.T; A_cv[:3, 3] = (-Rc.T @ tv).ravel()      # camera pose in the world, as estworldpose returns it
+        assert np.abs(r["A"][:3, :3] - A_cv[:3, :3]).max() < 2e-3
+        assert np.linalg.norm(r["A"][:3, 3] - A_cv[:3, 3]) < 0.05
+        cv_in = np.zeros(n, bool); cv_in[inl.ravel()] = True
+        both = (r["inliers"] & cv_in).sum()
+        assert both > 0.9 * max(r["inliers"].sum(), cv_in.sum())
+        assert not (r["inliers"] & out & (np.linalg.norm(uv - (np.c_[K4[0] * Xc[:, 0] / Xc[:, 2] + K4[2], K4[1] * Xc[:, 1] / Xc[:, 2] + K4[3]]), axis=1) > 5)).any()
+
+
 def test_p3p_solutions_equal_opencv_solvep3p():
     """The oracle's P3P (Gao) against OpenCV's solveP3P on 200 three-point problems: the same number of
     solutions, and each of them equal to 1e-5 (golden vectors: tests/golden/p3p_cv2.npz)."""
