@@ -276,3 +276,33 @@ def test_find_remaining_points_index_chain():
     assert np.array_equal(c["l_pos"], o["l_pos"]) and np.array_equal(c["r_pos"], o["r_pos"])
     assert np.array_equal(c["l_pos"] + 0.5, c["r_pos"])
     assert ks[3] == len(expect) and len(c["l_desc"]) == len(o["r_desc"]) == len(expect)
+
+
+def test_oracle_trajectory_vs_an_opencv_operator_loop():
+    """The whole path against independent implementations: the reference's loop (vo.VisualOdometry, the line-by-line
+    mirror of VO.m) with every toolbox call answered by OpenCV (tests/cv2_ops.py: cv2.SIFT, BFMatcher + matchFeatures
+    rules, triangulatePoints, solvePnPRansac) on the first 16 rendered street frames, against the oracle's golden
+    trajectory (tests/golden/street_oracle_225.npz).  Same number of tracked points per frame to within 1 %, relative
+    poses equal to the scatter of two RANSAC samplers (centimetres / hundredths of a degree over 0.86 m steps)."""
+    pytest.importorskip("cv2")
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from vo_b200 import vo, synth
+    from cv2_ops import Cv2Ops
+    g = np.load(os.path.join(G, "street_oracle_225.npz"))
+    n = 16
+    left, right, gt = bench.street_frames(n)
+    v = vo.VisualOdometry(synth.KITTI_P0, synth.KITTI_P1, Cv2Ops(seed=1))
+    dts, dRs = [], []
+    for i in range(n):
+        a = v.step(left[i], right[i])
+        if i == 0:
+            continue
+        o = g["rel"][i]
+        assert v.log[-1]["status"] == 0 and g["status"][i] == 0
+        assert abs(int(v.log[-1]["k4"]) - int(g["tracked"][i - 1])) <= max(5, 0.01 * g["tracked"][i - 1])
+        dts.append(np.linalg.norm(a[:3, 3] - o[:3, 3]))
+        dRs.append(np.degrees(np.arccos(np.clip((np.trace(a[:3, :3].T @ o[:3, :3]) - 1) / 2, -1, 1))))
+    assert max(dts) < 0.06 and np.median(dts) < 0.02, dts          # metres per 0.86 m step
+    assert max(dRs) < 0.2 and np.median(dRs) < 0.06, dRs          # degrees
