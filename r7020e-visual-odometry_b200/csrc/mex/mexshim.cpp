@@ -56,7 +56,7 @@ int mxGetString(const mxArray* a, char* buf, mwSize buflen) {
 mxArray* mxCreateNumericMatrix(mwSize m, mwSize n, mxClassID cls, mxComplexity) {
   mxArray* a = (mxArray*)malloc(sizeof(mxArray));
   a->cls = cls; a->m = m; a->n = n; a->ndim = 2; a->dims[0] = m; a->dims[1] = n; a->dims[2] = a->dims[3] = 1;
-  a->data = calloc(m * n ? m * n : 1, elem_size(cls));
+  a->data = calloc((m * n) != 0 ? m * n : 1, elem_size(cls));
   return a;
 }
 mxArray* mxCreateNumericArray(mwSize ndim, const mwSize* dims, mxClassID cls, mxComplexity c) {
