@@ -310,8 +310,8 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     # frames per step: a multiple of the core count (incl. the halo frame) sized so that the whole run stays
-    # within a few minutes (one round of `cores` frames takes ~4.5 s of wall time)
-    rounds = max(1, int(150.0 / (4.5 * max(args.steps + args.warmup, 1))))
+    # within a few minutes (one round of `cores` frames takes about 2.2 s of wall time on the GPU box's host)
+    rounds = max(1, int(150.0 / (2.2 * max(args.steps + args.warmup, 1))))
     n = min(cores * rounds, 385) - 1
     left, right, gt = street_frames(n + 1)
     log(f"reference arm: {n} frames (+1 halo) per step on {cores} processes")

@@ -17,6 +17,9 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#if defined(__AVX2__) && defined(__FMA__)
+#include <immintrin.h>
+#endif
 
 static float* to_row_major(const float* f, int n, int dim, int col_major) {
   float* r = (float*)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1) * dim);
@@ -45,23 +48,61 @@ static float ssd_unit(const float* a, float inva, const float* b, float invb, in
   return s < 0.f ? 0.f : s;
 }
 
+/* The scores of row a against all columns.  Each dot product is the same sequential fmaf chain as in ssd_unit(); with
+ * AVX2 + FMA, 32 columns advance together (four vectors of eight lanes: one fused multiply-add per lane and k, in the
+ * same order), which hides the latency of the chain without touching a single rounding.  Bt is B in blocks of eight
+ * columns: Bt[(j / 8) * dim * 8 + k * 8 + j % 8]. */
+static void scores_row(const float* a, float inva, const float* B, const float* Bt, const float* invb, int n2, int dim, float* s) {
+  int j = 0;
+#if defined(__AVX2__) && defined(__FMA__)
+  const __m256 m2 = _mm256_set1_ps(-2.0f), two = _mm256_set1_ps(2.0f), zero = _mm256_setzero_ps(), via = _mm256_set1_ps(inva);
+  for (; j + 32 <= n2; j += 32) {
+    const float* p = Bt + (size_t)(j / 8) * dim * 8;
+    __m256 c0 = zero, c1 = zero, c2 = zero, c3 = zero;
+    for (int k = 0; k < dim; ++k) {
+      const __m256 va = _mm256_set1_ps(a[k]);
+      c0 = _mm256_fmadd_ps(va, _mm256_loadu_ps(p + (size_t)k * 8), c0);
+      c1 = _mm256_fmadd_ps(va, _mm256_loadu_ps(p + (size_t)dim * 8 + (size_t)k * 8), c1);
+      c2 = _mm256_fmadd_ps(va, _mm256_loadu_ps(p + (size_t)dim * 16 + (size_t)k * 8), c2);
+      c3 = _mm256_fmadd_ps(va, _mm256_loadu_ps(p + (size_t)dim * 24 + (size_t)k * 8), c3);
+    }
+    __m256 acc[4] = {c0, c1, c2, c3};
+    for (int q = 0; q < 4; ++q) {
+      const __m256 key = _mm256_mul_ps(acc[q], _mm256_loadu_ps(invb + j + 8 * q));
+      const __m256 c = _mm256_mul_ps(key, via);
+      const __m256 sc = _mm256_fmadd_ps(m2, c, two);
+      /* s < 0 ? 0 : s  (a NaN stays a NaN, as in the scalar form) */
+      _mm256_storeu_ps(s + j + 8 * q, _mm256_blendv_ps(sc, zero, _mm256_cmp_ps(sc, zero, _CMP_LT_OQ)));
+    }
+  }
+#endif
+  (void)Bt;
+  for (; j < n2; ++j) s[j] = ssd_unit(a, inva, B + (size_t)j * dim, invb[j], dim);
+}
+
 static void top2_rows(const float* A, int n1, const float* B, int n2, int dim,
                       uint32_t* j1, float* s1, float* s2) {
   float* invb = (float*)malloc(sizeof(float) * (size_t)(n2 > 0 ? n2 : 1));
   for (int j = 0; j < n2; ++j) invb[j] = inv_norm(B + (size_t)j * dim, dim);
+  const int nb = n2 / 8;
+  float* Bt = (float*)malloc(sizeof(float) * (size_t)(nb > 0 ? nb : 1) * dim * 8);
+  for (int j = 0; j < nb * 8; ++j)
+    for (int k = 0; k < dim; ++k) Bt[(size_t)(j / 8) * dim * 8 + (size_t)k * 8 + (j % 8)] = B[(size_t)j * dim + k];
+  float* s = (float*)malloc(sizeof(float) * (size_t)(n2 > 0 ? n2 : 1));
   for (int i = 0; i < n1; ++i) {
     const float* a = A + (size_t)i * dim;
     float inva = inv_norm(a, dim);
     float b1 = INFINITY, b2 = INFINITY;
     uint32_t bj = UINT32_MAX;
+    scores_row(a, inva, B, Bt, invb, n2, dim, s);
     for (int j = 0; j < n2; ++j) {
-      float s = ssd_unit(a, inva, B + (size_t)j * dim, invb[j], dim);
-      if (s < b1) { b2 = b1; b1 = s; bj = (uint32_t)j; }
-      else if (s < b2) { b2 = s; }
+      const float sj = s[j];
+      if (sj < b1) { b2 = b1; b1 = sj; bj = (uint32_t)j; }
+      else if (sj < b2) { b2 = sj; }
     }
     j1[i] = bj; s1[i] = b1; s2[i] = b2;
   }
-  free(invb);
+  free(s); free(Bt); free(invb);
 }
 
 void vo_oracle_match_top2(const float* f1, int n1, const float* f2, int n2, int dim,
